@@ -1,0 +1,144 @@
+"""CPU tests: the oracle against the reference-generated golden vectors (in-tree pieces) and the
+published structural constants (third-party pieces)."""
+import numpy as np
+import pytest
+import torch as th
+
+from oracle import guidance as og
+from oracle import diffusion as od
+from oracle.unet import UNetModel, config_for, tiny_config, seeded_init_
+from oracle.clip_vit import VIT_CONFIGS, CLIPVisualOnly, ViTConfig
+
+
+def T(a):
+    return th.from_numpy(np.asarray(a))
+
+
+def test_losses_match_reference_goldens(golden):
+    g = golden
+    assert np.allclose(og.spherical_dist_loss(T(g["sph_small_x"]), T(g["sph_small_y"])).numpy(), g["sph_small"], atol=1e-7)
+    assert abs(float(g["sph_small"][0]) - 0.49663094) < 1e-6
+    img = T(g["img_small"])
+    assert np.allclose(og.range_loss(img).numpy(), g["range_small"], atol=1e-7)
+    assert np.allclose(og.tv_loss(img).numpy(), g["tv_small"], atol=1e-6)
+    assert np.allclose(g["range_small"], [0.64526457, 0.58686501], atol=1e-6)
+    assert np.allclose(g["tv_small"], [7.11696005, 7.48520803], atol=1e-5)
+
+
+def test_loss_gradients_match_reference_goldens(golden):
+    g = golden
+    img = T(g["img_med"]).requires_grad_()
+    r, t = og.range_loss(img), og.tv_loss(img)
+    assert np.allclose(r.detach().numpy(), g["range_med"], atol=1e-7)
+    assert np.allclose(t.detach().numpy(), g["tv_med"], atol=1e-6)
+    assert np.allclose(th.autograd.grad(r.sum(), img, retain_graph=True)[0].numpy(), g["range_med_grad"], atol=1e-8)
+    assert np.allclose(th.autograd.grad(t.sum(), img)[0].numpy(), g["tv_med_grad"], atol=1e-7)
+    emb = T(g["sph_emb"]).requires_grad_()
+    d = og.spherical_dist_loss(emb.unsqueeze(0), T(g["sph_tgt"]).unsqueeze(0))
+    assert np.allclose(d.detach().numpy(), g["sph_med"], atol=1e-6)
+    assert np.allclose(th.autograd.grad(d.sum(), emb)[0].numpy(), g["sph_med_grad"], atol=1e-6)
+
+
+def test_cutout_coordinate_law(golden):
+    th.manual_seed(0)
+    c = og.MakeCutouts(224, 4, 1.0)._generate_coords(256, 256, 4)
+    assert np.array_equal(np.array(c), golden["coords_256_seed0"])
+    assert c == [(9, 11, 239), (26, 6, 228), (1, 1, 239), (12, 11, 244)]
+    th.manual_seed(0)
+    c = og.MakeCutouts(224, 6, 0.5)._generate_coords(512, 512, 6)
+    assert np.array_equal(np.array(c), golden["coords_512_pow05_seed0"])
+    # 64^2 checkpoints: min == max == 64 -> whole-image window
+    assert og.MakeCutouts(224, 3)._generate_coords(64, 64, 3) == [(0, 0, 64)] * 3
+
+
+def test_cutouts_values_and_grad(golden):
+    g = golden
+    src = T(g["cut_src"]).requires_grad_()
+    coords = [tuple(int(v) for v in r) for r in g["cut_coords"]]
+    cut = og.MakeCutouts(32, 3)(src, coords=coords)
+    assert cut.shape == (6, 3, 32, 32)
+    assert np.allclose(cut.detach().numpy(), g["cut_out"], atol=1e-6)
+    grad = th.autograd.grad((cut * T(g["cut_wgt"])).sum(), src)[0]
+    assert np.allclose(grad.numpy(), g["cut_grad"], atol=1e-5)
+    th.manual_seed(3)  # same CPU-RNG draws as the reference run
+    cut2 = og.MakeCutouts(32, 3)(src.detach())
+    assert np.allclose(cut2.numpy(), g["cut_out"], atol=1e-6)
+    up = og.MakeCutouts(56, 2)(T(g["cut_up_src"]), coords=[tuple(int(v) for v in r) for r in g["cut_up_coords"]])
+    assert np.allclose(up.numpy(), g["cut_up_out"], atol=1e-6)
+
+
+def test_reference_test_make_cutouts_shape():
+    # /root/reference/test.py:233-249: [1,3,512,512], cut 224, cutn 8, pow 0.5 -> [8,3,224,224]
+    out = og.MakeCutouts(224, 8, 0.5)(th.rand(1, 3, 512, 512))
+    assert out.shape == (8, 3, 224, 224)
+
+
+def test_schedule_constants():
+    # SURVEY Appendix E (derived from the published formulas)
+    d = od.create_gaussian_diffusion(1000, "linear", "25")
+    assert d.timestep_map[:4] == [0, 42, 83, 125] and d.timestep_map[-3:] == [916, 957, 999]
+    assert abs(d.betas[0] - 1e-4) < 1e-12 and abs(d.betas[24] - 0.5643942) < 1e-6
+    s = d.sqrt_one_minus_alphas_cumprod
+    assert abs(s[0] - 0.010000) < 1e-6 and abs(s[12] - 0.960314) < 1e-5 and abs(s[24] - 0.99997982) < 1e-7
+    assert abs(d.posterior_variance[1] - 9.95564e-5) < 1e-9
+    d = od.create_gaussian_diffusion(1000, "linear", "ddim250")
+    assert d.timestep_map[:3] == [0, 4, 8] and d.timestep_map[-1] == 996 and d.num_timesteps == 250
+    assert abs(d.betas[249] - 7.729432e-2) < 1e-7 and abs(d.sqrt_one_minus_alphas_cumprod[249] - 0.99997856) < 1e-7
+    d = od.create_gaussian_diffusion(1000, "linear", "1000")
+    assert abs(d.betas[999] - 0.02) < 1e-12 and abs(d.posterior_variance[1] - 5.453188e-5) < 1e-10
+    d = od.create_gaussian_diffusion(1000, "cosine", "1000")
+    assert abs(d.betas[0] - 4.128422e-5) < 1e-9 and d.betas[999] == 0.999
+    assert abs(d.sqrt_one_minus_alphas_cumprod[500] - 0.712541) < 1e-5
+
+
+def _nparams(m):
+    return sum(p.numel() for p in m.parameters())
+
+
+@pytest.mark.parametrize("size,cond,expect", [(64, True, 295.9e6), (256, True, 553.8e6), (256, False, 552.8e6),
+                                              (512, True, 559.0e6), (128, True, 421.5e6)])
+def test_unet_param_counts(size, cond, expect):
+    with th.device("meta"):
+        m = UNetModel(config_for(size, cond))
+    assert abs(_nparams(m) - expect) < 0.06e6, _nparams(m)
+
+
+@pytest.mark.parametrize("name,expect", [("ViT-B/32", 87.8e6), ("ViT-B/16", 86.2e6), ("ViT-L/14", 304.0e6)])
+def test_vit_param_counts(name, expect):
+    with th.device("meta"):
+        m = CLIPVisualOnly(VIT_CONFIGS[name])
+    assert abs(_nparams(m) - expect) < 0.06e6, _nparams(m)
+
+
+def test_unet_state_dict_keys():
+    with th.device("meta"):
+        m = UNetModel(config_for(256, True))
+    keys = set(m.state_dict().keys())
+    for k in ["time_embed.0.weight", "time_embed.2.bias", "label_emb.weight", "input_blocks.0.0.weight",
+              "input_blocks.1.0.in_layers.0.weight", "input_blocks.1.0.in_layers.2.bias",
+              "input_blocks.1.0.emb_layers.1.weight", "input_blocks.1.0.out_layers.3.weight",
+              "input_blocks.3.0.in_layers.2.weight", "middle_block.1.qkv.weight", "middle_block.1.proj_out.bias",
+              "middle_block.1.norm.weight", "output_blocks.0.0.skip_connection.weight", "out.0.weight", "out.2.bias"]:
+        assert k in keys, k
+    assert m.state_dict()["middle_block.1.qkv.weight"].shape == (3072, 1024, 1)
+
+
+def test_tiny_unet_and_step_run():
+    cfg = tiny_config()
+    m = seeded_init_(UNetModel(cfg)).eval()
+    x = th.randn(2, 3, 32, 32)
+    out = m(x, th.tensor([3.0, 500.0]), th.tensor([1, 2]))
+    assert out.shape == (2, 6, 32, 32) and th.isfinite(out).all() and out.std() > 1e-3
+    vit = seeded_init_(CLIPVisualOnly(ViTConfig(64, 32, 128, 2, 64)), seed=5).eval()
+    diff = od.create_gaussian_diffusion(1000, "linear", "25")
+    tgt = th.nn.functional.normalize(th.randn(1, 64), dim=-1)
+    cond = og.OracleCondFn(diff, vit, tgt, th.tensor([1.0]), cut_size=64, num_cutouts=2)
+    th.manual_seed(0)
+    gen = diff.p_sample_loop_progressive(m, (2, 3, 32, 32), clip_denoised=False, model_kwargs={"y": th.zeros(2, dtype=th.long)},
+                                         cond_fn=cond, randomize_class=True, cond_fn_with_grad=True)
+    o = next(gen)
+    assert o["sample"].shape == (2, 3, 32, 32) and th.isfinite(o["sample"]).all()
+    gen2 = diff.ddim_sample_loop_progressive(m, (1, 3, 32, 32), clip_denoised=False, model_kwargs={"y": th.zeros(1, dtype=th.long)},
+                                             cond_fn=cond, randomize_class=True, cond_fn_with_grad=True)
+    o = next(gen2)
+    assert th.isfinite(o["sample"]).all()
