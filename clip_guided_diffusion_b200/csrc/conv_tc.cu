@@ -1,0 +1,517 @@
+// conv_tc.cu -- implicit-GEMM convolution / GEMM on Blackwell tcgen05 tensor cores.
+//
+// Replaces (forward and input-gradient directions) the [3P] guided-diffusion UNet Conv2d 3x3 / 1x1 and
+// Conv1d k=1 layers and the [3P] CLIP ViT Linear / patch-conv layers that the reference runs through
+// cuDNN / cuBLAS.
+//
+// Formulation.  Activations are pixel-major fp16 ([n, y, x, c], c contiguous).  One CTA owns a
+// 128-pixel x BN-channel output tile; the 128 pixels are a TW x TH x TN box of the image grid.
+// For every filter tap and every 64-channel slice of the input, one TMA 4-D tiled load fetches the
+// (dx,dy)-shifted box -- out-of-image coordinates are zero-filled by the TMA unit, which *is* the
+// conv padding -- into a 128B-swizzled K-major shared-memory tile; one 2-D TMA load fetches the
+// matching [BN x 64] slice of the pre-packed weights.  A single thread issues
+// tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage, accumulating in TMEM.
+// Pipeline: STAGES-deep smem ring with full/empty mbarriers (TMA producer warp <-> MMA warp),
+// tcgen05.commit releases stages and finally signals the 4 epilogue warps, which read the
+// accumulator with tcgen05.ld (32 lanes x 32 columns), add bias / residual and store fp16.
+// Small-M layers (8x8, 16x16 feature maps with K up to 18k) use split-K over gridDim.z with an fp32
+// workspace and a reduce kernel, so that the weight stream is spread over many SMs.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace cgd {
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("cgd conv_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane = accumulator row)
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 64 fp16 (128 B), 8-row swizzle atoms of 1024 B.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                   // leading byte offset: unused for swizzled K-major (one atom along K)
+  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset between 8-row atoms, bits [32,46)
+  d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                   // layout type SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+  return (1u << 4)                    // D format fp32
+         | (0u << 7) | (0u << 10)     // A, B format fp16
+         | (0u << 15) | (0u << 16)    // A, B K-major
+         | ((uint32_t)(n >> 3) << 17) // N / 8
+         | ((uint32_t)(128 >> 4) << 24);  // M / 16
+}
+
+// ---------------------------------------------------------------- kernel
+constexpr int BM = 128, BK = 64;
+constexpr int kThreads = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = (BN >= 192) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int mt = blockIdx.x;
+  const int tw_i = mt % p.tiles_w;
+  const int th_i = (mt / p.tiles_w) % p.tiles_h;
+  const int tn_i = mt / (p.tiles_w * p.tiles_h);
+  const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
+  const int ncol0 = blockIdx.y * BN;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer
+    if (lane == 0) {
+      const int cblks = p.Cin / BK;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        const int tap = kb / cblks, cb = kb - tap * cblks;
+        int dy = 0, dx = 0;
+        if (p.taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        tma_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], cb * BK, w0 + dx, h0 + dy, n0);
+        tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, ncol0);
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+        const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (>>4) address field
+          tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      tc_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quadrant = warp % 4
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // accumulator row = pixel within the tile
+    const int w_off = r % p.TW, h_off = (r / p.TW) % p.TH, n_off = r / (p.TW * p.TH);
+    const int n = n0 + n_off, h = h0 + h_off, w = w0 + w_off;
+    const bool row_ok = (n < p.NB) && (h < p.H) && (w < p.W);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+    if (p.splits > 1) {
+      // raw fp32 partials -> workspace [split][tile row][Npad]
+      float* ws = p.ws + ((size_t)blockIdx.z * ((size_t)gridDim.x * BM) + (size_t)mt * BM + r) * p.Npad + ncol0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tc_ld_32x16(taddr_row + c, v);
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(ws + c + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    } else {
+      const int64_t o_off = (int64_t)n * p.out_sn + (int64_t)h * p.out_sh + (int64_t)w * p.out_sw;
+      const int64_t r_off = (int64_t)n * p.res_sn + (int64_t)h * p.res_sh + (int64_t)w * p.res_sw;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        __syncwarp();                   // reconverge: the TMEM load is warp-collective (.sync.aligned)
+        tc_ld_32x16(taddr_row + c, v);
+        tc_ld_wait();
+        const int col = ncol0 + c;
+        if (row_ok && col < p.Cout) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
+        if (col + 16 <= p.Cout && !p.out_f32 && p.out_sc == 1) {
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
+              acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
+            }
+          }
+          if (p.res) {
+            float rr[16];
+            unpack8(ld8(p.res + r_off + col), rr);
+            unpack8(ld8(p.res + r_off + col + 8), rr + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] += rr[j];
+          }
+          __half* o = reinterpret_cast<__half*>(p.out) + o_off + col;
+          st8(o, pack8(acc));
+          st8(o + 8, pack8(acc + 8));
+        } else {
+          for (int j = 0; j < 16 && col + j < p.Cout; ++j) {
+            float a = acc[j];
+            if (p.bias) a += p.bias[col + j];
+            if (p.res) a += __half2float(p.res[r_off + col + j]);
+            if (p.out_f32) reinterpret_cast<float*>(p.out)[o_off + (col + j) * p.out_sc] = a;
+            else reinterpret_cast<__half*>(p.out)[o_off + (col + j) * p.out_sc] = __float2half_rn(a);
+          }
+        }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+  }
+}
+
+// split-K second pass: sum partials, add bias / residual, store.
+__global__ void conv_splitk_reduce_kernel(const ConvTcParams p, int m_tiles) {
+  const int64_t total = (int64_t)m_tiles * BM * (p.Cout);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % p.Cout);
+    const int64_t trow = idx / p.Cout;
+    const int r = (int)(trow % BM);
+    const int mt = (int)(trow / BM);
+    const int tw_i = mt % p.tiles_w, th_i = (mt / p.tiles_w) % p.tiles_h, tn_i = mt / (p.tiles_w * p.tiles_h);
+    const int w = tw_i * p.TW + r % p.TW, h = th_i * p.TH + (r / p.TW) % p.TH, n = tn_i * p.TN + r / (p.TW * p.TH);
+    if (n >= p.NB || h >= p.H || w >= p.W) continue;
+    float a = 0.f;
+    for (int s = 0; s < p.splits; ++s) a += p.ws[((size_t)s * ((size_t)m_tiles * BM) + trow) * p.Npad + col];
+    if (p.bias) a += p.bias[col];
+    if (p.res) a += __half2float(p.res[(int64_t)n * p.res_sn + (int64_t)h * p.res_sh + (int64_t)w * p.res_sw + col]);
+    const int64_t o = (int64_t)n * p.out_sn + (int64_t)h * p.out_sh + (int64_t)w * p.out_sw + col * p.out_sc;
+    if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = a;
+    else reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(a);
+  }
+}
+
+// ---------------------------------------------------------------- SIMT verification kernel
+// Same contract, CUDA cores only, one thread per output element.  Exists so that GPU tests can
+// cross-check the tcgen05 path layer by layer and so a tcgen05 regression cannot block bring-up of the
+// rest of the step; never selected by the shipped plans (impl = 0).
+__global__ void conv_simt_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, const ConvTcParams p,
+                                 int64_t a_sn, int64_t a_sh, int64_t a_sw) {
+  const int64_t total = (int64_t)p.NB * p.H * p.W * p.Cout;
+  const int K = p.taps * p.Cin;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % p.Cout);
+    int64_t pix = idx / p.Cout;
+    const int w = (int)(pix % p.W);
+    pix /= p.W;
+    const int h = (int)(pix % p.H);
+    const int n = (int)(pix / p.H);
+    float acc = 0.f;
+    for (int tap = 0; tap < p.taps; ++tap) {
+      const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+      const int yy = h + dy, xx = w + dx;
+      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+      const __half2* a = reinterpret_cast<const __half2*>(A + n * a_sn + yy * a_sh + xx * a_sw);
+      const __half2* wr = reinterpret_cast<const __half2*>(Wp + (int64_t)co * K + (int64_t)tap * p.Cin);
+      for (int c = 0; c < p.Cin / 2; ++c) {
+        const float2 av = __half22float2(a[c]), wv = __half22float2(wr[c]);
+        acc = fmaf(av.x, wv.x, acc);
+        acc = fmaf(av.y, wv.y, acc);
+      }
+    }
+    if (p.bias) acc += p.bias[co];
+    if (p.res) acc += __half2float(p.res[(int64_t)n * p.res_sn + (int64_t)h * p.res_sh + (int64_t)w * p.res_sw + co]);
+    const int64_t o = (int64_t)n * p.out_sn + (int64_t)h * p.out_sh + (int64_t)w * p.out_sw + co * p.out_sc;
+    if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = acc;
+    else reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(acc);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static int pick_tile(int64_t W, int64_t H, int& TW, int& TH, int& TN) {
+  // TW = smallest power of two >= min(W, 128); TH = largest power of two with TW*TH <= 128 not exceeding
+  // the power-of-two ceiling of H; TN fills the remaining rows of the 128-pixel tile.
+  int tw = 1;
+  while (tw < W && tw < 128) tw <<= 1;
+  int hceil = 1;
+  while (hceil < H) hceil <<= 1;
+  int th = 128 / tw;
+  if (th > hceil) th = hceil;
+  TW = tw;
+  TH = th;
+  TN = 128 / (tw * th);
+  return 0;
+}
+
+int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
+  ConvTcParams& p = L.p;
+  const int64_t NB = op.i[0], H = op.i[1], W = op.i[2], Cin = op.i[3], Cout = op.i[4], Npad = op.i[5], taps = op.i[6];
+  const int64_t BN = op.i[16], splits = op.i[17] > 0 ? op.i[17] : 1;
+  CGD_CHECK_ARG(NB > 0 && H > 0 && W > 0, "conv: bad image dims %lld %lld %lld", (long long)NB, (long long)H, (long long)W);
+  CGD_CHECK_ARG(Cin > 0 && Cin % 64 == 0, "conv: Cin=%lld must be a positive multiple of 64", (long long)Cin);
+  CGD_CHECK_ARG(taps == 1 || taps == 9, "conv: taps must be 1 or 9");
+  CGD_CHECK_ARG(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 192 || BN == 256, "conv: unsupported BN=%lld", (long long)BN);
+  CGD_CHECK_ARG(Npad % BN == 0 && Cout <= Npad && Cout > 0, "conv: Npad=%lld must be a multiple of BN=%lld and >= Cout=%lld",
+                (long long)Npad, (long long)BN, (long long)Cout);
+  CGD_CHECK_ARG(op.p[0] && op.p[1] && op.p[4], "conv: null A / W / out pointer");
+  CGD_CHECK_ARG(((uintptr_t)op.p[0] % 16) == 0 && ((uintptr_t)op.p[1] % 16) == 0 && ((uintptr_t)op.p[4] % 16) == 0,
+                "conv: A / W / out must be 16-byte aligned");
+  for (int k = 7; k <= 9; ++k) CGD_CHECK_ARG(op.i[k] % 8 == 0, "conv: A strides must be multiples of 8 elements (16 B)");
+  p.NB = (int)NB; p.H = (int)H; p.W = (int)W; p.Cin = (int)Cin; p.Cout = (int)Cout; p.Npad = (int)Npad; p.taps = (int)taps;
+  pick_tile(W, H, p.TW, p.TH, p.TN);
+  p.tiles_w = (int)ceil_div(W, p.TW);
+  p.tiles_h = (int)ceil_div(H, p.TH);
+  p.tiles_n = (int)ceil_div(NB, p.TN);
+  p.kblocks = (int)(taps * Cin / 64);
+  p.splits = (int)splits;
+  CGD_CHECK_ARG(p.splits >= 1 && p.splits <= p.kblocks, "conv: splits=%d out of range (kblocks=%d)", p.splits, p.kblocks);
+  p.kb_per_split = (int)ceil_div(p.kblocks, p.splits);
+  p.splits = (int)ceil_div(p.kblocks, p.kb_per_split);  // no empty splits
+  p.out_sn = op.i[10]; p.out_sh = op.i[11]; p.out_sw = op.i[12];
+  p.res_sn = op.i[13]; p.res_sh = op.i[14]; p.res_sw = op.i[15];
+  p.bias = reinterpret_cast<const float*>(op.p[2]);
+  p.res = reinterpret_cast<const __half*>(op.p[3]);
+  p.out = op.p[4];
+  p.ws = reinterpret_cast<float*>(op.p[5]);
+  p.out_f32 = (op.flags & 1) ? 1 : 0;
+  p.out_sc = op.i[19] > 0 ? op.i[19] : 1;
+  if (!p.out_f32 && p.out_sc == 1) CGD_CHECK_ARG(op.i[10] % 8 == 0 && op.i[11] % 8 == 0 && op.i[12] % 8 == 0, "conv: fp16 out strides must be multiples of 8");
+  if (p.res) CGD_CHECK_ARG(op.i[13] % 8 == 0 && op.i[14] % 8 == 0 && op.i[15] % 8 == 0 && ((uintptr_t)p.res % 16) == 0, "conv: residual must be 16-byte aligned with strides %% 8 == 0");
+  if (p.splits > 1) CGD_CHECK_ARG(p.ws != nullptr, "conv: split-K needs a workspace");
+  L.BN = (int)BN;
+  L.impl = (int)op.i[18];
+  L.A = reinterpret_cast<const __half*>(op.p[0]);
+  L.Wp = reinterpret_cast<const __half*>(op.p[1]);
+  L.a_sn = op.i[7]; L.a_sh = op.i[8]; L.a_sw = op.i[9];
+  L.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  L.n_tiles = (int)(Npad / BN);
+  if (L.impl != 0) return 0;
+
+  PFN_encodeTiled enc = get_encode_fn();
+  CGD_CHECK_ARG(enc != nullptr, "conv: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t strides[3] = {(cuuint64_t)op.i[9] * 2, (cuuint64_t)op.i[8] * 2, (cuuint64_t)op.i[7] * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&L.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, op.p[0], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(A) failed with %d (dims %lld,%lld,%lld,%lld strides %lld,%lld,%lld box %d,%d,%d)",
+                  (int)r, (long long)Cin, (long long)W, (long long)H, (long long)NB, (long long)strides[0], (long long)strides[1],
+                  (long long)strides[2], p.TW, p.TH, p.TN);
+  }
+  {
+    const cuuint64_t K = (cuuint64_t)(taps * Cin);
+    cuuint64_t dims[2] = {K, (cuuint64_t)Npad};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, op.p[1], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+  }
+  return 0;
+}
+
+template <int BN>
+static int launch_tc(const ConvTcLaunch& L, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CGD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(L.m_tiles, L.n_tiles, L.p.splits);
+  conv_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(L.tmA, L.tmB, L.p);
+  CGD_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
+  if (L.impl != 0) {
+    const int64_t total = (int64_t)L.p.NB * L.p.H * L.p.W * L.p.Cout;
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+    ConvTcParams p = L.p;
+    p.splits = 1;
+    conv_simt_kernel<<<blocks, 256, 0, st>>>(L.A, L.Wp, p, L.a_sn, L.a_sh, L.a_sw);
+    CGD_LAUNCH_CHECK();
+    return 0;
+  }
+  int rc = 0;
+  switch (L.BN) {
+    case 16: rc = launch_tc<16>(L, st); break;
+    case 32: rc = launch_tc<32>(L, st); break;
+    case 64: rc = launch_tc<64>(L, st); break;
+    case 128: rc = launch_tc<128>(L, st); break;
+    case 192: rc = launch_tc<192>(L, st); break;
+    case 256: rc = launch_tc<256>(L, st); break;
+    default: set_error("conv: unsupported BN %d", L.BN); return -1;
+  }
+  if (rc) return rc;
+  if (L.p.splits > 1) {
+    const int64_t total = (int64_t)L.m_tiles * BM * L.p.Cout;
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 8);
+    conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(L.p, L.m_tiles);
+    CGD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int conv_tc_num_launches(const ConvTcLaunch& L) { return (L.impl == 0 && L.p.splits > 1) ? 2 : 1; }
+
+}  // namespace cgd

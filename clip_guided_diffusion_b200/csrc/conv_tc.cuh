@@ -1,0 +1,39 @@
+// conv_tc.cuh -- parameter blocks of the tcgen05 implicit-GEMM conv (see conv_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/cgd_b200.h"
+
+namespace cgd {
+
+struct ConvTcParams {
+  int NB, H, W, Cin, Cout, Npad, taps;
+  int TW, TH, TN;                    // 128-pixel tile = TW x TH x TN box of the (W, H, N) grid
+  int tiles_w, tiles_h, tiles_n;
+  int kblocks, splits, kb_per_split; // K loop = taps * Cin/64 blocks, optionally split over gridDim.z
+  int out_f32;
+  int64_t out_sn, out_sh, out_sw;    // output / residual strides in elements (channel contiguous)
+  int64_t res_sn, res_sh, res_sw;
+  int64_t out_sc;                    // output channel stride (1 except for NCHW fp32 outputs; scalar-store paths only)
+  const float* bias;
+  const __half* res;
+  void* out;
+  float* ws;                         // split-K partials [splits][m_tiles*128][Npad]
+};
+
+struct ConvTcLaunch {
+  CUtensorMap tmA, tmB;
+  ConvTcParams p;
+  int BN, impl, m_tiles, n_tiles;
+  const __half* A;
+  const __half* Wp;
+  int64_t a_sn, a_sh, a_sw;
+};
+
+int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L);
+int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st);
+int conv_tc_num_launches(const ConvTcLaunch& L);
+
+}  // namespace cgd
