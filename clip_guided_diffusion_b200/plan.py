@@ -1,0 +1,508 @@
+"""Plan builder: turns a network description into the flat op list of include/cgd_b200.h.
+
+A *plan* is built once per (network, batch shape): every activation, saved tensor, gradient and workspace gets a
+fixed offset in one arena (a single device allocation, 180 GB HBM makes reuse unnecessary at these sizes), weights
+are packed into the kernel layouts and uploaded into the same arena, and the forward and input-gradient backward
+op lists are emitted.  Per timestep the host only replays the list (``Plan.run``; normally inside a CUDA graph).
+
+The backward list is produced by a tape at plan-build time (hand-scheduled reverse mode, dgrad only -- no weight
+gradients exist on this path, cgd/cgd.py:228, cgd/script_util.py:318); nothing is traced at run time.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional
+
+import numpy as np
+import torch as th
+
+from . import _lib
+from ._lib import OP, CgdOp
+
+_DT = {"h": (2, th.float16), "f": (4, th.float32), "i32": (4, th.int32), "i64": (8, th.int64), "u32": (4, th.int32)}
+
+
+@dataclass
+class Buf:
+    """A typed region of the arena."""
+    off: int  # byte offset
+    numel: int
+    dt: str
+    name: str = ""
+
+    @property
+    def nbytes(self):
+        return self.numel * _DT[self.dt][0]
+
+
+@dataclass
+class Act:
+    """Pixel-major fp16 activation view: [N, H, W, C] with row stride ld (elements), image stride H*W*ld."""
+    buf: Buf
+    eoff: int  # element offset into buf
+    N: int
+    H: int
+    W: int
+    C: int
+    ld: int
+    frozen: bool = False  # never accumulate into this storage in place
+
+    @property
+    def HW(self):
+        return self.H * self.W
+
+    @property
+    def rows(self):
+        return self.N * self.H * self.W
+
+    def cslice(self, c0, c1):
+        return Act(self.buf, self.eoff + c0, self.N, self.H, self.W, c1 - c0, self.ld, self.frozen)
+
+    def key(self):
+        return (self.buf.off, self.eoff, self.C, self.ld)
+
+
+@dataclass
+class PlanOp:
+    code: int
+    flags: int = 0
+    i: list = field(default_factory=list)
+    f: list = field(default_factory=list)
+    p: list = field(default_factory=list)  # entries: None | (Buf, element offset)
+    tag: str = ""
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def pick_bn(npad: int, m_tiles: int) -> int:
+    cands = [b for b in (256, 192, 128, 64, 32, 16) if npad % b == 0]
+    big = [b for b in cands if b >= 64]
+    if not big:
+        return cands[0]
+    for b in big:  # largest BN that still fills the 148 SMs
+        if m_tiles * (npad // b) >= 148:
+            return b
+    # cannot fill the GPU with output tiles: narrower tiles give more CTAs, split-K tops up the rest
+    return 128 if 128 in big else big[-1]
+
+
+def conv_tile_count(NB, H, W):
+    tw = 1
+    while tw < W and tw < 128:
+        tw <<= 1
+    hceil = 1
+    while hceil < H:
+        hceil <<= 1
+    t_h = min(128 // tw, hceil)
+    tn = 128 // (tw * t_h)
+    return -(-W // tw) * -(-H // t_h) * -(-NB // tn)
+
+
+def pick_splits(m_tiles, n_tiles, kblocks, npad, ws_cap_bytes=16 << 20) -> int:
+    tiles = m_tiles * n_tiles
+    if tiles >= 120 or kblocks < 8:
+        return 1
+    s = min(kblocks // 4, -(-296 // tiles), 32)
+    cap = ws_cap_bytes // (m_tiles * 128 * npad * 4)
+    s = max(1, min(s, cap))
+    per = -(-kblocks // s)
+    return -(-kblocks // per)
+
+
+class Plan:
+    def __init__(self, conv_impl: int = 0):
+        self.ops: list[PlanOp] = []
+        self._size = 0
+        self._consts: list[tuple[Buf, th.Tensor]] = []
+        self._tape: list[Callable[[], None]] = []
+        self._grads: dict = {}
+        self.conv_impl = conv_impl
+        self.arena: Optional[th.Tensor] = None
+        self.handle = None
+        self._c_ops = None
+        self.marks: dict[str, int] = {}
+
+    # ------------------------------------------------------------------ memory
+    def new(self, numel: int, dt: str, name: str = "") -> Buf:
+        off = _round_up(self._size, 256)
+        b = Buf(off, int(numel), dt, name)
+        self._size = off + b.nbytes
+        return b
+
+    def const(self, t: th.Tensor, dt: str, name: str = "") -> Buf:
+        t = t.detach().to(_DT[dt][1]).contiguous().cpu()
+        b = self.new(t.numel(), dt, name)
+        self._consts.append((b, t))
+        return b
+
+    def act(self, N, H, W, C, name="", ld=None) -> Act:
+        ld = ld or C
+        return Act(self.new(N * H * W * ld, "h", name), 0, N, H, W, C, ld)
+
+    # ------------------------------------------------------------------ low-level emit
+    def emit(self, code, *, flags=0, i=(), f=(), p=(), tag=""):
+        self.ops.append(PlanOp(OP[code] if isinstance(code, str) else code, flags, list(i), list(f), list(p), tag))
+
+    def mark(self, name):
+        self.marks[name] = len(self.ops)
+
+    @staticmethod
+    def _ap(a: Optional[Act]):
+        return None if a is None else (a.buf, a.eoff)
+
+    @staticmethod
+    def _bp(b: Optional[Buf], eoff: int = 0):
+        return None if b is None else (b, eoff)
+
+    # ------------------------------------------------------------------ gradient bookkeeping (build time only)
+    def grad_of(self, a: Act) -> Optional[Act]:
+        return self._grads.get(a.key())
+
+    def add_grad(self, a: Act, g: Act):
+        """Accumulate gradient view g into the gradient of activation a (alias when first, in-place ADD otherwise)."""
+        cur = self._grads.get(a.key())
+        if cur is None:
+            self._grads[a.key()] = g
+            return
+        if cur.frozen:
+            dst = self.act(a.N, a.H, a.W, a.C, "gsum")
+        else:
+            dst = cur
+        self.emit("ADD", i=[a.rows, a.C, cur.ld, g.ld, dst.ld], p=[self._ap(cur), self._ap(g), self._ap(dst)], tag="grad+=")
+        self._grads[a.key()] = dst
+
+    def writable_grad(self, a: Act) -> tuple[Optional[Act], bool]:
+        """Gradient storage of `a` that a kernel may accumulate into in place: (act, exists)."""
+        cur = self._grads.get(a.key())
+        if cur is None:
+            return None, False
+        if cur.frozen:
+            dst = self.act(a.N, a.H, a.W, a.C, "gcopy")
+            self.emit("COPY", i=[a.rows, a.C, cur.ld, dst.ld], p=[self._ap(cur), self._ap(dst)], tag="grad copy")
+            self._grads[a.key()] = dst
+            return dst, True
+        return cur, True
+
+    def backward(self):
+        """Emit the backward op list (reverse tape)."""
+        for fn in reversed(self._tape):
+            fn()
+        self._tape = []
+
+    # ------------------------------------------------------------------ conv / GEMM
+    def _emit_conv(self, x_ptr, x_strides, NB, H, W, Cin, wbuf, npad, Cout, taps, bias, res_ptr, res_strides, out_ptr, out_strides,
+                   out_f32=False, out_sc=1, tag=""):
+        m_tiles = conv_tile_count(NB, H, W)
+        bn = pick_bn(npad, m_tiles)
+        kblocks = taps * Cin // 64
+        splits = pick_splits(m_tiles, npad // bn, kblocks, npad)
+        ws = self.new(splits * m_tiles * 128 * npad, "f", "splitk_ws") if splits > 1 else None
+        i = [NB, H, W, Cin, Cout, npad, taps, *x_strides, *out_strides, *(res_strides or (0, 0, 0)), bn, splits, self.conv_impl, out_sc]
+        self.emit("CONV", flags=1 if out_f32 else 0, i=i,
+                  p=[x_ptr, self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws)], tag=tag)
+
+    @staticmethod
+    def _strides(a: Act):
+        return (a.H * a.W * a.ld, a.W * a.ld, a.ld)
+
+    def conv(self, x: Act, w: "ConvW", res: Optional[Act] = None, out: Optional[Act] = None, name="conv") -> Act:
+        """y = conv(x) + bias (+ res).  Registers the dgrad on the tape."""
+        assert x.C == w.cin_pad, (x.C, w.cin_pad, name)
+        y = out if out is not None else self.act(x.N, x.H, x.W, w.cout, name)
+        assert y.C == w.cout and (y.N, y.H, y.W) == (x.N, x.H, x.W)
+        self._emit_conv(self._ap(x), self._strides(x), x.N, x.H, x.W, x.C, w.fwd, w.fwd_npad, w.cout, w.taps, w.bias,
+                        self._ap(res), self._strides(res) if res is not None else None, self._ap(y), self._strides(y), tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            if res is not None:
+                self.add_grad(res, dy)
+            if w.bwd is None:
+                return
+            cur, has = self.writable_grad(x)
+            dx = cur if has else self.act(x.N, x.H, x.W, x.C, "d_" + name)
+            # dgrad: same kernel over dy with tap-flipped, transposed weights; existing dx folded in as the residual
+            self._emit_conv(self._ap(dy), self._strides(dy), x.N, x.H, x.W, dy.C, w.bwd, w.bwd_npad, x.C, w.taps, None,
+                            self._ap(cur) if has else None, self._strides(cur) if has else None, self._ap(dx), self._strides(dx),
+                            tag="d_" + name)
+            self._grads[x.key()] = dx
+
+        self._tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ GroupNorm (+SiLU, +scale/shift)
+    def group_norm(self, x: Act, gamma: Buf, beta: Buf, emb: Optional[tuple] = None, silu=True, eps=1e-5, name="gn") -> Act:
+        N, HW, C = x.N, x.HW, x.C
+        pp = max(1, 256 // (C // 8))
+        nchunk = int(min(max(1, -(-HW // (pp * 8))), max(1, 592 // N), 256))
+        partials = self.new(N * nchunk * 64, "f", name + "_part")
+        stats = self.new(N * 64, "f", name + "_stats")
+        counters = self.new(N, "u32", name + "_cnt")
+        y = self.act(N, x.H, x.W, C, name)
+        embp = self._bp(emb[0], emb[1]) if emb is not None else None
+        self.emit("GN_STATS", i=[N, HW, C, x.ld, nchunk], f=[eps], p=[self._ap(x), self._bp(partials), self._bp(stats), self._bp(counters)], tag=name)
+        self.emit("GN_APPLY", flags=1 if silu else 0, i=[N, HW, C, x.ld, nchunk, y.ld], f=[eps],
+                  p=[self._ap(x), self._bp(stats), self._bp(gamma), self._bp(beta), embp, self._ap(y)], tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            bpart = self.new(N * nchunk * 64, "f", name + "_bpart")
+            sums = self.new(N * 64, "f", name + "_bsums")
+            bcnt = self.new(N, "u32", name + "_bcnt")
+            common = [self._ap(dy), self._ap(x), self._bp(stats), self._bp(gamma), self._bp(beta), embp]
+            self.emit("GN_BWD_STATS", flags=1 if silu else 0, i=[N, HW, C, dy.ld, x.ld, nchunk], f=[eps],
+                      p=common + [self._bp(bpart), self._bp(sums), self._bp(bcnt)], tag="d_" + name)
+            cur, has = self.writable_grad(x)
+            dx = cur if has else self.act(N, x.H, x.W, C, "d_" + name)
+            self.emit("GN_BWD_APPLY", flags=(1 if silu else 0) | (2 if has else 0), i=[N, HW, C, dy.ld, x.ld, nchunk, dx.ld], f=[eps],
+                      p=common + [self._bp(sums), self._ap(dx)], tag="d_" + name)
+            self._grads[x.key()] = dx
+
+        self._tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ resampling
+    def pool2(self, x: Act, name="down") -> Act:
+        y = self.act(x.N, x.H // 2, x.W // 2, x.C, name)
+        self.emit("POOL2", i=[x.N, x.H, x.W, x.C, x.ld, y.ld], f=[0.25], p=[self._ap(x), self._ap(y)], tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            dx = self.act(x.N, x.H, x.W, x.C, "d_" + name)
+            self.emit("UP2", i=[y.N, y.H, y.W, y.C, dy.ld, dx.ld], f=[0.25], p=[self._ap(dy), self._ap(dx)], tag="d_" + name)
+            self.add_grad(x, dx)
+
+        self._tape.append(bwd)
+        return y
+
+    def up2(self, x: Act, name="up") -> Act:
+        y = self.act(x.N, x.H * 2, x.W * 2, x.C, name)
+        self.emit("UP2", i=[x.N, x.H, x.W, x.C, x.ld, y.ld], f=[1.0], p=[self._ap(x), self._ap(y)], tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            dx = self.act(x.N, x.H, x.W, x.C, "d_" + name)
+            self.emit("POOL2", i=[y.N, y.H, y.W, y.C, dy.ld, dx.ld], f=[1.0], p=[self._ap(dy), self._ap(dx)], tag="d_" + name)
+            self.add_grad(x, dx)
+
+        self._tape.append(bwd)
+        return y
+
+    def concat(self, a: Act, b: Act, name="cat") -> Act:
+        """channel concat [a | b]; `a`/`b` are copied (callers may instead produce `a` directly into the slice)."""
+        y = self.act(a.N, a.H, a.W, a.C + b.C, name)
+        ya, yb = y.cslice(0, a.C), y.cslice(a.C, a.C + b.C)
+        self.emit("COPY", i=[a.rows, a.C, a.ld, ya.ld], p=[self._ap(a), self._ap(ya)], tag=name)
+        self.emit("COPY", i=[b.rows, b.C, b.ld, yb.ld], p=[self._ap(b), self._ap(yb)], tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            # slices of a gradient buffer alias storage that later in-place accumulation must not touch
+            ga, gb = dy.cslice(0, a.C), dy.cslice(a.C, a.C + b.C)
+            ga.frozen = gb.frozen = True
+            self.add_grad(a, ga)
+            self.add_grad(b, gb)
+
+        self._tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ attention (head dim 64)
+    def attention(self, qkv: Act, heads: int, T: int, nbatch: int, legacy_order: bool, name="attn") -> Act:
+        """qkv: [nbatch*T rows, 3C].  legacy_order: per-head [q|k|v] interleave (UNet QKVAttentionLegacy);
+        otherwise [q heads | k heads | v heads] (QKVAttention, nn.MultiheadAttention)."""
+        C = qkv.C // 3
+        d = C // heads
+        assert d == 64, "attention kernels support head dim 64"
+        out = Act(self.new(nbatch * T * C, "h", name), 0, qkv.N, qkv.H, qkv.W, C, C)
+        lse = self.new(nbatch * heads * T, "f", name + "_lse")
+        if legacy_order:
+            hs, qo, ko, vo = 3 * d, 0, d, 2 * d
+        else:
+            hs, qo, ko, vo = d, 0, C, 2 * C
+        ii = [nbatch, heads, T, d, T * qkv.ld, qkv.ld, hs, T * out.ld, out.ld, d]
+        scale = 1.0 / math.sqrt(d)
+        q = (qkv.buf, qkv.eoff + qo)
+        k = (qkv.buf, qkv.eoff + ko)
+        v = (qkv.buf, qkv.eoff + vo)
+        self.emit("ATTN_FWD", i=ii, f=[scale], p=[q, k, v, self._ap(out), self._bp(lse)], tag=name)
+
+        def bwd():
+            do = self.grad_of(out)
+            if do is None:
+                return
+            assert do.ld == out.ld
+            dqkv = Act(self.new(nbatch * T * qkv.ld, "h", "d_" + name), 0, qkv.N, qkv.H, qkv.W, qkv.C, qkv.ld)
+            delta = self.new(nbatch * heads * T, "f", name + "_delta")
+            self.emit("ATTN_BWD", i=ii, f=[scale],
+                      p=[q, k, v, self._ap(out), self._ap(do), self._bp(lse), (dqkv.buf, qo), (dqkv.buf, ko), (dqkv.buf, vo), self._bp(delta)],
+                      tag="d_" + name)
+            self.add_grad(qkv, dqkv)
+
+        self._tape.append(bwd)
+        return out
+
+    # ------------------------------------------------------------------ LayerNorm / QuickGELU (ViT)
+    def layer_norm(self, x: Act, gamma: Buf, beta: Buf, eps=1e-5, rows=None, ldx=None, name="ln") -> Act:
+        rows = rows if rows is not None else x.rows
+        ldx = ldx if ldx is not None else x.ld
+        y = Act(self.new(rows * x.C, "h", name), 0, 1, 1, rows, x.C, x.C)
+        stats = self.new(rows * 2, "f", name + "_stats")
+        self.emit("LN_FWD", i=[rows, x.C, ldx, y.ld], f=[eps], p=[self._ap(x), self._bp(gamma), self._bp(beta), self._ap(y), self._bp(stats)], tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            if rows == x.rows and ldx == x.ld:
+                cur, has = self.writable_grad(x)
+                dx = cur if has else self.act(x.N, x.H, x.W, x.C, "d_" + name)
+                self.emit("LN_BWD", flags=2 if has else 0, i=[rows, x.C, dy.ld, ldx, dx.ld],
+                          p=[self._ap(dy), self._ap(x), self._bp(gamma), self._bp(stats), self._ap(dx)], tag="d_" + name)
+                self._grads[x.key()] = dx
+            else:
+                # strided row subset (cls token of every image): scatter into a zero gradient of the full tensor.  The arena
+                # is zero-initialised and only these rows are ever written, so the other rows stay zero across replays.
+                assert self.grad_of(x) is None
+                dx = self.act(x.N, x.H, x.W, x.C, "d_" + name)
+                dx.frozen = True
+                self.emit("LN_BWD", i=[rows, x.C, dy.ld, ldx, ldx], p=[self._ap(dy), self._ap(x), self._bp(gamma), self._bp(stats), self._ap(dx)],
+                          tag="d_" + name)
+                self._grads[x.key()] = dx
+
+        self._tape.append(bwd)
+        return y
+
+    def quick_gelu(self, u: Act, name="gelu") -> Act:
+        assert u.ld == u.C
+        a = self.act(u.N, u.H, u.W, u.C, name)
+        self.emit("QGELU_FWD", i=[u.rows * u.C], p=[self._ap(u), self._ap(a)], tag=name)
+
+        def bwd():
+            da = self.grad_of(a)
+            if da is None:
+                return
+            assert da.ld == da.C
+            du = self.act(u.N, u.H, u.W, u.C, "d_" + name)
+            self.emit("QGELU_BWD", i=[u.rows * u.C], p=[self._ap(da), self._ap(u), self._ap(du)], tag="d_" + name)
+            self.add_grad(u, du)
+
+        self._tape.append(bwd)
+        return a
+
+    # ------------------------------------------------------------------ finalize / run
+    def finalize(self, device):
+        """Allocate the arena on `device`, upload constants, lower ops.  On a CUDA device this also creates the
+        native plan (TMA descriptors); on CPU the arena exists only so tests can interpret the op list."""
+        device = th.device(device)
+        nbytes = _round_up(self._size, 256) + 256
+        self.arena = th.zeros(nbytes, dtype=th.uint8, device=device)
+        for b, t in self._consts:
+            self.arena[b.off:b.off + b.nbytes].copy_(t.view(-1).view(th.uint8))
+        self._consts_done = True
+        if device.type != "cuda":
+            return self
+        lib = _lib.load()
+        base = self.arena.data_ptr()
+        assert base % 256 == 0
+        arr = (CgdOp * len(self.ops))()
+        for k, op in enumerate(self.ops):
+            c = arr[k]
+            c.code, c.flags = op.code, op.flags
+            assert len(op.i) <= _lib.CGD_OP_NI and len(op.f) <= _lib.CGD_OP_NF and len(op.p) <= _lib.CGD_OP_NP, op.tag
+            for j, v in enumerate(op.i):
+                c.i[j] = int(v)
+            for j, v in enumerate(op.f):
+                c.f[j] = float(v)
+            for j, v in enumerate(op.p):
+                c.p[j] = None if v is None else base + v[0].off + v[1] * _DT[v[0].dt][0]
+        h = ctypes.c_void_p()
+        _lib.check(lib.cgd_plan_create(arr, len(self.ops), ctypes.byref(h)), "cgd_plan_create")
+        self.handle, self._c_ops = h, arr
+        return self
+
+    def view(self, b: Buf, shape=None) -> th.Tensor:
+        t = self.arena[b.off:b.off + b.nbytes].view(_DT[b.dt][1])
+        return t.view(shape) if shape is not None else t
+
+    def run(self, first: int = 0, count: Optional[int] = None, stream=None):
+        if self.handle is None:
+            raise _lib.CgdError("plan has no native handle: it was finalized on a CPU device; the sampling step has no CPU path "
+                                "(tests interpret op lists with tests/plan_interp.py)")
+        count = len(self.ops) - first if count is None else count
+        st = th.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(_lib.load().cgd_plan_run(self.handle, first, count, ctypes.c_void_p(st)), "cgd_plan_run")
+
+    def run_range(self, a: str, b: str, stream=None):
+        self.run(self.marks[a], self.marks[b] - self.marks[a], stream)
+
+    def num_launches(self, first=0, count=None) -> int:
+        count = len(self.ops) - first if count is None else count
+        return int(_lib.load().cgd_plan_num_launches(self.handle, first, count))
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                _lib.load().cgd_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------- weight packing
+@dataclass
+class ConvW:
+    """Packed weights of one conv / linear layer (forward and dgrad orientations)."""
+    fwd: Buf
+    fwd_npad: int
+    bwd: Optional[Buf]
+    bwd_npad: int
+    bias: Optional[Buf]
+    cin_pad: int
+    cout: int
+    taps: int
+
+
+def _npad(n):
+    return _round_up(n, 16) if n < 64 else _round_up(n, 64)
+
+
+def pack_conv(plan: Plan, w: th.Tensor, bias: Optional[th.Tensor], *, need_bwd=True, cin_pad=None, name="w") -> ConvW:
+    """w: [Cout, Cin, kh, kw] (kh=kw in {1,3}) or [Cout, Cin] / [Cout, Cin, 1].  Input channels are zero-padded to a
+    multiple of 64 (TMA K-slices are 64 channels), output rows to the tile width."""
+    w = w.detach().float()
+    if w.dim() == 3:
+        w = w[..., None]
+    if w.dim() == 2:
+        w = w[..., None, None]
+    cout, cin, kh, kw = w.shape
+    taps = kh * kw
+    assert taps in (1, 9)
+    cin_p = cin_pad or _round_up(cin, 64)
+    cout_p64 = _round_up(cout, 64)
+    # forward: Wp[co, tap*cin_p + ci]
+    wf = th.zeros(_npad(cout), taps, cin_p)
+    wf[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, taps, cin)
+    fwd = plan.const(wf.reshape(_npad(cout), taps * cin_p), "h", name + ".fwd")
+    bwd, bnp = None, 0
+    if need_bwd:
+        # dgrad: Wd[ci, tap'*cout_p + co] = w[co, ci, 2-ky', 2-kx'] (taps flipped), K = taps * cout_p
+        bnp = _npad(cin)
+        wb = th.zeros(bnp, taps, cout_p64)
+        wflip = th.flip(w, dims=(2, 3)) if taps == 9 else w
+        wb[:cin, :, :cout] = wflip.permute(1, 2, 3, 0).reshape(cin, taps, cout)
+        bwd = plan.const(wb.reshape(bnp, taps * cout_p64), "h", name + ".bwd")
+    b = plan.const(bias.float(), "f", name + ".bias") if bias is not None else None
+    return ConvW(fwd, _npad(cout), bwd, bnp, b, cin_p, cout, taps)

@@ -1,0 +1,147 @@
+"""CLIP visual tower (``clip.model.VisionTransformer``) as a B200 op plan: encode_image forward and input gradient.
+
+Replaces [3P] ``clip_model.encode_image`` (called at cgd/cgd.py:194) and its autograd backward (cgd/cgd.py:228).
+Weights come from a state_dict in upstream key layout (``visual.*``).  The input is
+not an image tensor but the patch matrix that the cutout kernel writes directly in patch order, so the patch
+"convolution" is a plain GEMM.  Linear layers run on the tcgen05 GEMM kernel with fp16 operands / fp32
+accumulation (the reference's CUDA path loads CLIP in fp16, cgd/clip_util.py:64-65); LayerNorm statistics,
+softmax and the final projection are fp32.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch as th
+
+from .plan import Act, Plan, pack_conv, _round_up
+
+
+@dataclass
+class ViTConfig:
+    input_resolution: int = 224
+    patch_size: int = 32
+    width: int = 768
+    layers: int = 12
+    output_dim: int = 512
+
+    @property
+    def heads(self):
+        return self.width // 64
+
+    @property
+    def grid(self):
+        return self.input_resolution // self.patch_size
+
+    @property
+    def tokens(self):
+        return self.grid ** 2 + 1
+
+    @property
+    def kpad(self):
+        """patch vector length 3*P*P zero-padded to a multiple of 64 (TMA K slices)"""
+        return _round_up(3 * self.patch_size ** 2, 64)
+
+
+VIT_CONFIGS = {
+    "ViT-B/32": ViTConfig(224, 32, 768, 12, 512),
+    "ViT-B/16": ViTConfig(224, 16, 768, 12, 512),
+    "ViT-L/14": ViTConfig(224, 14, 1024, 24, 768),
+}
+
+
+def vit_config_from_state_dict(sd: dict) -> ViTConfig:
+    w = sd["visual.conv1.weight"]
+    width, _, ps, _ = w.shape
+    tokens = sd["visual.positional_embedding"].shape[0]
+    grid = int(round((tokens - 1) ** 0.5))
+    layers = len({k.split(".")[3] for k in sd if k.startswith("visual.transformer.resblocks.")})
+    return ViTConfig(grid * ps, ps, width, layers, sd["visual.proj"].shape[1])
+
+
+class ViTB200:
+    """encode_image for n = cutn*B cutouts.  ``patches`` (fp16 [n, grid^2, kpad]) is the plan's input buffer;
+    ``embeds`` (fp32 [n, D]) its output; ``d_embeds`` -> ``d_patches`` the backward."""
+
+    def __init__(self, cfg: ViTConfig, state_dict: dict, n_images: int, device="cuda", conv_impl: int = 0, build_backward=True,
+                 plan: Plan = None):
+        self.cfg, self.n = cfg, n_images
+        self.sd = state_dict
+        self.own_plan = plan is None
+        self.plan = plan or Plan(conv_impl=conv_impl)
+        self._build(build_backward)
+        if self.own_plan:
+            self.plan.finalize(device)
+        del self.sd
+
+    def _w(self, key):
+        return self.sd["visual." + key].detach().float().cpu()
+
+    def _const(self, key):
+        return self.plan.const(self._w(key), "f", key)
+
+    def _build(self, build_backward):
+        p, cfg, n = self.plan, self.cfg, self.n
+        w, T, G2, D, kp = cfg.width, cfg.tokens, cfg.grid ** 2, cfg.output_dim, cfg.kpad
+        rows = n * T
+        self.patches = p.new(n * G2 * kp, "h", "patches")
+        self.embeds = p.new(n * D, "f", "embeds")
+        self.d_embeds = p.new(n * D, "f", "d_embeds")
+        self.d_patches = p.new(n * G2 * kp, "h", "d_patches")
+
+        p.mark("vit_fwd")
+        # patch embedding: tok[n, 1+g, :] = patches[n, g, :] @ conv1^T   (no bias)
+        wpatch = pack_conv(p, self._w("conv1.weight").reshape(w, -1), None, need_bwd=build_backward, cin_pad=kp, name="conv1")
+        tok = Act(p.new(rows * w, "h", "tok"), 0, 1, 1, rows, w, w)
+        p._emit_conv((self.patches, 0), (G2 * kp, G2 * kp, kp), n, 1, G2, kp, wpatch.fwd, wpatch.fwd_npad, w, 1, None, None, None,
+                     (tok.buf, w), (T * w, T * w, w), tag="patch_embed")
+        p.emit("VIT_EMBED", i=[n, T, w], p=[(tok.buf, 0), (self._const("class_embedding"), 0), (self._const("positional_embedding"), 0)],
+               tag="cls+pos")
+        x = p.layer_norm(tok, self._const("ln_pre.weight"), self._const("ln_pre.bias"), name="ln_pre")
+        ln_pre_in, ln_pre_out = tok, x
+        for li in range(cfg.layers):
+            pre = f"transformer.resblocks.{li}"
+            y = p.layer_norm(x, self._const(pre + ".ln_1.weight"), self._const(pre + ".ln_1.bias"), name=pre + ".ln_1")
+            qkv = p.conv(y, pack_conv(p, self._w(pre + ".attn.in_proj_weight"), self._w(pre + ".attn.in_proj_bias"), name=pre + ".in_proj"),
+                         name=pre + ".qkv")
+            a = p.attention(qkv, cfg.heads, T, n, legacy_order=False, name=pre + ".attn")
+            x = p.conv(a, pack_conv(p, self._w(pre + ".attn.out_proj.weight"), self._w(pre + ".attn.out_proj.bias"), name=pre + ".out_proj"),
+                       res=x, name=pre + ".out_proj")
+            y = p.layer_norm(x, self._const(pre + ".ln_2.weight"), self._const(pre + ".ln_2.bias"), name=pre + ".ln_2")
+            u = p.conv(y, pack_conv(p, self._w(pre + ".mlp.c_fc.weight"), self._w(pre + ".mlp.c_fc.bias"), name=pre + ".c_fc"), name=pre + ".c_fc")
+            g = p.quick_gelu(u, name=pre + ".gelu")
+            x = p.conv(g, pack_conv(p, self._w(pre + ".mlp.c_proj.weight"), self._w(pre + ".mlp.c_proj.bias"), name=pre + ".c_proj"),
+                       res=x, name=pre + ".c_proj")
+        # ln_post on the class token of every image, then the fp32 projection
+        c = p.layer_norm(x, self._const("ln_post.weight"), self._const("ln_post.bias"), rows=n, ldx=T * w, name="ln_post")
+        proj = self._w("proj")  # [w, D]
+        p.emit("LINEAR_SMALL", flags=4, i=[n, w, D, w, D], p=[(c.buf, 0), (p.const(proj.t().contiguous(), "f", "proj^T"), 0), None, (self.embeds, 0)],
+               tag="proj")
+        p.mark("vit_bwd")
+        if not build_backward:
+            p.mark("vit_end")
+            return
+        # ---- backward
+        dc = Act(p.new(n * w, "h", "d_cls"), 0, 1, 1, n, w, w)
+        p.emit("LINEAR_SMALL", flags=8, i=[n, D, w, D, w], p=[(self.d_embeds, 0), (p.const(proj.contiguous(), "f", "proj"), 0), None, (dc.buf, 0)],
+               tag="d_proj")
+        p._grads[c.key()] = dc
+        p.backward()
+        d_tok = p.grad_of(ln_pre_in)
+        assert d_tok is not None and d_tok.ld == w
+        # d_patches[n, g, :] = d_tok[n, 1+g, :] @ conv1
+        p._emit_conv((d_tok.buf, d_tok.eoff + w), (T * w, T * w, w), n, 1, G2, w, wpatch.bwd, wpatch.bwd_npad, kp, 1, None, None, None,
+                     (self.d_patches, 0), (G2 * kp, G2 * kp, kp), tag="d_patch_embed")
+        p.mark("vit_end")
+
+    # ---- run-time API (stand-alone use; the fused step drives the shared plan directly)
+    def encode_patches(self, patches: th.Tensor = None) -> th.Tensor:
+        if patches is not None:
+            self.plan.view(self.patches, patches.shape).copy_(patches)
+        self.plan.run_range("vit_fwd", "vit_bwd")
+        return self.plan.view(self.embeds, (self.n, self.cfg.output_dim))
+
+    def backward_patches(self, d_embeds: th.Tensor = None) -> th.Tensor:
+        if d_embeds is not None:
+            self.plan.view(self.d_embeds, d_embeds.shape).copy_(d_embeds)
+        self.plan.run_range("vit_bwd", "vit_end")
+        return self.plan.view(self.d_patches, (self.n, self.cfg.grid ** 2, self.cfg.kpad))

@@ -1,0 +1,77 @@
+"""CPU tests of the host-side plan builder: the UNet / ViT op lists (graph walk, weight packing, strides,
+hand-scheduled backward) are executed with the test-only PyTorch interpreter and compared with the oracle's
+forward and autograd input gradients.  No CUDA involved; the same op lists run through libcgd_b200 on the GPU."""
+import numpy as np
+import pytest
+import torch as th
+
+from clip_guided_diffusion_b200 import unet as pu
+from clip_guided_diffusion_b200 import vit as pv
+from oracle.unet import UNetModel, tiny_config, seeded_init_
+from oracle.clip_vit import CLIPVisualOnly, ViTConfig as OViTConfig
+from tests.plan_interp import Interp
+
+
+def rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def cos(a, b):
+    return float(th.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0))
+
+
+def _prod_cfg(ocfg):
+    return pu.UNetConfig(image_size=ocfg.image_size, model_channels=ocfg.model_channels, num_res_blocks=ocfg.num_res_blocks,
+                         channel_mult=ocfg.channel_mult, attention_resolutions=ocfg.attention_resolutions,
+                         num_heads=ocfg.num_heads, num_head_channels=ocfg.num_head_channels, class_cond=ocfg.class_cond,
+                         num_classes=ocfg.num_classes, use_new_attention_order=ocfg.use_new_attention_order)
+
+
+@pytest.mark.parametrize("new_order,cond", [(False, True), (True, False)])
+def test_unet_plan_matches_oracle(new_order, cond):
+    th.manual_seed(0)
+    ocfg = tiny_config(image_size=32, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(16,),
+                       class_cond=cond, use_new_attention_order=new_order)
+    oracle = seeded_init_(UNetModel(ocfg)).eval()
+    B = 2
+    net = pu.UNetB200(_prod_cfg(ocfg), oracle.state_dict(), batch=B, device="cpu", seed_scale=64.0)
+    it = Interp(net.plan)
+    x = th.randn(B, 3, 32, 32)
+    t = th.tensor([7.0, 431.0])
+    y = th.tensor([3, 8]) if cond else None
+    net.set_inputs(x, t, y)
+    it.run_range("emb", "bwd")
+    xo = x.clone().requires_grad_()
+    ref = oracle(xo, t, y)
+    out = net.out_view.clone()
+    assert rel(out, ref.detach()) < 2e-2, rel(out, ref.detach())
+    d_out = th.randn(B, 6, 32, 32) * 0.1
+    (gref,) = th.autograd.grad((ref * d_out).sum(), xo)
+    sv = net.seed_view
+    sv[:, :, :6] = (d_out * net.seed_scale).reshape(B, 6, -1).permute(0, 2, 1).half()
+    it.run_range("bwd", "end")
+    g = net.dx_view / net.seed_scale
+    assert cos(g, gref) > 0.999 and rel(g, gref) < 4e-2, (cos(g, gref), rel(g, gref))
+
+
+def test_vit_plan_matches_oracle():
+    th.manual_seed(0)
+    ocfg = OViTConfig(64, 32, 128, 2, 64)
+    oracle = seeded_init_(CLIPVisualOnly(ocfg), seed=5).eval()
+    n = 3
+    cfg = pv.ViTConfig(64, 32, 128, 2, 64)
+    assert pv.vit_config_from_state_dict(oracle.state_dict()) == cfg
+    net = pv.ViTB200(cfg, oracle.state_dict(), n_images=n, device="cpu")
+    it = Interp(net.plan)
+    img = th.randn(n, 3, 64, 64, requires_grad=True)
+    ref = oracle.encode_image(img)
+    net.plan.view(net.patches, (n, 4, cfg.kpad)).copy_(Interp._patchify(img.detach(), 32, cfg.kpad))
+    it.run_range("vit_fwd", "vit_bwd")
+    emb = net.plan.view(net.embeds, (n, 64)).clone()
+    assert rel(emb, ref.detach()) < 2e-2, rel(emb, ref.detach())
+    d_emb = th.randn(n, 64)
+    (gref,) = th.autograd.grad((ref * d_emb).sum(), img)
+    net.plan.view(net.d_embeds, (n, 64)).copy_(d_emb)
+    it.run_range("vit_bwd", "vit_end")
+    g = Interp._unpatchify(net.plan.view(net.d_patches, (n, 4, cfg.kpad)).float(), 32, 64)
+    assert cos(g, gref) > 0.999 and rel(g, gref) < 4e-2, (cos(g, gref), rel(g, gref))
