@@ -1,0 +1,404 @@
+"""The guided sampling step engine: UNet fwd -> cond_fn (cutouts, CLIP fwd/bwd, losses) -> UNet dgrad -> update.
+
+Replaces the L1 <-> L3 <-> L2 ping-pong the reference executes once per timestep:
+``p_mean_variance`` + ``cond_fn`` (cgd/cgd.py:151-239) + ``-autograd.grad`` (cgd/cgd.py:228) + the ancestral / DDIM
+update.  One op plan holds both networks and every guidance kernel in a single arena; a whole step is ~1.3k kernel
+launches replayed from one CUDA graph, fed per step by one small pinned H2D copy (scalars, cutout windows, t, y).
+
+Surfaces kept: ``cond_fn(x, t, out, y=None)``, ``MakeCutouts``, ``model(x, timesteps, y)``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch as th
+
+from . import _lib
+from ._lib import SC
+from .plan import Plan
+from .unet import IN_PAD, UNetB200, UNetConfig
+from .vit import ViTB200, ViTConfig
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)  # cgd/clip_util.py:45
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+class MakeCutouts(th.nn.Module):
+    """cgd/modules.py:5-66 surface: same constructor, ``cached_coords``, ``cache_coordinates`` and the same CPU-generator
+    draw order (3 draws per cutout: size, offsetx, offsety).  ``forward`` runs the batched CUDA cutout kernel and
+    returns ``[cutn*B, 3, cut_size, cut_size]`` fp32 (un-normalised pooled cutouts, like the reference)."""
+
+    def __init__(self, cut_size: int, num_cutouts: int, cutout_size_power: float = 1.0, use_augs: bool = False):
+        super().__init__()
+        if use_augs:
+            raise NotImplementedError("torchvision augmentations are outside the B200 hot path (the reference CLI hard-disables "
+                                      "them, cgd/cgd.py:402)")
+        self.cut_size, self.cutn, self.cut_pow = cut_size, num_cutouts, cutout_size_power
+        self.cached_coords = None
+
+    def _generate_coords(self, side_x: int, side_y: int, cutn: int):
+        max_size = min(side_y, side_x)
+        min_size = min(side_y, side_x, self.cut_size)
+        coords = []
+        for _ in range(cutn):
+            size = int(th.rand([]) ** self.cut_pow * (max_size - min_size) + min_size)
+            offsetx = th.randint(0, side_x - size + 1, ()).item()
+            offsety = th.randint(0, side_y - size + 1, ()).item()
+            coords.append((offsetx, offsety, size))
+        return coords
+
+    def cache_coordinates(self, side_x: int, side_y: int):
+        self.cached_coords = self._generate_coords(side_x, side_y, self.cutn)
+
+    def coords_for(self, side_x, side_y, use_cache=False, num_cutouts_override=None):
+        cutn = num_cutouts_override if num_cutouts_override is not None else self.cutn
+        if use_cache and self.cached_coords is not None:
+            return self.cached_coords[:cutn]
+        return self._generate_coords(side_x, side_y, cutn)
+
+    def forward(self, input: th.Tensor, use_cache: bool = False, num_cutouts_override: int = None):
+        import ctypes
+        if not input.is_cuda:
+            raise _lib.CgdError("MakeCutouts.forward runs on the GPU only (no CPU fallback)")
+        B, C, H, W = input.shape
+        assert C == 3
+        coords = self.coords_for(H, W, use_cache, num_cutouts_override)  # sic: (H, W) passed as (side_x, side_y), modules.py:52
+        cs = self.cut_size
+        x = input.detach().float().contiguous()
+        cdev = th.tensor(coords, dtype=th.int32, device=x.device)
+        out = th.empty(len(coords) * B, 1, 3 * cs * cs, dtype=th.float16, device=x.device)
+        mean = (ctypes.c_float * 3)(0.5, 0.5, 0.5)  # with std 0.5 and the kernel's (x+1)/2 this yields the raw pooled value
+        std = (ctypes.c_float * 3)(0.5, 0.5, 0.5)
+        lib = _lib.load()
+        # patch = cut_size -> a single "patch" per cutout whose (c, ky, kx) order is exactly CHW
+        rc = lib.cgd_cutouts_fwd(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(cdev.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                 ctypes.c_int64(B), ctypes.c_int64(H), ctypes.c_int64(W), ctypes.c_int64(len(coords)),
+                                 ctypes.c_int64(cs), ctypes.c_int64(cs), ctypes.c_int64(3 * cs * cs), mean, std,
+                                 ctypes.c_void_p(th.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "cgd_cutouts_fwd")
+        return out.view(len(coords) * B, 3, cs, cs).float()
+
+
+class EngineModel:
+    """What the loops and ``p_sample`` receive as ``model``: ``model(x, timesteps, y) -> [B, 6, H, W]``."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.num_classes = engine.unet.num_classes
+        self.dtype = th.float16
+
+    def __call__(self, x, timesteps, y=None):
+        return self.engine.unet(x, timesteps, y)
+
+    def parameters(self):
+        yield self.engine.plan.arena
+
+    def eval(self):
+        return self
+
+    def requires_grad_(self, flag=False):
+        return self
+
+    def convert_to_fp16(self):
+        return self
+
+
+class GuidedStepB200:
+    """Engine for one (local batch, H, W, cutn, CLIP tower) configuration on one GPU."""
+
+    def __init__(self, unet_cfg: UNetConfig, unet_sd: dict, vit_cfg: ViTConfig = None, vit_sd: dict = None, *, batch: int,
+                 height: int = None, width: int = None, num_cutouts: int = 16, max_prompts: int = 1, clip_guidance_scale=1000.0,
+                 tv_scale=150.0, range_scale=50.0, sat_scale=0.0, use_magnitude=False, device="cuda", seed_scale=16.0,
+                 vit_grad_scale=1.0, conv_impl=0, rank: int = 0, world_size: int = 1, use_graph: bool = True):
+        self.device = th.device(device)
+        self.B = batch
+        self.rank, self.world = rank, world_size
+        self.global_batch = batch * world_size
+        self.H = height or unet_cfg.image_size
+        self.W = width or unet_cfg.image_size
+        self.cutn = num_cutouts if vit_cfg is not None else 0
+        self.P = max_prompts
+        self.scales = dict(cgs=float(clip_guidance_scale), tv=float(tv_scale), rng=float(range_scale), sat=float(sat_scale))
+        self.use_magnitude = bool(use_magnitude)
+        self.seed_scale, self.vit_grad_scale = float(seed_scale), float(vit_grad_scale)
+        self.use_graph = use_graph and self.device.type == "cuda"
+        self.plan = p = Plan(conv_impl=conv_impl)
+        B, H, W, HW = self.B, self.H, self.W, self.H * self.W
+        self.unet = UNetB200(unet_cfg, unet_sd, batch=B, height=H, width=W, device=device, seed_scale=seed_scale, plan=p,
+                             build_backward=vit_cfg is not None)
+        n3 = B * 3 * HW
+        self.sc = p.new(SC["COUNT"], "f", "scalars")
+        self.noise = p.new(n3, "f", "noise")
+        self.x0 = p.new(n3, "f", "pred_xstart")
+        self.mean = p.new(n3, "f", "mean")
+        self.var = p.new(n3, "f", "variance")
+        self.logvar = p.new(n3, "f", "log_variance")
+        self.x_inb = p.new(n3, "f", "x_in")
+        self.g = p.new(n3, "f", "g")
+        self.sample = p.new(n3, "f", "sample")
+        self.loss = p.new(4 * B, "f", "losses")  # [clip | tv | range | sat] per image
+        p.mark("pmv")
+        p.emit("PMV_BLEND", i=[B, HW, 3 * B], p=[(self.unet.x_in, 0), (self.unet.out, 0), (self.sc, 0), (self.x0, 0), (self.mean, 0),
+                                                 (self.var, 0), (self.logvar, 0), (self.x_inb, 0), (self.loss, B)], tag="p_mean_variance+blend")
+        p.mark("cond")
+        self.vit = None
+        if vit_cfg is not None:
+            cutn, cs, ps, kp, D = self.cutn, vit_cfg.input_resolution, vit_cfg.patch_size, vit_cfg.kpad, vit_cfg.output_dim
+            self.vit_cfg = vit_cfg
+            self.coords = p.new(cutn * 3, "i32", "cutout_coords")
+            self.targets = p.new(self.P * D, "f", "target_embeds")
+            self.weights = p.new(self.P, "f", "prompt_weights")
+            self.g_clip = p.new(n3, "f", "g_clip")
+            self.dx_direct = p.new(n3, "f", "dx_direct")
+            self.fg_ws = p.new(128, "f", "final_grad_ws")
+            self.vit = ViTB200(vit_cfg, vit_sd, n_images=cutn * B, device=device, plan=p)
+            p.mark("cut_fwd")
+            p.emit("CUTOUTS_FWD", i=[B, H, W, cutn, cs, ps, kp], f=[*CLIP_MEAN, *CLIP_STD], p=[(self.x_inb, 0), (self.coords, 0), (self.vit.patches, 0)],
+                   tag="make_cutouts+normalize")
+            p.mark("sph")
+            p.emit("SPHERICAL", i=[cutn, B, self.P, D], f=[self.scales["cgs"], self.vit_grad_scale],
+                   p=[(self.vit.embeds, 0), (self.targets, 0), (self.weights, 0), (self.vit.d_embeds, 0), (self.loss, 0)], tag="spherical_dist_loss")
+            p.mark("cut_bwd")
+            p.emit("CUTOUTS_BWD", i=[B, H, W, cutn, cs, ps, kp], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
+                   p=[(self.vit.d_patches, 0), (self.coords, 0), (self.g_clip, 0)], tag="d_make_cutouts")
+            p.mark("guide")
+            p.emit("GUIDE_GRAD", i=[B, H, W, IN_PAD], f=[self.scales["tv"], self.scales["rng"], self.scales["sat"], self.seed_scale],
+                   p=[(self.x_inb, 0), (self.x0, 0), (self.g_clip, 0), (self.sc, 0), (self.unet.seed, 0), (self.dx_direct, 0), (self.loss, B)],
+                   tag="tv+range+sat")
+            p.mark("final")
+            p.emit("FINAL_GRAD", flags=1 if self.use_magnitude else 0, i=[B, HW], f=[1.0 / self.seed_scale, 0.05],
+                   p=[(self.dx_direct, 0), (self.unet.dx, 0), (self.g, 0), (self.fg_ws, 0)], tag="-grad")
+        n = n3
+        p.mark("upd_anc_g")
+        p.emit("SAMPLE_ANCESTRAL", i=[n], p=[(self.mean, 0), (self.var, 0), (self.logvar, 0), (self.g, 0), (self.noise, 0), (self.sc, 0), (self.sample, 0)])
+        p.mark("upd_anc")
+        p.emit("SAMPLE_ANCESTRAL", i=[n], p=[(self.mean, 0), (self.var, 0), (self.logvar, 0), None, (self.noise, 0), (self.sc, 0), (self.sample, 0)])
+        p.mark("upd_ddim_g")
+        p.emit("SAMPLE_DDIM", i=[n], p=[(self.unet.x_in, 0), (self.x0, 0), (self.g, 0), (self.noise, 0), (self.sc, 0), (self.sample, 0)])
+        p.mark("upd_ddim")
+        p.emit("SAMPLE_DDIM", i=[n], p=[(self.unet.x_in, 0), (self.x0, 0), None, (self.noise, 0), (self.sc, 0), (self.sample, 0)])
+        p.mark("engine_end")
+        p.finalize(device)
+        self.model = EngineModel(self)
+        self.shape = (B, 3, H, W)
+        # pinned staging for the per-step host->device refresh
+        self._n_stage = SC["COUNT"] * 4 + self.cutn * 3 * 4 + B * 4 + B * 8
+        pin = self.device.type == "cuda"
+        self._stage = th.zeros(self._n_stage, dtype=th.uint8, pin_memory=pin)
+        self._graphs = {}
+        self._last_out = None
+        self._fwd_valid = False
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ------------------------------------------------------------------ views
+    def v(self, buf, shape=None):
+        return self.plan.view(buf, shape)
+
+    def img(self, buf):
+        return self.plan.view(buf, self.shape)
+
+    def set_targets(self, target_embeds: th.Tensor, weights: th.Tensor):
+        """target_embeds [P, D] (un-normalised is fine: the loss normalises, cgd/losses.py:12-13); weights already divided by
+        their |sum| like cgd/cgd.py:102-105."""
+        P = target_embeds.shape[0]
+        if P != self.P:
+            raise ValueError(f"engine was built for {self.P} prompt(s), got {P}")
+        if self.B > 1 and P > 1:
+            raise RuntimeError("the reference's spherical-loss broadcast is only defined for batch 1 or a single prompt (quirk B1)")
+        self.v(self.targets, (P, self.vit_cfg.output_dim)).copy_(target_embeds.detach().float())
+        self.v(self.weights, (P,)).copy_(weights.detach().float())
+
+    # ------------------------------------------------------------------ RNG (torch generators: seed parity)
+    def local_rows(self, t: th.Tensor) -> th.Tensor:
+        return t[self.rank * self.B:(self.rank + 1) * self.B]
+
+    def draw_initial_noise(self, shape=None) -> th.Tensor:
+        full = th.randn(self.global_batch, 3, self.H, self.W, device=self.device)
+        return self.local_rows(full).contiguous()
+
+    def draw_noise(self) -> th.Tensor:
+        """th.randn_like(x) of the reference; with several ranks every rank draws the full batch and keeps its rows."""
+        if self.world == 1:
+            return self.img(self.noise).normal_()
+        full = th.randn(self.global_batch, 3, self.H, self.W, device=self.device)
+        self.img(self.noise).copy_(self.local_rows(full))
+        return self.img(self.noise)
+
+    def draw_classes(self) -> th.Tensor:
+        full = th.randint(0, self.unet.num_classes, (self.global_batch,), device=self.device)
+        return self.local_rows(full)
+
+    # ------------------------------------------------------------------ segment-wise execution (API-parity path)
+    def _push_scalars(self, sc: np.ndarray):
+        self.v(self.sc).copy_(th.from_numpy(sc), non_blocking=True)
+
+    def unet_forward(self, diffusion, x, t_index: int, y=None, fac_index=None) -> dict:
+        if fac_index is None:
+            fac_index = t_index
+        self._cur_t = t_index
+        self._push_scalars(diffusion.scalar_table(t_index, fac_index))
+        ts = th.full((self.B,), diffusion.model_timestep(t_index), dtype=th.float32)
+        self.unet.set_inputs(x, ts.to(self.device, non_blocking=True), y)
+        self.plan.run_range("unet_emb", "unet_bwd")
+        self.plan.run_range("pmv", "cond")
+        self._fwd_valid = True
+        out = {"mean": self.img(self.mean), "variance": self.img(self.var), "log_variance": self.img(self.logvar),
+               "pred_xstart": self.img(self.x0), "engine": self}
+        self._last_out = out
+        return out
+
+    def cond_grad(self, diffusion, coords, fac_index: int) -> th.Tensor:
+        """-d(loss)/dx for the last unet_forward (what cond_fn returns)."""
+        if not self._fwd_valid:
+            raise RuntimeError("cond_fn called without a preceding p_mean_variance on this engine")
+        if self.vit is None:
+            raise RuntimeError("engine built without a CLIP tower")
+        if fac_index != self._cur_t:  # quirk B2: fac follows the closure's current_timestep, not t
+            sc = diffusion.scalar_table(self._cur_t, fac_index)
+            self._push_scalars(sc)
+            self.plan.run_range("pmv", "cond")
+        assert len(coords) == self.cutn, "cutout count is fixed per engine"
+        self.v(self.coords, (self.cutn, 3)).copy_(th.tensor(coords, dtype=th.int32), non_blocking=True)
+        for a, b in (("cut_fwd", "sph"), ("vit_fwd", "vit_bwd"), ("sph", "cut_bwd"), ("vit_bwd", "vit_end"), ("cut_bwd", "guide"),
+                     ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g")):
+            self.plan.run_range(a, b)
+        return self.img(self.g)
+
+    def update(self, diffusion, mode, t_index, g, noise, eta=0.0) -> th.Tensor:
+        if mode == "ddim" and eta != 0.0:
+            self.v(self.sc)[SC["ETA"]] = float(eta)
+        if noise.data_ptr() != self.v(self.noise).data_ptr():
+            self.img(self.noise).copy_(noise)
+        if g is not None and g.data_ptr() != self.v(self.g).data_ptr():
+            self.img(self.g).copy_(g)
+        name = ("upd_anc" if mode == "ancestral" else "upd_ddim") + ("_g" if g is not None else "")
+        order = ["upd_anc_g", "upd_anc", "upd_ddim_g", "upd_ddim", "engine_end"]
+        self.plan.run_range(name, order[order.index(name) + 1])
+        self._fwd_valid = False
+        return self.img(self.sample).clone()
+
+    # ------------------------------------------------------------------ fused step (one CUDA graph)
+    def can_fuse(self, cond_fn, clip_denoised, denoised_fn) -> bool:
+        return (isinstance(cond_fn, CondFnB200) and cond_fn.engine is self and not clip_denoised and denoised_fn is None
+                and cond_fn.fusable())
+
+    def _run_all(self, mode, runner=None):
+        pr = runner or self.plan.run_range
+        pr("unet_emb", "unet_bwd")
+        pr("pmv", "cond")
+        pr("cut_fwd", "sph")
+        pr("vit_fwd", "vit_bwd")
+        pr("sph", "cut_bwd")
+        pr("vit_bwd", "vit_end")
+        pr("cut_bwd", "guide")
+        pr("guide", "final")
+        pr("unet_bwd", "unet_end")
+        pr("final", "upd_anc_g")
+        if mode == "ancestral":
+            pr("upd_anc_g", "upd_anc")
+        else:
+            pr("upd_ddim_g", "upd_ddim")
+
+    def launches_per_step(self, mode="ddim") -> int:
+        m = self.plan.marks
+        segs = [("unet_emb", "unet_bwd"), ("pmv", "cond"), ("cut_fwd", "sph"), ("vit_fwd", "vit_bwd"), ("sph", "cut_bwd"), ("vit_bwd", "vit_end"),
+                ("cut_bwd", "guide"), ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g"),
+                ("upd_anc_g", "upd_anc") if mode == "ancestral" else ("upd_ddim_g", "upd_ddim")]
+        return sum(self.plan.num_launches(m[a], m[b] - m[a]) for a, b in segs)
+
+    def stage_step(self, sc: np.ndarray, coords, t_model: float, y=None):
+        """One pinned staging buffer -> small async H2D copies (classes, scalars, timestep, cutout windows)."""
+        st = self._stage
+        o = self.B * 8  # [0, 8B): int64 classes (kept first for alignment)
+        self.h2d_bytes = 0
+        if y is not None and self.unet.cfg.class_cond:
+            if y.device.type == "cpu":
+                st[0:o].view(th.int64).copy_(y)
+                self.v(self.unet.y_in).view(th.uint8).copy_(st[0:o], non_blocking=True)
+                self.h2d_bytes += o
+            else:
+                self.v(self.unet.y_in).copy_(y)
+        n = SC["COUNT"] * 4
+        st[o:o + n].view(th.float32).copy_(th.from_numpy(sc))
+        self.v(self.sc).view(th.uint8).copy_(st[o:o + n], non_blocking=True)
+        o += n
+        n = self.B * 4
+        st[o:o + n].view(th.float32).fill_(t_model)
+        self.v(self.unet.t_in).view(th.uint8).copy_(st[o:o + n], non_blocking=True)
+        o += n
+        self.h2d_bytes += SC["COUNT"] * 4 + self.B * 4
+        if self.cutn:
+            n = self.cutn * 12
+            st[o:o + n].view(th.int32).copy_(th.tensor(coords, dtype=th.int32).view(-1))
+            self.v(self.coords).view(th.uint8).copy_(st[o:o + n], non_blocking=True)
+            self.h2d_bytes += n
+
+    def fused_step(self, diffusion, mode, t_index, img, y, cond_fn, eta=0.0) -> dict:
+        fac_index = cond_fn.current_timestep
+        coords = cond_fn.next_coords(self.H, self.W)
+        sc = diffusion.scalar_table(t_index, fac_index, eta)
+        self.stage_step(sc, coords, diffusion.model_timestep(t_index), y)
+        xin = self.img(self.unet.x_in)
+        if img.data_ptr() != xin.data_ptr():
+            xin.copy_(img, non_blocking=True)
+        # RNG order: ancestral draws before cond_fn, DDIM after (values are identical either way: the generator is only
+        # consumed by this draw within a step; cutout windows come from the CPU generator)
+        self.draw_noise()
+        self.replay(mode)
+        return {"sample": self.img(self.sample).clone(), "pred_xstart": self.img(self.x0).clone()}
+
+    def replay(self, mode):
+        if not self.use_graph:
+            self._run_all(mode)
+            return
+        g = self._graphs.get(mode)
+        if g is None:
+            self._run_all(mode)  # warm-up: sets kernel attributes, touches every buffer
+            th.cuda.synchronize()
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g):
+                self._run_all(mode)
+            self._graphs[mode] = g
+        g.replay()
+
+    def losses(self) -> dict:
+        """per-image loss terms of the last step (device->host sync; logging only, like tqdm.write at cgd/cgd.py:234-236)"""
+        l = self.v(self.loss, (4, self.B)).cpu()
+        return {"clip": l[0], "tv": l[1], "range": l[2], "sat": l[3]}
+
+
+class CondFnB200:
+    """The reference's ``cond_fn(x, t, out, y=None)`` closure (cgd/cgd.py:151-239) bound to an engine, including its
+    ``current_timestep`` bookkeeping (quirk B2) and the reduce_clip / progressive_cutout / cached_cutouts switches."""
+
+    with_grad = True
+
+    def __init__(self, engine: GuidedStepB200, diffusion, make_cutouts: MakeCutouts, *, cached_cutouts=False, reduce_clip=False,
+                 progressive_cutout=False):
+        self.engine, self.diffusion, self.make_cutouts = engine, diffusion, make_cutouts
+        self.cached_cutouts, self.reduce_clip, self.progressive_cutout = cached_cutouts, reduce_clip, progressive_cutout
+        self.current_timestep = diffusion.num_timesteps - 1  # cgd/cgd.py:265
+        if progressive_cutout:
+            raise NotImplementedError("progressive_cutout changes the per-step cutout count; one engine has a fixed cutn (SURVEY 8f next)")
+
+    def fusable(self):
+        return not self.reduce_clip
+
+    def step_done(self):  # cgd/cgd.py:267
+        self.current_timestep -= 1
+
+    def next_coords(self, H, W):
+        return self.make_cutouts.coords_for(H, W, use_cache=self.cached_cutouts, num_cutouts_override=self.engine.cutn)
+
+    def __call__(self, x, t, out, y=None):
+        eng = self.engine
+        if out.get("engine") is not eng:
+            raise RuntimeError("cond_fn: `out` must come from this engine's p_mean_variance (the UNet backward re-enters its saved "
+                               "activations)")
+        if self.reduce_clip:  # cgd/cgd.py:157-164
+            total = self.diffusion.num_timesteps
+            pct = (total - self.current_timestep) / total
+            if pct < 0.7 and int((pct - 0.2) * total) % 4 != 0:
+                return th.zeros_like(x)
+        coords = self.next_coords(x.shape[2], x.shape[3])
+        return eng.cond_grad(self.diffusion, coords, self.current_timestep)

@@ -125,12 +125,14 @@ class Plan:
         self.handle = None
         self._c_ops = None
         self.marks: dict[str, int] = {}
+        self.bufs: list[Buf] = []
 
     # ------------------------------------------------------------------ memory
     def new(self, numel: int, dt: str, name: str = "") -> Buf:
         off = _round_up(self._size, 256)
         b = Buf(off, int(numel), dt, name)
         self._size = off + b.nbytes
+        self.bufs.append(b)
         return b
 
     def const(self, t: th.Tensor, dt: str, name: str = "") -> Buf:

@@ -60,7 +60,7 @@ class UNetB200:
     ``backward_input()`` (what autograd does for the reference).  One instance is bound to one (batch, H, W)."""
 
     def __init__(self, cfg: UNetConfig, state_dict: dict, batch: int, height: int = None, width: int = None, device="cuda",
-                 conv_impl: int = 0, seed_scale: float = 1.0, build_backward: bool = True):
+                 conv_impl: int = 0, seed_scale: float = 1.0, build_backward: bool = True, plan: Plan = None):
         self.cfg = cfg
         self.B = batch
         self.H = height or cfg.image_size
@@ -69,9 +69,11 @@ class UNetB200:
         self.dtype = th.float16
         self.seed_scale = float(seed_scale)
         self.sd = {k: v for k, v in state_dict.items()}
-        self.plan = Plan(conv_impl=conv_impl)
+        self.own_plan = plan is None
+        self.plan = plan or Plan(conv_impl=conv_impl)
         self._build(build_backward)
-        self.plan.finalize(device)
+        if self.own_plan:
+            self.plan.finalize(device)
         self.device = th.device(device)
         del self.sd
 
@@ -137,7 +139,7 @@ class UNetB200:
         self.dx = p.new(B * 3 * H * W, "f", "dx")
 
         # ---- prelude: timestep / class embedding and every ResBlock's scale-shift vector (x-independent)
-        p.mark("emb")
+        p.mark("unet_emb")
         te = p.new(B * mc, "f", "t_sin")
         p.emit("TIMESTEP_EMB", i=[B, mc], f=[1.0], p=[(self.t_in, 0), (te, 0)], tag="timestep_embedding")
         h1 = p.new(B * ted, "f", "te_h1")
@@ -189,7 +191,7 @@ class UNetB200:
                 b["e_up"] = self._resblock_prepare(b["prefix"] + (".2" if b["attn"] else ".1"), b["cout"])
 
         # ---- forward trunk
-        p.mark("fwd")
+        p.mark("unet_fwd")
         x0 = Act(p.new(B * H * W * IN_PAD, "h", "x_pm"), 0, B, H, W, IN_PAD, IN_PAD)
         p.emit("NCHW_TO_PM", i=[B, 3, H * W, IN_PAD], f=[1.0], p=[(self.x_in, 0), (x0.buf, 0)], tag="x->pixel-major")
         stem_w = self._conv_w("input_blocks.0.0", need_bwd=build_backward, cin_pad=IN_PAD)
@@ -217,9 +219,9 @@ class UNetB200:
         oc = cfg.out_channels
         p._emit_conv(p._ap(hn), p._strides(hn), B, H, W, hn.C, head_w.fwd, head_w.fwd_npad, oc, 9, head_w.bias, None, None,
                      (self.out, 0), (oc * HW, W, 1), out_f32=True, out_sc=HW, tag="head")
-        p.mark("bwd")
+        p.mark("unet_bwd")
         if not build_backward:
-            p.mark("end")
+            p.mark("unet_end")
             return
 
         # ---- backward: head dgrad from the seed, reverse tape, stem dgrad to fp32 NCHW
@@ -233,7 +235,7 @@ class UNetB200:
         assert d_stem is not None
         p._emit_conv(p._ap(d_stem), p._strides(d_stem), B, H, W, d_stem.C, stem_w.bwd, stem_w.bwd_npad, 3, 9, None, None, None,
                      (self.dx, 0), (3 * HW, W, 1), out_f32=True, out_sc=HW, tag="d_stem")
-        p.mark("end")
+        p.mark("unet_end")
 
     # ------------------------------------------------------------------ run-time API
     def _v(self, buf, shape):
@@ -247,10 +249,10 @@ class UNetB200:
             self._v(self.y_in, (self.B,)).copy_(y)
 
     def run_forward(self):
-        self.plan.run_range("emb", "bwd")
+        self.plan.run_range("unet_emb", "unet_bwd")
 
     def run_backward(self):
-        self.plan.run_range("bwd", "end")
+        self.plan.run_range("unet_bwd", "unet_end")
 
     @property
     def out_view(self):

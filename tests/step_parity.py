@@ -1,0 +1,120 @@
+"""Teacher-forced single-step parity of the engine against the oracle (shared by CPU-interpreter tests, GPU tests and
+__graft_entry__.smoke()).  Identical (x_t, t, y, noise, cutout windows, weights) go to both sides."""
+import copy
+
+import numpy as np
+import torch as th
+
+from clip_guided_diffusion_b200 import gaussian_diffusion as pgd
+from clip_guided_diffusion_b200 import guidance as pg
+from clip_guided_diffusion_b200 import unet as pu
+from clip_guided_diffusion_b200 import vit as pv
+from oracle import diffusion as od
+from oracle import guidance as og
+from oracle.clip_vit import CLIPVisualOnly, ViTConfig as OViTConfig
+from oracle.unet import UNetModel, seeded_init_, tiny_config
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-20))
+
+
+def cos(a, b):
+    return float(th.nn.functional.cosine_similarity(a.flatten().float(), b.flatten().float(), dim=0))
+
+
+def prod_unet_cfg(ocfg):
+    return pu.UNetConfig(image_size=ocfg.image_size, model_channels=ocfg.model_channels, num_res_blocks=ocfg.num_res_blocks,
+                         channel_mult=ocfg.channel_mult, attention_resolutions=ocfg.attention_resolutions, num_heads=ocfg.num_heads,
+                         num_head_channels=ocfg.num_head_channels, class_cond=ocfg.class_cond, num_classes=ocfg.num_classes,
+                         use_new_attention_order=ocfg.use_new_attention_order, rescale_timesteps=ocfg.rescale_timesteps)
+
+
+def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0, respacing="25", conv_impl=0, use_graph=False, P=1,
+               new_order=False):
+    ocfg = tiny_config(image_size=image, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(image // 2,),
+                       class_cond=True, use_new_attention_order=new_order)
+    ounet = seeded_init_(UNetModel(ocfg)).eval()
+    ovit_cfg = OViTConfig(32, 16, 128, 2, 64)
+    oclip = seeded_init_(CLIPVisualOnly(ovit_cfg), seed=5).eval()
+    for prm in list(ounet.parameters()) + list(oclip.parameters()):
+        prm.requires_grad_(False)
+    odiff = od.create_gaussian_diffusion(1000, "linear", respacing)
+    pdiff = pgd.create_gaussian_diffusion(1000, "linear", respacing)
+    g = th.Generator().manual_seed(99)
+    targets = th.randn(P, 64, generator=g)
+    weights = th.ones(P) / P
+    kw = dict(clip_guidance_scale=1000.0, tv_scale=150.0, range_scale=50.0, sat_scale=sat_scale)
+    eng = pg.GuidedStepB200(prod_unet_cfg(ocfg), ounet.state_dict(), pv.ViTConfig(32, 16, 128, 2, 64), oclip.state_dict(), batch=B,
+                            num_cutouts=cutn, max_prompts=P, use_magnitude=use_magnitude, device=device, conv_impl=conv_impl,
+                            use_graph=use_graph, **kw)
+    eng.set_targets(targets, weights)
+    return dict(ounet=ounet, oclip=oclip, odiff=odiff, pdiff=pdiff, eng=eng, targets=targets, weights=weights, kw=kw,
+                use_magnitude=use_magnitude, cutn=cutn, B=B, image=image)
+
+
+def oracle_step(ctx, mode, x, t_index, y, noise_seed, coords, fac_index):
+    odiff = ctx["odiff"]
+    cond = og.OracleCondFn(odiff, ctx["oclip"], ctx["targets"], ctx["weights"], cut_size=32, num_cutouts=ctx["cutn"],
+                           use_magnitude=ctx["use_magnitude"], **ctx["kw"])
+    cond.current_timestep = fac_index
+    grabbed = {}
+
+    def cond_fn(xx, tt, out, y=None):
+        g = cond(xx, tt, out, y=y, coords=coords)
+        grabbed["g"] = g.detach().clone()
+        return g
+
+    t = th.full((x.shape[0],), t_index, dtype=th.long)
+    th.manual_seed(noise_seed)
+    fn = odiff.p_sample_with_grad if mode == "ancestral" else odiff.ddim_sample_with_grad
+    out = fn(ctx["ounet"], x, t, clip_denoised=False, cond_fn=cond_fn, model_kwargs={"y": y})
+    out["g"] = grabbed["g"]
+    out["terms"] = cond.last_terms
+    return out
+
+
+def engine_step(ctx, mode, x, t_index, y, noise, coords, fac_index, runner=None, fused=False):
+    eng, pdiff = ctx["eng"], ctx["pdiff"]
+    sc = pdiff.scalar_table(t_index, fac_index, 0.0)
+    eng.stage_step(sc, coords, pdiff.model_timestep(t_index), y)
+    eng.img(eng.unet.x_in).copy_(x)
+    eng.img(eng.noise).copy_(noise)
+    if fused:
+        eng.replay(mode)
+    else:
+        eng._run_all(mode, runner)
+    if eng.device.type == "cuda":
+        th.cuda.synchronize()
+    return dict(sample=eng.img(eng.sample).float().cpu().clone(), pred_xstart=eng.img(eng.x0).float().cpu().clone(),
+                g=eng.img(eng.g).float().cpu().clone(), losses={k: v.clone() for k, v in eng.losses().items()})
+
+
+def make_inputs(ctx, seed=3):
+    B, image = ctx["B"], ctx["image"]
+    g = th.Generator().manual_seed(seed)
+    x = th.randn(B, 3, image, image, generator=g)
+    y = th.randint(0, 10, (B,), generator=g)
+    th.manual_seed(seed + 100)
+    noise = th.randn_like(x)  # == what the oracle draws right after manual_seed(seed + 100)
+    th.manual_seed(seed + 200)
+    coords = og.MakeCutouts(32, ctx["cutn"])._generate_coords(image, image, ctx["cutn"])
+    return x, y, noise, seed + 100, coords
+
+
+def compare(o, e):
+    return dict(cos_g=cos(e["g"], o["g"]), rel_g=rel(e["g"], o["g"]), rel_x0=rel(e["pred_xstart"], o["pred_xstart"]),
+                rel_sample=rel(e["sample"], o["sample"]))
+
+
+def run_tiny_step_parity(device="cuda:0", mode="ancestral", t_index=14, runner_factory=None, **build_kw):
+    ctx = build_tiny(device, **build_kw)
+    x, y, noise, nseed, coords = make_inputs(ctx)
+    o = oracle_step(ctx, mode, x, t_index, y, nseed, coords, fac_index=t_index)
+    runner = runner_factory(ctx["eng"]) if runner_factory else None
+    e = engine_step(ctx, mode, x, t_index, y, noise, coords, fac_index=t_index, runner=runner)
+    res = compare(o, e)
+    res["clip_loss_rel"] = abs(float(e["losses"]["clip"].sum()) - o["terms"]["clip"]) / (abs(o["terms"]["clip"]) + 1e-9)
+    res["tv_loss_rel"] = abs(float(e["losses"]["tv"].sum()) - o["terms"]["tv"]) / (abs(o["terms"]["tv"]) + 1e-9)
+    res["range_loss_rel"] = abs(float(e["losses"]["range"].sum()) - o["terms"]["range"]) / (abs(o["terms"]["range"]) + 1e-9)
+    return res

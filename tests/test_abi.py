@@ -1,0 +1,60 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/cgd_b200.h declares; the Python op tables
+match the header; product entry points fail loudly without CUDA (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch as th
+
+import __graft_entry__ as ge
+from clip_guided_diffusion_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "include", "cgd_b200.h")).read()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    ge.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(cgd_\w+)\s*\(", HEADER, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.cgd_abi_version() == 1
+
+
+def test_op_tables_match_header():
+    ops = dict((k, int(v)) for k, v in re.findall(r"CGD_OP_(\w+) = (\d+)", HEADER))
+    assert ops == _lib.OP
+    sc = dict((k, int(v)) for k, v in re.findall(r"CGD_SC_(\w+) = (\d+)", HEADER))
+    sc.pop("_COUNT", None)
+    exp = {k: v for k, v in _lib.SC.items() if k != "COUNT"}
+    assert sc == exp
+    assert ctypes.sizeof(_lib.CgdOp) == 8 + 24 * 8 + 8 * 4 + 12 * 8
+
+
+def test_plan_create_validates(lib):
+    bad = (_lib.CgdOp * 1)()
+    bad[0].code = 999
+    h = ctypes.c_void_p()
+    assert lib.cgd_plan_create(bad, 1, ctypes.byref(h)) != 0
+    assert b"unknown code" in lib.cgd_last_error()
+    bad[0].code = _lib.OP["CONV"]  # all-zero conv: rejected by argument validation before any CUDA call
+    assert lib.cgd_plan_create(bad, 1, ctypes.byref(h)) != 0
+    assert b"conv" in lib.cgd_last_error()
+
+
+@pytest.mark.skipif(th.cuda.is_available(), reason="CPU-only check")
+def test_no_cpu_fallback():
+    from clip_guided_diffusion_b200.plan import Plan
+    p = Plan()
+    b = p.new(16, "f")
+    p.emit("QGELU_FWD", i=[16], p=[(b, 0), (b, 0)])
+    p.finalize("cpu")
+    with pytest.raises(_lib.CgdError):
+        p.run()

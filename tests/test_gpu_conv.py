@@ -1,0 +1,110 @@
+"""GPU: the tcgen05 implicit-GEMM conv / GEMM kernel (and its SIMT verification twin) against a plain PyTorch fp32
+reference of the same op, across tile geometries, paddings, split-K, epilogues and output layouts."""
+import pytest
+import torch as th
+import torch.nn.functional as F
+
+from clip_guided_diffusion_b200.plan import Plan, pack_conv, Act
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, NB, H, W, Cin, Cout, taps, bias, res
+    ("conv3x3_64x64_c128", 1, 64, 64, 128, 128, 9, True, False),
+    ("conv3x3_32x32_c256_res", 2, 32, 32, 256, 256, 9, True, True),
+    ("conv3x3_16x16_c512_splitk", 1, 16, 16, 512, 512, 9, True, True),
+    ("conv3x3_8x8_c1024_tn2", 2, 8, 8, 1024, 1024, 9, True, False),
+    ("conv3x3_8x8_b1", 1, 8, 8, 512, 1024, 9, False, False),
+    ("conv3x3_256w_c64", 1, 4, 256, 64, 64, 9, True, False),
+    ("conv1x1_skip", 1, 32, 32, 512, 256, 1, True, False),
+    ("conv3x3_c192", 1, 32, 32, 192, 384, 9, True, False),
+    ("conv3x3_c576_bn192", 1, 16, 16, 384, 576, 9, True, True),
+    ("linear_m800_qkv", 1, 1, 800, 768, 2304, 1, True, False),
+    ("linear_m50", 1, 1, 50, 768, 768, 1, True, True),
+    ("linear_k3072", 1, 1, 800, 3072, 768, 1, True, True),
+]
+
+
+def _ref_conv(x, w, b, res, taps):
+    xf = x.float().permute(0, 3, 1, 2)
+    y = F.conv2d(xf, w.float(), b.float() if b is not None else None, padding=1 if taps == 9 else 0)
+    y = y.permute(0, 2, 3, 1)
+    return y + res.float() if res is not None else y
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_fwd_and_dgrad(case, impl):
+    name, NB, H, W, Cin, Cout, taps, has_b, has_r = case
+    if impl == 1 and NB * H * W * Cout * taps * Cin > 3e10:
+        pytest.skip("SIMT twin only on small cases")
+    th.manual_seed(0)
+    k = 3 if taps == 9 else 1
+    w = th.randn(Cout, Cin, k, k) * (taps * Cin) ** -0.5
+    b = th.randn(Cout) * 0.1 if has_b else None
+    plan = Plan(conv_impl=impl)
+    cw = pack_conv(plan, w, b, need_bwd=True, name=name)
+    x = plan.act(NB, H, W, Cin, "x")
+    res = plan.act(NB, H, W, Cout, "res") if has_r else None
+    y = plan.conv(x, cw, res=res, name=name)
+    dy = plan.act(NB, H, W, Cout, "dy")
+    plan._grads[y.key()] = dy
+    plan.mark("bwd")
+    plan.backward()
+    plan.mark("end")
+    plan.finalize("cuda")
+    xv = plan.view(x.buf, (NB, H, W, Cin)).normal_()
+    rv = plan.view(res.buf, (NB, H, W, Cout)).normal_() if has_r else None
+    dyv = plan.view(dy.buf, (NB, H, W, Cout)).normal_()
+    plan.run(0, plan.marks["bwd"])
+    th.cuda.synchronize()
+    ref = _ref_conv(xv, w.cuda(), b.cuda() if has_b else None, rv, taps)
+    got = plan.view(y.buf, (NB, H, W, Cout)).float()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert th.isfinite(got).all() and err < 3e-3, f"{name} fwd impl={impl}: rel-to-max err {err:.3e}, got_max {float(got.abs().max()):.3e} ref_max {float(ref.abs().max()):.3e}"
+    # dgrad vs autograd of the reference
+    plan.run(plan.marks["bwd"], plan.marks["end"] - plan.marks["bwd"])
+    th.cuda.synchronize()
+    xg = xv.float().clone().requires_grad_()
+    yr = _ref_conv(xg, w.cuda(), None, None, taps)
+    (gref,) = th.autograd.grad((yr * dyv.float()).sum(), xg)
+    dx = plan.grad_of(x)
+    gg = plan.view(dx.buf, (NB, H, W, Cin)).float()
+    err = float((gg - gref).abs().max() / gref.abs().max())
+    assert th.isfinite(gg).all() and err < 3e-3, f"{name} dgrad impl={impl}: rel-to-max err {err:.3e}"
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_conv_special_layouts(impl):
+    """UNet head (fp32 NCHW out, 6 of 16 padded channels), stem dgrad (3 channels) and the ViT patch-embed geometry
+    (49 tokens per image written at a row offset with a batch stride)."""
+    th.manual_seed(1)
+    plan = Plan(conv_impl=impl)
+    B, H, W, C = 2, 16, 16, 128
+    w = th.randn(6, C, 3, 3) * (9 * C) ** -0.5
+    b = th.randn(6) * 0.1
+    cw = pack_conv(plan, w, b, need_bwd=False, name="head")
+    x = plan.act(B, H, W, C, "x")
+    out = plan.new(B * 6 * H * W, "f", "out")
+    plan._emit_conv(plan._ap(x), plan._strides(x), B, H, W, C, cw.fwd, cw.fwd_npad, 6, 9, cw.bias, None, None, (out, 0), (6 * H * W, W, 1),
+                    out_f32=True, out_sc=H * W, tag="head")
+    # patch-embed like: n images x 49 tokens, K=192, written to rows 1.. of a [n, 50, w] tensor
+    n, G2, T, K, wd = 5, 49, 50, 192, 128
+    wp = th.randn(wd, K) * K ** -0.5
+    cp = pack_conv(plan, wp, None, need_bwd=False, name="patch")
+    patches = plan.new(n * G2 * K, "h", "patches")
+    tok = plan.new(n * T * wd, "h", "tok")
+    plan._emit_conv((patches, 0), (G2 * K, G2 * K, K), n, 1, G2, K, cp.fwd, cp.fwd_npad, wd, 1, None, None, None, (tok, wd), (T * wd, T * wd, wd),
+                    tag="patch")
+    plan.finalize("cuda")
+    xv = plan.view(x.buf, (B, H, W, C)).normal_()
+    pvw = plan.view(patches, (n, G2, K)).normal_()
+    plan.run()
+    th.cuda.synchronize()
+    ref = F.conv2d(xv.float().permute(0, 3, 1, 2), w.cuda(), b.cuda(), padding=1)
+    got = plan.view(out, (B, 6, H, W))
+    assert float((got - ref).abs().max() / ref.abs().max()) < 3e-3
+    reft = pvw.float() @ wp.cuda().t()
+    gott = plan.view(tok, (n, T, wd)).float()
+    assert float((gott[:, 1:] - reft).abs().max() / reft.abs().max()) < 3e-3
+    assert float(gott[:, 0].abs().max()) == 0.0  # cls rows untouched

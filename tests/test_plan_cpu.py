@@ -40,7 +40,7 @@ def test_unet_plan_matches_oracle(new_order, cond):
     t = th.tensor([7.0, 431.0])
     y = th.tensor([3, 8]) if cond else None
     net.set_inputs(x, t, y)
-    it.run_range("emb", "bwd")
+    it.run_range("unet_emb", "unet_bwd")
     xo = x.clone().requires_grad_()
     ref = oracle(xo, t, y)
     out = net.out_view.clone()
@@ -49,7 +49,7 @@ def test_unet_plan_matches_oracle(new_order, cond):
     (gref,) = th.autograd.grad((ref * d_out).sum(), xo)
     sv = net.seed_view
     sv[:, :, :6] = (d_out * net.seed_scale).reshape(B, 6, -1).permute(0, 2, 1).half()
-    it.run_range("bwd", "end")
+    it.run_range("unet_bwd", "unet_end")
     g = net.dx_view / net.seed_scale
     assert cos(g, gref) > 0.999 and rel(g, gref) < 4e-2, (cos(g, gref), rel(g, gref))
 
