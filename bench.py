@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- diffusion-steps/sec of the CLIP-guided sampling step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                       # this framework, cfg2 per GPU
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference --steps K --warmup W               # the oracle port on the host CPU cores
+
+A "step" is one ddim_sample_with_grad iteration (UNet fwd -> cutouts -> CLIP ViT fwd/bwd -> losses -> UNet dgrad ->
+DDIM update) of BASELINE.json configs[1]: 256x256, ddim250, 1 image per GPU, 16 cutouts, ViT-B/32, synthetic noise and
+seeded random weights of the published architectures.  With N GPUs every rank owns one image (weak scaling, no
+data-path collective; one NCCL all-gather of the final images), and `value` counts image-steps per second.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch as th
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(image_size=256, respacing="ddim250", per_gpu_batch=1, cutn=16, clip="ViT-B/32")
+FLOP_PER_IMAGE_STEP = 4.775e12  # UNet 2.240+2.252, CLIP 0.141+0.143 TFLOP (fwd + dgrad)
+DOMINANT = dict(M=65536, N=256, K=2304)  # 256^2 x 256ch conv3x3: 31 % of the UNet FLOPs
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=float(d["bf16_tflops"]), sustained=float(d["bf16_tflops_sustained"]), hbm=float(d["hbm_gbs"]), src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def build_engine(device, rank, world):
+    from clip_guided_diffusion_b200 import gaussian_diffusion as gd
+    from clip_guided_diffusion_b200 import guidance as pg
+    from clip_guided_diffusion_b200 import unet as pu
+    from clip_guided_diffusion_b200 import vit as pv
+    from clip_guided_diffusion_b200 import weights as pw
+    ucfg = pu.config_for(CFG["image_size"], class_cond=True)
+    vcfg = pv.VIT_CONFIGS[CFG["clip"]]
+    usd = pw.seeded_state_dict(pw.unet_param_shapes(ucfg), seed=1234)
+    vsd = pw.seeded_state_dict(pw.vit_param_shapes(vcfg), seed=1235)
+    eng = pg.GuidedStepB200(ucfg, usd, vcfg, vsd, batch=CFG["per_gpu_batch"], num_cutouts=CFG["cutn"], device=device, rank=rank,
+                            world_size=world)
+    del usd, vsd
+    diff = gd.create_gaussian_diffusion(1000, "linear", CFG["respacing"])
+    th.manual_seed(0)
+    tgt = th.nn.functional.normalize(th.randn(1, vcfg.output_dim), dim=-1)
+    eng.set_targets(tgt, th.ones(1))
+    mk = pg.MakeCutouts(vcfg.input_resolution, CFG["cutn"])
+    cond = pg.CondFnB200(eng, diff, mk)
+    return eng, diff, cond
+
+
+def dominant_kernel_time(device, reps=24):
+    """Average duration of the dominant conv launch (256x256 pixels, 256 -> 256 channels, 3x3), rotating over buffers that
+    together exceed the 126 MB L2, CUDA events on the launching stream."""
+    from clip_guided_diffusion_b200.plan import Plan, pack_conv
+    th.manual_seed(0)
+    plan = Plan()
+    w = th.randn(256, 256, 3, 3) * (9 * 256) ** -0.5
+    cw = pack_conv(plan, w, th.zeros(256), need_bwd=False, name="dom")
+    nbuf = 4
+    for _ in range(nbuf):
+        x = plan.act(1, 256, 256, 256, "x")
+        plan.conv(x, cw, name="dom")
+    plan.finalize(device)
+    for b in plan.bufs:
+        if b.name == "x":
+            plan.view(b).normal_()
+    for _ in range(2):
+        plan.run()
+    th.cuda.synchronize()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    rounds = max(1, reps // nbuf)
+    e0.record()
+    for _ in range(rounds):
+        plan.run()
+    e1.record()
+    th.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / (rounds * nbuf)
+
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run for N>1)"
+    assert th.cuda.is_available(), "bench.py (own arm) needs a CUDA device; there is no CPU fallback"
+    th.cuda.set_device(local)
+    device = th.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    eng, diff, cond = build_engine(device, rank, world)
+    B = eng.B
+    T = diff.num_timesteps
+    y0 = th.zeros(eng.global_batch, dtype=th.long)
+
+    def step_resident(i, img):
+        y = eng.draw_classes()
+        out = eng.fused_step(diff, "ddim", i, img, y, cond, 0.0)
+        cond.step_done()
+        return out["sample"]
+
+    # ---------------- device-resident loop (value)
+    th.manual_seed(0)
+    img = eng.draw_initial_noise()
+    idx = T - 1
+    for _ in range(args.warmup):
+        img = step_resident(idx, img)
+        idx = max(idx - 1, 0)
+    if world > 1:
+        dist.barrier()
+    th.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        img = step_resident(idx, img)
+        idx = max(idx - 1, 0)
+    if world > 1:  # the run's single collective: gather the images of all ranks
+        gathered = [th.empty_like(img) for _ in range(world)]
+        dist.all_gather(gathered, img.contiguous())
+    e1.record()
+    th.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = th.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = float(ms.item())
+    finite = bool(th.isfinite(img).all())
+
+    # ---------------- end-to-end loop: host buffers, H2D of x_t and D2H of the sample inside every step
+    host_x = th.empty(B, 3, eng.H, eng.W, pin_memory=True)
+    host_out = th.empty(B, 3, eng.H, eng.W, pin_memory=True)
+    host_x.copy_(img.cpu())
+    idx_e = max(idx, 1)
+
+    def step_host(i):
+        y = th.randint(0, eng.unet.num_classes, (B,))  # host-side class draw, staged with the other per-step data
+        eng.img(eng.unet.x_in).copy_(host_x, non_blocking=True)
+        out = eng.fused_step(diff, "ddim", i, eng.img(eng.unet.x_in), y, cond, 0.0)
+        host_out.copy_(out["sample"], non_blocking=True)
+        th.cuda.current_stream().synchronize()
+        host_x.copy_(host_out)
+
+    for _ in range(min(3, args.warmup)):
+        step_host(idx_e)
+    if world > 1:
+        dist.barrier()
+    th.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step_host(idx_e)
+        idx_e = max(idx_e - 1, 0)
+    e1.record()
+    th.cuda.synchronize()
+    ms_e = th.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_e.item())
+    h2d = B * 3 * eng.H * eng.W * 4 + eng.h2d_bytes
+    d2h = B * 3 * eng.H * eng.W * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    launches = eng.launches_per_step("ddim")
+    value = args.steps * eng.global_batch / (ms_total * 1e-3)
+    e2e = args.steps * eng.global_batch / (ms_e2e * 1e-3)
+    # roofline of the dominant kernel, timed alone right after the step loops
+    t_dom = dominant_kernel_time(device)
+    flops_dom = 2.0 * DOMINANT["M"] * DOMINANT["N"] * DOMINANT["K"]
+    ach = flops_dom / t_dom / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dominant_conv_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    line = {
+        "metric": "diffusion-steps/sec", "value": value, "unit": "image-steps/s (1 step of one 256x256 image, 16 cutouts)",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate / norm / softmax / sampler)", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: image_size=256, respace=ddim250, batch=1 per GPU, cutn=16, ViT-B/32, class-cond UNet, "
+                               "seeded random weights", "global_batch": eng.global_batch, "parallelism": f"dp{world} (batch shard, no data-path collective)",
+                   "l2": "per-step working set (2.3 GB of packed weights + activations) exceeds the 126 MB L2; no explicit flush",
+                   "finite": finite},
+        "e2e": {"value": e2e, "unit": "image-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches * args.steps,
+        "launches_per_step": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"], "traffic": traffic,
+                     "kernel": "conv_tc_kernel<256> 256x256x256->256 3x3 (M=65536,N=256,K=2304)", "peak_source": pk["src"] + " burst (kernel timed alone)",
+                     "avg_launch_s": t_dom},
+        "step_tensor_frac": FLOP_PER_IMAGE_STEP * value / world / (pk["sustained"] * 1e12),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms (oracle port)
+def oracle_cpu_setup():
+    """The oracle (fp32 PyTorch restatement of the reference path) on the host cores -- the checker timed as the CPU baseline."""
+    from oracle import diffusion as od
+    from oracle import guidance as og
+    from oracle.clip_vit import VIT_CONFIGS, CLIPVisualOnly
+    from oracle.unet import UNetModel, config_for, seeded_init_
+    th.set_num_threads(os.cpu_count())
+    unet = seeded_init_(UNetModel(config_for(CFG["image_size"], True))).eval()
+    clip = seeded_init_(CLIPVisualOnly(VIT_CONFIGS[CFG["clip"]]), seed=1235).eval()
+    for p in list(unet.parameters()) + list(clip.parameters()):
+        p.requires_grad_(False)
+    diff = od.create_gaussian_diffusion(1000, "linear", CFG["respacing"])
+    tgt = th.nn.functional.normalize(th.randn(1, 512), dim=-1)
+    cond = og.OracleCondFn(diff, clip, tgt, th.ones(1), cut_size=224, num_cutouts=CFG["cutn"])
+    return unet, diff, cond
+
+
+def oracle_cpu_steps(unet, diff, cond, n_steps, x=None):
+    th.manual_seed(0)
+    B = CFG["per_gpu_batch"]
+    x = th.randn(B, 3, CFG["image_size"], CFG["image_size"]) if x is None else x
+    times = []
+    i = diff.num_timesteps - 1
+    for _ in range(n_steps):
+        t = th.full((B,), i, dtype=th.long)
+        y = th.randint(0, 1000, (B,))
+        t0 = time.perf_counter()
+        out = diff.ddim_sample_with_grad(unet, x, t, clip_denoised=False, cond_fn=cond, model_kwargs={"y": y})
+        times.append(time.perf_counter() - t0)
+        x = out["sample"]
+        cond.step_done()
+        i -= 1
+    return times, x
+
+
+def cpu_baseline(sample_steps=1):
+    unet, diff, cond = oracle_cpu_setup()
+    times, _ = oracle_cpu_steps(unet, diff, cond, sample_steps)
+    t = float(np.median(times))
+    return {"value": 1.0 / t, "unit": "image-steps/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{sample_steps} full cfg2 step(s) of the fp32 oracle port (PyTorch CPU, all host threads), {t:.2f} s/step"}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    unet, diff, cond = oracle_cpu_setup()
+    budget_s = 170.0
+    t_first, x = oracle_cpu_steps(unet, diff, cond, 1)  # warm-up step, also sizes the run
+    per = t_first[0]
+    n_timed = int(max(1, min(args.steps, budget_s // per)))
+    times, _ = oracle_cpu_steps(unet, diff, cond, n_timed, x)
+    total = float(sum(times))
+    value = n_timed / total
+    line = {"impl": "reference", "metric": "diffusion-steps/sec", "value": value, "unit": "image-steps/s (1 step of one 256x256 image, 16 cutouts)",
+            "n_gpus": args.gpus, "steps": n_timed, "requested_steps": args.steps, "warmup": 1, "ms_per_step": total / n_timed * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: image_size=256, respace=ddim250, batch=1, cutn=16, ViT-B/32 -- the reference's own "
+                                   "algorithm (fp32 oracle port; guided_diffusion / clip packages are not installable offline) on the host CPU",
+                       "global_batch": 1},
+            "cpu_baseline": {"value": value, "unit": "image-steps/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{n_timed} full cfg2 steps (bounded to ~{budget_s:.0f} s of CPU work; {args.steps} requested)"},
+            "e2e": {"value": value, "unit": "image-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

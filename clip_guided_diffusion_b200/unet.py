@@ -52,6 +52,42 @@ def config_for(image_size: int, class_cond: bool = True) -> UNetConfig:
     return UNetConfig(model_channels=256, **base)
 
 
+def topology(cfg: UNetConfig):
+    """Block list of the network (same walk as guided_diffusion.unet.UNetModel.__init__): input blocks after the stem,
+    the middle width, output blocks (with the width of the skip each one concatenates)."""
+    mc = cfg.model_channels
+    blocks_in, blocks_out = [], []
+    ch = int(cfg.channel_mult[0] * mc)
+    skip_chs = [ch]
+    ds = 1
+    idx = 1
+    for level, mult in enumerate(cfg.channel_mult):
+        for _ in range(cfg.num_res_blocks):
+            cout = int(mult * mc)
+            blocks_in.append(dict(prefix=f"input_blocks.{idx}", cin=ch, cout=cout, attn=ds in cfg.attention_ds, down=False))
+            ch = cout
+            skip_chs.append(ch)
+            idx += 1
+        if level != len(cfg.channel_mult) - 1:
+            blocks_in.append(dict(prefix=f"input_blocks.{idx}", cin=ch, cout=ch, attn=False, down=True))
+            skip_chs.append(ch)
+            ds *= 2
+            idx += 1
+    mid_ch = ch
+    idx = 0
+    for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
+        for i in range(cfg.num_res_blocks + 1):
+            ich = skip_chs.pop()
+            cout = int(mc * mult)
+            up = bool(level and i == cfg.num_res_blocks)
+            blocks_out.append(dict(prefix=f"output_blocks.{idx}", cin=ch + ich, cout=cout, attn=ds in cfg.attention_ds, up=up, ich=ich))
+            ch = cout
+            if up:
+                ds //= 2
+            idx += 1
+    return blocks_in, mid_ch, blocks_out
+
+
 IN_PAD = 64  # image channels are zero-padded to one 64-channel K slice for the stem conv / head dgrad
 
 
@@ -151,36 +187,7 @@ class UNetB200:
         if cfg.class_cond:
             p.emit("LABEL_ADD", i=[B, ted], p=[(self.emb, 0), (self._const("label_emb.weight"), 0), (self.y_in, 0)], tag="label_emb")
 
-        # network topology (same walk as guided_diffusion.unet.UNetModel.__init__)
-        blocks_in, blocks_out = [], []
-        ch = int(cfg.channel_mult[0] * mc)
-        skip_chs = [ch]
-        ds = 1
-        idx = 1
-        for level, mult in enumerate(cfg.channel_mult):
-            for _ in range(cfg.num_res_blocks):
-                cout = int(mult * mc)
-                blocks_in.append(dict(prefix=f"input_blocks.{idx}", cout=cout, attn=ds in cfg.attention_ds, down=False))
-                ch = cout
-                skip_chs.append(ch)
-                idx += 1
-            if level != len(cfg.channel_mult) - 1:
-                blocks_in.append(dict(prefix=f"input_blocks.{idx}", cout=ch, attn=False, down=True))
-                skip_chs.append(ch)
-                ds *= 2
-                idx += 1
-        mid_ch = ch
-        idx = 0
-        for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
-            for i in range(cfg.num_res_blocks + 1):
-                ich = skip_chs.pop()
-                cout = int(mc * mult)
-                up = bool(level and i == cfg.num_res_blocks)
-                blocks_out.append(dict(prefix=f"output_blocks.{idx}", cout=cout, attn=ds in cfg.attention_ds, up=up, ich=ich))
-                ch = cout
-                if up:
-                    ds //= 2
-                idx += 1
+        blocks_in, mid_ch, blocks_out = topology(cfg)
         # scale-shift vectors (prelude ops must precede the trunk)
         for b in blocks_in:
             b["e"] = self._resblock_prepare(b["prefix"] + ".0", b["cout"])

@@ -75,3 +75,19 @@ def test_vit_plan_matches_oracle():
     it.run_range("vit_bwd", "vit_end")
     g = Interp._unpatchify(net.plan.view(net.d_patches, (n, 4, cfg.kpad)).float(), 32, 64)
     assert cos(g, gref) > 0.999 and rel(g, gref) < 4e-2, (cos(g, gref), rel(g, gref))
+
+
+def test_param_inventories_match_oracle():
+    from clip_guided_diffusion_b200 import weights as pw
+    from oracle.unet import config_for as oconfig_for
+    from oracle.clip_vit import VIT_CONFIGS as OV
+    for size, cond in [(64, True), (256, True), (256, False), (512, True)]:
+        with th.device("meta"):
+            m = UNetModel(oconfig_for(size, cond))
+        ref = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert pw.unet_param_shapes(pu.config_for(size, cond)) == ref
+    for name in ("ViT-B/32", "ViT-B/16", "ViT-L/14"):
+        with th.device("meta"):
+            m = CLIPVisualOnly(OV[name])
+        ref = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert pw.vit_param_shapes(pv.VIT_CONFIGS[name]) == ref
