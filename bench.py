@@ -140,9 +140,12 @@ def run_ours(args):
     y0 = th.zeros(eng.global_batch, dtype=th.long)
 
     def step_resident(i, img):
+        # x_t is fresh synthetic noise every step: with random (non-denoising) weights a chained trajectory diverges within a
+        # few steps (pred_xstart ~ 1e3 and growing), which says nothing about throughput; timing is value-independent
+        img = eng.draw_initial_noise()
         y = eng.draw_classes()
         out = eng.fused_step(diff, "ddim", i, img, y, cond, 0.0)
-        cond.step_done()
+        cond.current_timestep = max(cond.current_timestep - 1, 0)
         return out["sample"]
 
     # ---------------- device-resident loop (value)
@@ -180,7 +183,7 @@ def run_ours(args):
     # ---------------- end-to-end loop: host buffers, H2D of x_t and D2H of the sample inside every step
     host_x = th.empty(B, 3, eng.H, eng.W, pin_memory=True)
     host_out = th.empty(B, 3, eng.H, eng.W, pin_memory=True)
-    host_x.copy_(img.cpu())
+    host_x.copy_(th.randn(B, 3, eng.H, eng.W))
     idx_e = max(idx, 1)
 
     def step_host(i):
@@ -189,7 +192,6 @@ def run_ours(args):
         out = eng.fused_step(diff, "ddim", i, eng.img(eng.unet.x_in), y, cond, 0.0)
         host_out.copy_(out["sample"], non_blocking=True)
         th.cuda.current_stream().synchronize()
-        host_x.copy_(host_out)
 
     for _ in range(min(3, args.warmup)):
         step_host(idx_e)
@@ -228,7 +230,7 @@ def run_ours(args):
     line = {
         "metric": "diffusion-steps/sec", "value": value, "unit": "image-steps/s (1 step of one 256x256 image, 16 cutouts)",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate / norm / softmax / sampler)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate / norm / softmax / sampler)", "data": "synthetic (x_t ~ N(0,1) redrawn every step, seeded random weights)",
         "config": {"workload": "BASELINE configs[1]: image_size=256, respace=ddim250, batch=1 per GPU, cutn=16, ViT-B/32, class-cond UNet, "
                                "seeded random weights", "global_batch": eng.global_batch, "parallelism": f"dp{world} (batch shard, no data-path collective)",
                    "l2": "per-step working set (2.3 GB of packed weights + activations) exceeds the 126 MB L2; no explicit flush",
@@ -242,6 +244,10 @@ def run_ours(args):
                      "avg_launch_s": t_dom},
         "step_tensor_frac": FLOP_PER_IMAGE_STEP * value / world / (pk["sustained"] * 1e12),
     }
+    if world == 1 and args.torch_baseline:
+        del eng
+        th.cuda.empty_cache()
+        line["torch_cuda_baseline"] = torch_cuda_baseline(device, max(5, args.steps // 2))
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(sample_steps=1)
     print(json.dumps(line))
@@ -250,13 +256,40 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms (oracle port)
+_CPU_THREADS = None
+
+
+def pick_cpu_threads() -> int:
+    """Thread count that runs a representative fp32 conv fastest on this host (all cores is often slower on many-core boxes:
+    the build box' 8 cores take 30 s/step, a 128-core host with 128 threads took 206 s/step)."""
+    global _CPU_THREADS
+    if _CPU_THREADS is not None:
+        return _CPU_THREADS
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 48, 64, 96, ncpu) if c <= ncpu})
+    x = th.randn(1, 256, 128, 128)
+    w = th.randn(256, 256, 3, 3)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        th.set_num_threads(c)
+        th.nn.functional.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            th.nn.functional.conv2d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    _CPU_THREADS = best
+    return best
+
+
 def oracle_cpu_setup():
     """The oracle (fp32 PyTorch restatement of the reference path) on the host cores -- the checker timed as the CPU baseline."""
     from oracle import diffusion as od
     from oracle import guidance as og
     from oracle.clip_vit import VIT_CONFIGS, CLIPVisualOnly
     from oracle.unet import UNetModel, config_for, seeded_init_
-    th.set_num_threads(os.cpu_count())
+    th.set_num_threads(pick_cpu_threads())
     unet = seeded_init_(UNetModel(config_for(CFG["image_size"], True))).eval()
     clip = seeded_init_(CLIPVisualOnly(VIT_CONFIGS[CFG["clip"]]), seed=1235).eval()
     for p in list(unet.parameters()) + list(clip.parameters()):
@@ -285,11 +318,49 @@ def oracle_cpu_steps(unet, diff, cond, n_steps, x=None):
     return times, x
 
 
+def torch_cuda_baseline(device, n_steps):
+    """The reference's PyTorch-CUDA configuration (SURVEY.md BASELINE section 5): the same op sequence on cuDNN / cuBLAS / ATen with
+    eager autograd -- fp16 UNet trunk (convert_to_fp16: conv weights of input/middle/output blocks), fp16 CLIP, fp32 norms -- here
+    via the oracle port because the reference's third-party packages cannot be installed offline.  Context only."""
+    from oracle import guidance as og
+    unet, diff, cond = oracle_cpu_setup()
+    unet = unet.to(device)
+    for blocks in (unet.input_blocks, unet.middle_block, unet.output_blocks):
+        for m in blocks.modules():
+            if isinstance(m, (th.nn.Conv1d, th.nn.Conv2d)):
+                m.half()
+    unet.dtype = th.float16
+    clip = cond.clip_model.to(device).half()
+    cond = og.OracleCondFn(diff, clip, cond.target_embeds.to(device), cond.weights.to(device), cut_size=224, num_cutouts=CFG["cutn"])
+    B = CFG["per_gpu_batch"]
+    i = diff.num_timesteps - 1
+
+    def one(i):
+        x = th.randn(B, 3, CFG["image_size"], CFG["image_size"], device=device)
+        t = th.full((B,), i, dtype=th.long, device=device)
+        y = th.randint(0, 1000, (B,), device=device)
+        return diff.ddim_sample_with_grad(unet, x, t, clip_denoised=False, cond_fn=cond, model_kwargs={"y": y})["sample"]
+
+    for _ in range(3):
+        one(i)
+    th.cuda.synchronize()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(n_steps):
+        out = one(i - k)
+    e1.record()
+    th.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n_steps
+    return {"value": 1e3 / ms, "unit": "image-steps/s", "ms_per_step": ms, "steps": n_steps,
+            "what": "oracle port on cuda: eager PyTorch autograd, fp16 UNet trunk + fp16 CLIP (cuDNN/cuBLAS/ATen), no .item() logging",
+            "torch": th.__version__, "finite": bool(th.isfinite(out).all())}
+
+
 def cpu_baseline(sample_steps=1):
     unet, diff, cond = oracle_cpu_setup()
     times, _ = oracle_cpu_steps(unet, diff, cond, sample_steps)
     t = float(np.median(times))
-    return {"value": 1.0 / t, "unit": "image-steps/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": 1.0 / t, "unit": "image-steps/s", "cores": pick_cpu_threads(), "host_cpus": os.cpu_count(), "kind": "port",
             "sample": f"{sample_steps} full cfg2 step(s) of the fp32 oracle port (PyTorch CPU, all host threads), {t:.2f} s/step"}
 
 
@@ -310,7 +381,7 @@ def run_reference(args):
             "config": {"workload": "BASELINE configs[1]: image_size=256, respace=ddim250, batch=1, cutn=16, ViT-B/32 -- the reference's own "
                                    "algorithm (fp32 oracle port; guided_diffusion / clip packages are not installable offline) on the host CPU",
                        "global_batch": 1},
-            "cpu_baseline": {"value": value, "unit": "image-steps/s", "cores": os.cpu_count(), "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "image-steps/s", "cores": pick_cpu_threads(), "host_cpus": os.cpu_count(), "kind": "port",
                              "sample": f"{n_timed} full cfg2 steps (bounded to ~{budget_s:.0f} s of CPU work; {args.steps} requested)"},
             "e2e": {"value": value, "unit": "image-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -324,6 +395,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-baseline", action="store_true", help="also time the PyTorch-CUDA (cuDNN/cuBLAS eager autograd) oracle port")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

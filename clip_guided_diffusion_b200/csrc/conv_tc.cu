@@ -250,8 +250,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
         uint32_t v[16];
+        __syncwarp();
         tc_ld_32x16(taddr_row + c, v);
         tc_ld_wait();
+        if (row_ok)  // rows outside the image (partial tiles at the 8x8 / 16x16 levels) are never read back
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
           *reinterpret_cast<float4*>(ws + c + j) =
@@ -309,24 +311,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// split-K second pass: sum partials, add bias / residual, store.
+// split-K second pass: sum partials, add bias / residual, store.  One thread per 4 consecutive columns (float4 partial
+// loads, splits unrolled by 4 for memory-level parallelism).
 __global__ void conv_splitk_reduce_kernel(const ConvTcParams p, int m_tiles) {
-  const int64_t total = (int64_t)m_tiles * BM * (p.Cout);
+  const int cq = (p.Cout + 3) / 4;
+  const int64_t total = (int64_t)m_tiles * BM * cq;
+  const size_t split_stride = (size_t)m_tiles * BM * p.Npad;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int col = (int)(idx % p.Cout);
-    const int64_t trow = idx / p.Cout;
+    const int col = (int)(idx % cq) * 4;
+    const int64_t trow = idx / cq;
     const int r = (int)(trow % BM);
     const int mt = (int)(trow / BM);
     const int tw_i = mt % p.tiles_w, th_i = (mt / p.tiles_w) % p.tiles_h, tn_i = mt / (p.tiles_w * p.tiles_h);
     const int w = tw_i * p.TW + r % p.TW, h = th_i * p.TH + (r / p.TW) % p.TH, n = tn_i * p.TN + r / (p.TW * p.TH);
     if (n >= p.NB || h >= p.H || w >= p.W) continue;
-    float a = 0.f;
-    for (int s = 0; s < p.splits; ++s) a += p.ws[((size_t)s * ((size_t)m_tiles * BM) + trow) * p.Npad + col];
-    if (p.bias) a += p.bias[col];
-    if (p.res) a += __half2float(p.res[(int64_t)n * p.res_sn + (int64_t)h * p.res_sh + (int64_t)w * p.res_sw + col]);
-    const int64_t o = (int64_t)n * p.out_sn + (int64_t)h * p.out_sh + (int64_t)w * p.out_sw + col * p.out_sc;
-    if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = a;
-    else reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(a);
+    const float* src = p.ws + (size_t)trow * p.Npad + col;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 4 <= p.splits; s += 4) {
+      const float4 v0 = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(s + 0) * split_stride));
+      const float4 v1 = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(s + 1) * split_stride));
+      const float4 v2 = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(s + 2) * split_stride));
+      const float4 v3 = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(s + 3) * split_stride));
+      a.x += (v0.x + v1.x) + (v2.x + v3.x); a.y += (v0.y + v1.y) + (v2.y + v3.y);
+      a.z += (v0.z + v1.z) + (v2.z + v3.z); a.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; s < p.splits; ++s) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)s * split_stride));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float acc[4] = {a.x, a.y, a.z, a.w};
+    const int64_t o = (int64_t)n * p.out_sn + (int64_t)h * p.out_sh + (int64_t)w * p.out_sw;
+    const int64_t ro = (int64_t)n * p.res_sn + (int64_t)h * p.res_sh + (int64_t)w * p.res_sw;
+    if (col + 4 <= p.Cout && !p.out_f32 && p.out_sc == 1) {
+      if (p.bias) {
+        const float4 bv = *reinterpret_cast<const float4*>(p.bias + col);
+        acc[0] += bv.x; acc[1] += bv.y; acc[2] += bv.z; acc[3] += bv.w;
+      }
+      if (p.res) {
+        const __half2* rp = reinterpret_cast<const __half2*>(p.res + ro + col);
+        const float2 r0 = __half22float2(rp[0]), r1 = __half22float2(rp[1]);
+        acc[0] += r0.x; acc[1] += r0.y; acc[2] += r1.x; acc[3] += r1.y;
+      }
+      __half2* op = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.out) + o + col);
+      op[0] = __floats2half2_rn(acc[0], acc[1]);
+      op[1] = __floats2half2_rn(acc[2], acc[3]);
+    } else {
+      for (int j = 0; j < 4 && col + j < p.Cout; ++j) {
+        float v = acc[j];
+        if (p.bias) v += p.bias[col + j];
+        if (p.res) v += __half2float(p.res[ro + col + j]);
+        if (p.out_f32) reinterpret_cast<float*>(p.out)[o + (col + j) * p.out_sc] = v;
+        else reinterpret_cast<__half*>(p.out)[o + (col + j) * p.out_sc] = __float2half_rn(v);
+      }
+    }
   }
 }
 
@@ -504,7 +542,7 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
   }
   if (rc) return rc;
   if (L.p.splits > 1) {
-    const int64_t total = (int64_t)L.m_tiles * BM * L.p.Cout;
+    const int64_t total = (int64_t)L.m_tiles * BM * ((L.p.Cout + 3) / 4);
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 8);
     conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(L.p, L.m_tiles);
     CGD_LAUNCH_CHECK();

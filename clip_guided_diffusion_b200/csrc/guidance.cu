@@ -267,7 +267,8 @@ __global__ void guide_grad_kernel(const float* __restrict__ xin, const float* __
     l_r += er * er;
     const float d_x0 = fac * d_xin + rs * inv_n * 2.f * er;
     // pred_xstart = a*x - bb*eps  =>  d/d eps = -bb * d_x0 (UNet dgrad seed), direct d/dx = a * d_x0
-    seed[((int64_t)b * HW + p) * ld + c] = __float2half_rn(-bb * d_x0 * seed_scale);
+    // saturate instead of overflowing to inf: a diverged chain (e.g. random weights) must not poison the fp16 backward with NaNs
+    seed[((int64_t)b * HW + p) * ld + c] = __float2half_rn(fminf(fmaxf(-bb * d_x0 * seed_scale, -60000.f), 60000.f));
     dxd[((int64_t)b * 3 + c) * HW + p] = omf * d_xin + a * d_x0;
   }
   l_tv = block_sum(l_tv, red);

@@ -24,11 +24,40 @@ static GnGeom gn_geom(int C) {
   return g;
 }
 
+// Fixed-order (deterministic) fold of [nchunk][32][2] partials by the whole block: thread t sums chunks t/32, t/32 + nthr/32, ...
+// for group t%32 in fp64, then the per-part sums are combined in ascending part order.
+__device__ __forceinline__ void fold_partials(const float* part, int nchunk, double* out_s, double* out_q) {
+  __shared__ double ps[8][32], pq[8][32];
+  const int g = threadIdx.x & 31, part_id = threadIdx.x >> 5;
+  const int nparts = min((int)(blockDim.x >> 5), 8);
+  if (part_id < nparts) {
+    double ds = 0.0, dq = 0.0;
+    for (int c = part_id; c < nchunk; c += nparts) {
+      ds += (double)__ldcg(part + ((int64_t)c * 32 + g) * 2);
+      dq += (double)__ldcg(part + ((int64_t)c * 32 + g) * 2 + 1);
+    }
+    ps[part_id][g] = ds;
+    pq[part_id][g] = dq;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double ds = 0.0, dq = 0.0;
+    for (int k = 0; k < nparts; ++k) {
+      ds += ps[k][g];
+      dq += pq[k][g];
+    }
+    out_s[g] = ds;
+    out_q[g] = dq;
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------
 // pass 1: per-(image, chunk, group) sum and sum of squares; last block per image folds the chunks.
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partials, float* __restrict__ stats,
                                 unsigned int* __restrict__ counters, int HW, int C, int64_t ld, int nchunk, float eps) {
   __shared__ float gs[32], gq[32];
+  __shared__ double fold_s[32], fold_q[32];
   __shared__ int is_last;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int V = C / 8, col = threadIdx.x % V, pl = threadIdx.x / V, PP = blockDim.x / V;
@@ -40,13 +69,22 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const __half* xb = x + (int64_t)n * HW * ld + col * 8;
-  for (int p = p0 + pl; p < p1; p += PP) {
-    float v[8];
-    unpack8(ld8(xb + (int64_t)p * ld), v);
+  for (int p = p0 + pl; p < p1; p += 4 * PP) {  // 4 independent 128-bit loads in flight per thread
+    half8 raw[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j] += v[j];
-      q[j] = fmaf(v[j], v[j], q[j]);
+    for (int u = 0; u < 4; ++u)
+      if (p + u * PP < p1) raw[u] = ld8(xb + (int64_t)(p + u * PP) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p + u * PP < p1) {
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += v[j];
+          q[j] = fmaf(v[j], v[j], q[j]);
+        }
+      }
     }
   }
   __syncthreads();
@@ -80,13 +118,9 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
   __syncthreads();
   if (is_last) {
     __threadfence();
+    fold_partials(partials + (int64_t)n * nchunk * 64, nchunk, fold_s, fold_q);
     if (threadIdx.x < 32) {
-      double ds = 0.0, dq = 0.0;
-      for (int c = 0; c < nchunk; ++c) {
-        const float* o = partials + (((int64_t)n * nchunk + c) * 32 + threadIdx.x) * 2;
-        ds += (double)__ldcg(o);
-        dq += (double)__ldcg(o + 1);
-      }
+      const double ds = fold_s[threadIdx.x], dq = fold_q[threadIdx.x];
       const double m = (double)cpg * (double)HW;
       const double mean = ds / m;
       double var = dq / m - mean * mean;
@@ -129,15 +163,25 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
   gn_coeffs(stats, gamma, beta, emb, n, C, col, A, Bc, G, mu, rs);
   const __half* xb = x + (int64_t)n * HW * ldx + col * 8;
   __half* yb = y + (int64_t)n * HW * ldy + col * 8;
-  for (int p = blockIdx.x * PP + pl; p < HW; p += gridDim.x * PP) {
-    float v[8];
-    unpack8(ld8(xb + (int64_t)p * ldx), v);
+  const int stride = gridDim.x * PP;
+  for (int p = blockIdx.x * PP + pl; p < HW; p += 4 * stride) {
+    half8 raw[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = fmaf(v[j], A[j], Bc[j]);
-      v[j] = silu ? silu_f(t) : t;
+    for (int u = 0; u < 4; ++u)
+      if (p + u * stride < HW) raw[u] = ld8(xb + (int64_t)(p + u * stride) * ldx);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p + u * stride < HW) {
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(v[j], A[j], Bc[j]);
+          v[j] = silu ? silu_f(t) : t;
+        }
+        st8(yb + (int64_t)(p + u * stride) * ldy, pack8(v));
+      }
     }
-    st8(yb + (int64_t)p * ldy, pack8(v));
   }
 }
 
@@ -147,6 +191,7 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
                                     float* __restrict__ partials, float* __restrict__ sums, unsigned int* __restrict__ counters,
                                     int HW, int C, int64_t ld_dy, int64_t ldx, int nchunk, int silu) {
   __shared__ float gs[32], gq[32];
+  __shared__ double fold_s[32], fold_q[32];
   __shared__ int is_last;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int V = C / 8, col = threadIdx.x % V, pl = threadIdx.x / V, PP = blockDim.x / V;
@@ -161,18 +206,30 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const __half* xb = x + (int64_t)n * HW * ldx + col * 8;
   const __half* db = dy + (int64_t)n * HW * ld_dy + col * 8;
-  for (int p = p0 + pl; p < p1; p += PP) {
-    float v[8], d[8];
-    unpack8(ld8(xb + (int64_t)p * ldx), v);
-    unpack8(ld8(db + (int64_t)p * ld_dy), d);
+  for (int p = p0 + pl; p < p1; p += 2 * PP) {  // 4 independent 128-bit loads in flight per thread
+    half8 rx[2], rd[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float dv = d[j];
-      if (silu) dv *= silu_grad_f(fmaf(v[j], A[j], Bc[j]));
-      const float dxh = dv * G[j];
-      const float xh = (v[j] - mu[j]) * rs[j];
-      s[j] += dxh;
-      q[j] = fmaf(dxh, xh, q[j]);
+    for (int u = 0; u < 2; ++u)
+      if (p + u * PP < p1) {
+        rx[u] = ld8(xb + (int64_t)(p + u * PP) * ldx);
+        rd[u] = ld8(db + (int64_t)(p + u * PP) * ld_dy);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * PP < p1) {
+        float v[8], d[8];
+        unpack8(rx[u], v);
+        unpack8(rd[u], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dv = d[j];
+          if (silu) dv *= silu_grad_f(fmaf(v[j], A[j], Bc[j]));
+          const float dxh = dv * G[j];
+          const float xh = (v[j] - mu[j]) * rs[j];
+          s[j] += dxh;
+          q[j] = fmaf(dxh, xh, q[j]);
+        }
+      }
     }
   }
   __syncthreads();
@@ -206,13 +263,9 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
   __syncthreads();
   if (is_last) {
     __threadfence();
+    fold_partials(partials + (int64_t)n * nchunk * 64, nchunk, fold_s, fold_q);
     if (threadIdx.x < 32) {
-      double ds = 0.0, dq = 0.0;
-      for (int c = 0; c < nchunk; ++c) {
-        const float* o = partials + (((int64_t)n * nchunk + c) * 32 + threadIdx.x) * 2;
-        ds += (double)__ldcg(o);
-        dq += (double)__ldcg(o + 1);
-      }
+      const double ds = fold_s[threadIdx.x], dq = fold_q[threadIdx.x];
       const double m = (double)cpg * (double)HW;
       sums[((int64_t)n * 32 + threadIdx.x) * 2 + 0] = (float)(ds / m);  // mean(dxhat)
       sums[((int64_t)n * 32 + threadIdx.x) * 2 + 1] = (float)(dq / m);  // mean(dxhat * xhat)
@@ -239,21 +292,35 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ dy, const __half*
   const __half* xb = x + (int64_t)n * HW * ldx + col * 8;
   const __half* db = dy + (int64_t)n * HW * ld_dy + col * 8;
   __half* ob = dx + (int64_t)n * HW * ld_dx + col * 8;
-  for (int p = blockIdx.x * PP + pl; p < HW; p += gridDim.x * PP) {
-    float v[8], d[8], o[8];
-    unpack8(ld8(xb + (int64_t)p * ldx), v);
-    unpack8(ld8(db + (int64_t)p * ld_dy), d);
-    if (accumulate) unpack8(ld8(ob + (int64_t)p * ld_dx), o);
+  const int stride = gridDim.x * PP;
+  for (int p = blockIdx.x * PP + pl; p < HW; p += 2 * stride) {
+    half8 rx[2], rd[2], ro[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float dv = d[j];
-      if (silu) dv *= silu_grad_f(fmaf(v[j], A[j], Bc[j]));
-      const float dxh = dv * G[j];
-      const float xh = (v[j] - mu[j]) * rs[j];
-      const float r = rs[j] * (dxh - m1[j] - xh * m2[j]);
-      o[j] = accumulate ? o[j] + r : r;
+    for (int u = 0; u < 2; ++u)
+      if (p + u * stride < HW) {
+        rx[u] = ld8(xb + (int64_t)(p + u * stride) * ldx);
+        rd[u] = ld8(db + (int64_t)(p + u * stride) * ld_dy);
+        if (accumulate) ro[u] = ld8(ob + (int64_t)(p + u * stride) * ld_dx);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * stride < HW) {
+        float v[8], d[8], o[8];
+        unpack8(rx[u], v);
+        unpack8(rd[u], d);
+        if (accumulate) unpack8(ro[u], o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dv = d[j];
+          if (silu) dv *= silu_grad_f(fmaf(v[j], A[j], Bc[j]));
+          const float dxh = dv * G[j];
+          const float xh = (v[j] - mu[j]) * rs[j];
+          const float r = rs[j] * (dxh - m1[j] - xh * m2[j]);
+          o[j] = accumulate ? o[j] + r : r;
+        }
+        st8(ob + (int64_t)(p + u * stride) * ld_dx, pack8(o));
+      }
     }
-    st8(ob + (int64_t)p * ld_dx, pack8(o));
   }
 }
 
@@ -264,7 +331,7 @@ static int gn_check(const CgdOp& op, int64_t C, int64_t HW, int64_t N) {
 }
 static int gn_apply_chunks(int64_t HW, int64_t N, int PP) {
   int64_t c = ceil_div(HW, (int64_t)PP * 4);
-  const int64_t cap = ceil_div(148 * 4, N);
+  const int64_t cap = ceil_div(148 * 8, N);
   if (c > cap) c = cap;
   if (c < 1) c = 1;
   return (int)c;

@@ -103,10 +103,12 @@ def conv_tile_count(NB, H, W):
 
 
 def pick_splits(m_tiles, n_tiles, kblocks, npad, ws_cap_bytes=16 << 20) -> int:
+    """split-K factor for layers whose output tiles cannot fill the 148 SMs: aim at one full wave of CTAs, keep at least
+    6 K-blocks (of 64) per CTA so the TMA/MMA pipeline amortises its fill, bound the fp32 partial workspace."""
     tiles = m_tiles * n_tiles
-    if tiles >= 120 or kblocks < 8:
+    if tiles >= 100 or kblocks < 12:
         return 1
-    s = min(kblocks // 4, -(-296 // tiles), 32)
+    s = min(kblocks // 6, 148 // tiles, 32)
     cap = ws_cap_bytes // (m_tiles * 128 * npad * 4)
     s = max(1, min(s, cap))
     per = -(-kblocks // s)
@@ -242,7 +244,7 @@ class Plan:
     def group_norm(self, x: Act, gamma: Buf, beta: Buf, emb: Optional[tuple] = None, silu=True, eps=1e-5, name="gn") -> Act:
         N, HW, C = x.N, x.HW, x.C
         pp = max(1, 256 // (C // 8))
-        nchunk = int(min(max(1, -(-HW // (pp * 8))), max(1, 592 // N), 256))
+        nchunk = int(min(max(1, -(-HW // (pp * 8))), max(1, 1184 // N), 1024))
         partials = self.new(N * nchunk * 64, "f", name + "_part")
         stats = self.new(N * 64, "f", name + "_stats")
         counters = self.new(N, "u32", name + "_cnt")
