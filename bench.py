@@ -247,7 +247,10 @@ def run_ours(args):
     if world == 1 and args.torch_baseline:
         del eng
         th.cuda.empty_cache()
-        line["torch_cuda_baseline"] = torch_cuda_baseline(device, max(5, args.steps // 2))
+        try:
+            line["torch_cuda_baseline"] = torch_cuda_baseline(device, max(5, args.steps // 2))
+        except Exception as e:  # context only: never lose the measured line
+            line["torch_cuda_baseline"] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(sample_steps=1)
     print(json.dumps(line))
@@ -331,6 +334,9 @@ def torch_cuda_baseline(device, n_steps):
                 m.half()
     unet.dtype = th.float16
     clip = cond.clip_model.to(device).half()
+    for m in clip.modules():  # clip.model.convert_weights leaves LayerNorm in fp32
+        if isinstance(m, th.nn.LayerNorm):
+            m.float()
     cond = og.OracleCondFn(diff, clip, cond.target_embeds.to(device), cond.weights.to(device), cut_size=224, num_cutouts=CFG["cutn"])
     B = CFG["per_gpu_batch"]
     i = diff.num_timesteps - 1

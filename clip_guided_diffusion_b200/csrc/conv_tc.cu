@@ -22,110 +22,9 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "tc_ptx.cuh"
 
 namespace cgd {
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("cgd conv_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane = accumulator row)
-__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 64 fp16 (128 B), 8-row swizzle atoms of 1024 B.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)0 << 16;                   // leading byte offset: unused for swizzled K-major (one atom along K)
-  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset between 8-row atoms, bits [32,46)
-  d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                   // layout type SWIZZLE_128B
-  return d;
-}
-// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M=128, N=BN
-__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
-  return (1u << 4)                    // D format fp32
-         | (0u << 7) | (0u << 10)     // A, B format fp16
-         | (0u << 15) | (0u << 16)    // A, B K-major
-         | ((uint32_t)(n >> 3) << 17) // N / 8
-         | ((uint32_t)(128 >> 4) << 24);  // M / 16
-}
 
 // ---------------------------------------------------------------- kernel
 constexpr int BM = 128, BK = 64;
@@ -246,7 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16);
     if (p.splits > 1) {
       // raw fp32 partials -> workspace [split][tile row][Npad]
-      float* ws = p.ws + ((size_t)blockIdx.z * ((size_t)gridDim.x * BM) + (size_t)mt * BM + r) * p.Npad + ncol0;
+      float* ws = p.ws + ((size_t)blockIdx.z * p.ws_rows + (size_t)mt * BM + r) * p.Npad + ncol0;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
         uint32_t v[16];
@@ -316,7 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void conv_splitk_reduce_kernel(const ConvTcParams p, int m_tiles) {
   const int cq = (p.Cout + 3) / 4;
   const int64_t total = (int64_t)m_tiles * BM * cq;
-  const size_t split_stride = (size_t)m_tiles * BM * p.Npad;
+  const size_t split_stride = (size_t)p.ws_rows * p.Npad;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int col = (int)(idx % cq) * 4;
     const int64_t trow = idx / cq;
@@ -477,8 +376,9 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   L.Wp = reinterpret_cast<const __half*>(op.p[1]);
   L.a_sn = op.i[7]; L.a_sh = op.i[8]; L.a_sw = op.i[9];
   L.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.ws_rows = ((L.m_tiles + 1) / 2) * 2 * BM;
   L.n_tiles = (int)(Npad / BN);
-  if (L.impl != 0) return 0;
+  if (L.impl == 1) return 0;
 
   PFN_encodeTiled enc = get_encode_fn();
   CGD_CHECK_ARG(enc != nullptr, "conv: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -502,6 +402,10 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
     CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, op.p[1], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+    cuuint32_t box2[2] = {64, (cuuint32_t)(BN / 2)};
+    r = enc(&L.tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, op.p[1], dims, strides, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W half) failed with %d", (int)r);
   }
   return 0;
 }
@@ -520,8 +424,12 @@ static int launch_tc(const ConvTcLaunch& L, cudaStream_t st) {
   return 0;
 }
 
+// impl: 0 = auto (CTA-pair persistent kernel when the layer has at least two 128-pixel tiles, else the single-CTA kernel),
+// 1 = SIMT verification twin, 2 = force single-CTA kernel, 3 = force CTA-pair kernel
+bool conv_use_pair_kernel(const ConvTcLaunch& L) { return L.impl == 3 || (L.impl == 0 && L.m_tiles >= 2); }
+
 int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
-  if (L.impl != 0) {
+  if (L.impl == 1) {
     const int64_t total = (int64_t)L.p.NB * L.p.H * L.p.W * L.p.Cout;
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
     ConvTcParams p = L.p;
@@ -531,6 +439,8 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
     return 0;
   }
   int rc = 0;
+  if (conv_use_pair_kernel(L)) rc = conv_tc2_launch(L, st);
+  else
   switch (L.BN) {
     case 16: rc = launch_tc<16>(L, st); break;
     case 32: rc = launch_tc<32>(L, st); break;
@@ -550,6 +460,6 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
   return 0;
 }
 
-int conv_tc_num_launches(const ConvTcLaunch& L) { return (L.impl == 0 && L.p.splits > 1) ? 2 : 1; }
+int conv_tc_num_launches(const ConvTcLaunch& L) { return (L.impl != 1 && L.p.splits > 1) ? 2 : 1; }
 
 }  // namespace cgd

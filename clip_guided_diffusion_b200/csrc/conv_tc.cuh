@@ -14,6 +14,7 @@ struct ConvTcParams {
   int tiles_w, tiles_h, tiles_n;
   int kblocks, splits, kb_per_split; // K loop = taps * Cin/64 blocks, optionally split over gridDim.z
   int out_f32;
+  int ws_rows;                       // rows per split in the split-K workspace (= even-rounded m_tiles * 128)
   int64_t out_sn, out_sh, out_sw;    // output / residual strides in elements (channel contiguous)
   int64_t res_sn, res_sh, res_sw;
   int64_t out_sc;                    // output channel stride (1 except for NCHW fp32 outputs; scalar-store paths only)
@@ -24,7 +25,8 @@ struct ConvTcParams {
 };
 
 struct ConvTcLaunch {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB;              // A: 4-D pixel box; B: [BN x 64] weight slice (single-CTA kernel)
+  CUtensorMap tmB2;                  // B: [BN/2 x 64] half slice per CTA of a pair (cta_group::2 kernel)
   ConvTcParams p;
   int BN, impl, m_tiles, n_tiles;
   const __half* A;
@@ -35,5 +37,7 @@ struct ConvTcLaunch {
 int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L);
 int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st);
 int conv_tc_num_launches(const ConvTcLaunch& L);
+int conv_tc2_launch(const ConvTcLaunch& L, cudaStream_t st);  // conv_tc2.cu
+bool conv_use_pair_kernel(const ConvTcLaunch& L);
 
 }  // namespace cgd

@@ -1,0 +1,278 @@
+// conv_tc2.cu -- persistent CTA-pair variant of the implicit-GEMM conv (see conv_tc.cu for the formulation).
+//
+// What changes against conv_tc_kernel (measured on B200, ncu, 256x256x256->256 3x3: tensor pipe 33 % active, 3.46 waves of
+// one-tile CTAs, un-overlapped epilogue, 48 KB of L2->smem traffic per K-block per CTA):
+//   * cta_group::2: two CTAs of a cluster (one TPC) form a 256-pixel x BN tile.  Each CTA stages its own 128 pixel rows of
+//     A and only HALF of the weight tile (BN/2 rows); tcgen05.mma.cta_group::2 (M=256) reads B from both CTAs' shared
+//     memory, so the weight traffic per CTA halves (48 KB -> 32 KB per K-block at BN=256) and the ring gets 6 stages.
+//   * persistent: grid = one cluster per SM pair, static round-robin over (split, pixel-pair tile, channel tile).
+//   * two TMEM accumulator stages (2 x BN columns): the epilogue warps drain tile i while the MMA warp already works on
+//     tile i+1 (tmem_full / tmem_empty mbarriers; tmem_empty is arrived remotely by the peer CTA's epilogue threads).
+// Protocol (DeepGEMM / CUTLASS sm100 2-SM skeleton): both CTAs run a TMA producer whose loads complete_tx on the LEADER's
+// full barrier (peer-bit-masked address); the leader's single MMA thread issues the MMAs and multicasts tcgen05.commit to
+// the empty barriers / tmem_full barriers of both CTAs.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace cgd {
+
+constexpr int BM2 = 128, BK2 = 64;
+constexpr int kThreads2 = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int kEpiThreads2 = 128;
+
+template <int BN>
+struct Tc2Cfg {
+  static constexpr int kABytes = BM2 * BK2 * 2;          // 16 KB: this CTA's 128 pixel rows
+  static constexpr int kBBytes = (BN / 2) * BK2 * 2;     // this CTA's half of the weight tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+struct Tile2 {
+  int mt, n_tile, kb0, kb1, split;
+};
+// tile index -> (split, pixel-pair tile, channel tile); channel tile fastest so neighbouring clusters share A in L2
+__device__ __forceinline__ Tile2 decode_tile(const ConvTcParams& p, int t, int n_tiles, int pair_tiles, uint32_t rank) {
+  Tile2 r;
+  r.n_tile = t % n_tiles;
+  const int rest = t / n_tiles;
+  const int pair = rest % pair_tiles;
+  r.split = rest / pair_tiles;
+  r.mt = 2 * pair + (int)rank;
+  r.kb0 = r.split * p.kb_per_split;
+  r.kb1 = min(r.kb0 + p.kb_per_split, p.kblocks);
+  return r;
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, int n_tiles,
+                int pair_tiles, int total_tiles) {
+  using Cfg = Tc2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::kAccStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's copy is the one used: one arrive per CTA (+ the TMA transaction bytes)
+      mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
+    }
+    for (int a = 0; a < Cfg::kAccStages; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);                  // multicast tcgen05.commit
+      mbar_init(&tmem_empty_bar[a], 2 * kEpiThreads2);  // leader's copy: every epilogue thread of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one thread per CTA)
+    if (lane == 0) {
+      const int cblks = p.Cin / BK2;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+        const Tile2 tl = decode_tile(p, t, n_tiles, pair_tiles, rank);
+        const int tw_i = tl.mt % p.tiles_w, th_i = (tl.mt / p.tiles_w) % p.tiles_h, tn_i = tl.mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
+        const int bcol = tl.n_tile * BN + (int)rank * (BN / 2);
+        for (int kb = tl.kb0; kb < tl.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int tap = kb / cblks, cb = kb - tap * cblks;
+          int dy = 0, dx = 0;
+          if (p.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          tma2_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], cb * BK2, w0 + dx, h0 + dy, n0);
+          tma2_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK2, bcol);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          else mbar_arrive_remote(&full_bar[stage], 0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16_mn(256, BN);
+      int stage = 0, iter = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
+        const Tile2 tl = decode_tile(p, t, n_tiles, pair_tiles, rank);
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogues of both CTAs have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = tl.kb0; kb < tl.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK2 / 16; ++k)
+            tc2_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > tl.kb0 || k > 0) ? 1u : 0u);
+          tc2_commit_mc(&empty_bar[stage], 0x3);  // frees the stage in both CTAs
+          if (kb == tl.kb1 - 1) tc2_commit_mc(&tmem_full_bar[acc], 0x3);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      // all remote arrivals on this CTA's barriers must have landed before it may exit
+      if (iter > 0) {
+        const int last = iter - 1;
+        mbar_wait(&tmem_empty_bar[last & 1], (last >> 1) & 1);
+        if (iter > 1) mbar_wait(&tmem_empty_bar[(last - 1) & 1], ((last - 1) >> 1) & 1);
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): TMEM lane quadrant = warp % 4
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    int iter = 0;
+    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
+      const Tile2 tl = decode_tile(p, t, n_tiles, pair_tiles, rank);
+      const int tw_i = tl.mt % p.tiles_w, th_i = (tl.mt / p.tiles_w) % p.tiles_h, tn_i = tl.mt / (p.tiles_w * p.tiles_h);
+      const int w = tw_i * p.TW + r % p.TW, h = th_i * p.TH + (r / p.TW) % p.TH, n = tn_i * p.TN + r / (p.TW * p.TH);
+      const bool row_ok = (n < p.NB) && (h < p.H) && (w < p.W);
+      const int ncol0 = tl.n_tile * BN;
+      const int acc = iter & 1;
+      mbar_wait(&tmem_full_bar[acc], (iter >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      if (p.splits > 1) {
+        float* ws = p.ws + ((size_t)tl.split * p.ws_rows + (size_t)tl.mt * BM2 + r) * p.Npad + ncol0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t v[16];
+          __syncwarp();
+          tc_ld_32x16(taddr_row + c, v);
+          tc_ld_wait();
+          if (row_ok)
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(ws + c + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      } else {
+        const int64_t o_off = (int64_t)n * p.out_sn + (int64_t)h * p.out_sh + (int64_t)w * p.out_sw;
+        const int64_t r_off = (int64_t)n * p.res_sn + (int64_t)h * p.res_sh + (int64_t)w * p.res_sw;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t v[16];
+          __syncwarp();
+          tc_ld_32x16(taddr_row + c, v);
+          tc_ld_wait();
+          const int col = ncol0 + c;
+          if (row_ok && col < p.Cout) {
+            float a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = __uint_as_float(v[j]);
+            if (col + 16 <= p.Cout && !p.out_f32 && p.out_sc == 1) {
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
+                  a[j] += b.x; a[j + 1] += b.y; a[j + 2] += b.z; a[j + 3] += b.w;
+                }
+              }
+              if (p.res) {
+                float rr[16];
+                unpack8(ld8(p.res + r_off + col), rr);
+                unpack8(ld8(p.res + r_off + col + 8), rr + 8);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) a[j] += rr[j];
+              }
+              __half* o = reinterpret_cast<__half*>(p.out) + o_off + col;
+              st8(o, pack8(a));
+              st8(o + 8, pack8(a + 8));
+            } else {
+              for (int j = 0; j < 16 && col + j < p.Cout; ++j) {
+                float x = a[j];
+                if (p.bias) x += p.bias[col + j];
+                if (p.res) x += __half2float(p.res[r_off + col + j]);
+                if (p.out_f32) reinterpret_cast<float*>(p.out)[o_off + (col + j) * p.out_sc] = x;
+                else reinterpret_cast<__half*>(p.out)[o_off + (col + j) * p.out_sc] = __float2half_rn(x);
+              }
+            }
+          }
+        }
+      }
+      // this thread's TMEM reads of the accumulator are complete: release it to the leader's MMA thread
+      tc_fence_before();
+      mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+  }
+}
+
+template <int BN>
+static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
+  using Cfg = Tc2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CGD_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int pair_tiles = (L.m_tiles + 1) / 2;
+  const int total = pair_tiles * L.n_tiles * L.p.splits;
+  const int clusters = std::min(total, 74);  // 148 SMs = 74 TPC pairs
+  conv_tc2_kernel<BN><<<2 * clusters, kThreads2, Cfg::kSmemBytes, st>>>(L.tmA, L.tmB2, L.p, L.n_tiles, pair_tiles, total);
+  CGD_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_tc2_launch(const ConvTcLaunch& L, cudaStream_t st) {
+  switch (L.BN) {
+    case 16: return launch_tc2<16>(L, st);
+    case 32: return launch_tc2<32>(L, st);
+    case 64: return launch_tc2<64>(L, st);
+    case 128: return launch_tc2<128>(L, st);
+    case 192: return launch_tc2<192>(L, st);
+    case 256: return launch_tc2<256>(L, st);
+    default: set_error("conv: unsupported BN %d", L.BN); return -1;
+  }
+}
+
+}  // namespace cgd

@@ -204,7 +204,7 @@ class Plan:
         bn = pick_bn(npad, m_tiles)
         kblocks = taps * Cin // 64
         splits = pick_splits(m_tiles, npad // bn, kblocks, npad)
-        ws = self.new(splits * m_tiles * 128 * npad, "f", "splitk_ws") if splits > 1 else None
+        ws = self.new(splits * ((m_tiles + 1) // 2 * 2) * 128 * npad, "f", "splitk_ws") if splits > 1 else None
         i = [NB, H, W, Cin, Cout, npad, taps, *x_strides, *out_strides, *(res_strides or (0, 0, 0)), bn, splits, self.conv_impl, out_sc]
         self.emit("CONV", flags=1 if out_f32 else 0, i=i,
                   p=[x_ptr, self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws)], tag=tag)

@@ -32,7 +32,7 @@ def _ref_conv(x, w, b, res, taps):
     return y + res.float() if res is not None else y
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["auto", "simt", "tc1", "tc2pair"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_fwd_and_dgrad(case, impl):
     name, NB, H, W, Cin, Cout, taps, has_b, has_r = case
@@ -74,7 +74,7 @@ def test_conv_fwd_and_dgrad(case, impl):
     assert th.isfinite(gg).all() and err < 3e-3, f"{name} dgrad impl={impl}: rel-to-max err {err:.3e}"
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["auto", "simt", "tc1", "tc2pair"])
 def test_conv_special_layouts(impl):
     """UNet head (fp32 NCHW out, 6 of 16 padded channels), stem dgrad (3 channels) and the ViT patch-embed geometry
     (49 tokens per image written at a row offset with a batch stride)."""
