@@ -32,9 +32,22 @@ __device__ __forceinline__ void fold_partials(const float* part, int nchunk, dou
   const int nparts = min((int)(blockDim.x >> 5), 8);
   if (part_id < nparts) {
     double ds = 0.0, dq = 0.0;
-    for (int c = part_id; c < nchunk; c += nparts) {
-      ds += (double)__ldcg(part + ((int64_t)c * 32 + g) * 2);
-      dq += (double)__ldcg(part + ((int64_t)c * 32 + g) * 2 + 1);
+    int c = part_id;
+    // 8 independent (sum, sumsq) pairs in flight per thread: the loop is latency-bound (L2), not bandwidth-bound
+    for (; c + 7 * nparts < nchunk; c += 8 * nparts) {
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float2*>(part + ((int64_t)(c + u * nparts) * 32 + g) * 2));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        ds += (double)v[u].x;
+        dq += (double)v[u].y;
+      }
+    }
+    for (; c < nchunk; c += nparts) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(part + ((int64_t)c * 32 + g) * 2));
+      ds += (double)v.x;
+      dq += (double)v.y;
     }
     ps[part_id][g] = ds;
     pq[part_id][g] = dq;
@@ -330,8 +343,8 @@ static int gn_check(const CgdOp& op, int64_t C, int64_t HW, int64_t N) {
   return 0;
 }
 static int gn_apply_chunks(int64_t HW, int64_t N, int PP) {
-  int64_t c = ceil_div(HW, (int64_t)PP * 4);
-  const int64_t cap = ceil_div(148 * 8, N);
+  int64_t c = ceil_div(HW, (int64_t)PP * 8);
+  const int64_t cap = ceil_div(148 * 3, N);
   if (c > cap) c = cap;
   if (c < 1) c = 1;
   return (int)c;
