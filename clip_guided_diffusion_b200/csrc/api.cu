@@ -40,6 +40,9 @@ static int dispatch(const CgdOp& op, const ConvTcLaunch* conv, cudaStream_t st) 
     case CGD_OP_COPY: return launch_copy(op, st);
     case CGD_OP_ATTN_FWD: return launch_attn_fwd(op, st);
     case CGD_OP_ATTN_BWD: return launch_attn_bwd(op, st);
+    case CGD_OP_TRANSPOSE: return launch_transpose(op, st);
+    case CGD_OP_SOFTMAX_FWD: return launch_softmax_fwd(op, st);
+    case CGD_OP_SOFTMAX_BWD: return launch_softmax_bwd(op, st);
     case CGD_OP_LINEAR_SMALL: return launch_linear_small(op, st);
     case CGD_OP_TIMESTEP_EMB: return launch_timestep_emb(op, st);
     case CGD_OP_LABEL_ADD: return launch_label_add(op, st);

@@ -350,4 +350,152 @@ int launch_attn_bwd(const CgdOp& op, cudaStream_t st) {
   return 0;
 }
 
+// ================================================================================================
+// Tensor-core attention for long sequences (T % 256 == 0: the 32x32 and 16x16 UNet levels).
+// S = Q K^T, O = P V and the four backward products run as batched GEMMs on the tcgen05 CTA-pair kernel (conv_tc2.cu,
+// CGD_OP_CONV with a batched B operand); the kernels below are the glue: batched fp16 transposes (so that every GEMM
+// operand is K-major), the fp32 row softmax (fp16 in/out like the reference's `softmax(w.float()).type(w.dtype)`), and
+// its backward dS = P * (dP - rowsum(P * dP)) * scale.
+// ================================================================================================
+
+struct TransposeArgs {
+  const __half* src[3];
+  __half* dst[3];
+  int64_t sb1[3], sb2[3], sr[3];
+  int npairs, nb1, nb2, R, C;
+  int64_t Rp;
+};
+// dst[b1][b2][c][r] = src[b1][b2][r][c]; 32x32 tiles through shared memory, coalesced both ways
+__global__ void transpose_kernel(const TransposeArgs a) {
+  __shared__ __half tile[32][34];
+  int z = blockIdx.z;
+  const int pair = z % a.npairs;
+  z /= a.npairs;
+  const int b2 = z % a.nb2, b1 = z / a.nb2;
+  const __half* src = a.src[pair] + (int64_t)b1 * a.sb1[pair] + (int64_t)b2 * a.sb2[pair];
+  __half* dst = a.dst[pair] + ((int64_t)b1 * a.nb2 + b2) * a.C * a.Rp;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < a.R && c < a.C) ? src[(int64_t)r * a.sr[pair] + c] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < a.C && r < a.R) dst[(int64_t)c * a.Rp + r] = tile[threadIdx.x][j];
+  }
+}
+int launch_transpose(const CgdOp& op, cudaStream_t st) {
+  TransposeArgs a{};
+  a.nb1 = (int)op.i[0]; a.nb2 = (int)op.i[1]; a.R = (int)op.i[2]; a.C = (int)op.i[3]; a.Rp = op.i[13];
+  CGD_CHECK_ARG(a.nb1 > 0 && a.nb2 > 0 && a.R > 0 && a.C > 0 && a.Rp >= a.R, "transpose: bad dims");
+  for (int k = 0; k < 3; ++k) {
+    if (!op.p[2 * k]) break;
+    CGD_CHECK_ARG(op.p[2 * k + 1] != nullptr, "transpose: null destination");
+    a.src[k] = (const __half*)op.p[2 * k];
+    a.dst[k] = (__half*)op.p[2 * k + 1];
+    a.sb1[k] = op.i[4 + 3 * k]; a.sb2[k] = op.i[5 + 3 * k]; a.sr[k] = op.i[6 + 3 * k];
+    a.npairs = k + 1;
+  }
+  CGD_CHECK_ARG(a.npairs > 0, "transpose: no operands");
+  dim3 grid((unsigned)ceil_div(a.R, 32), (unsigned)ceil_div(a.C, 32), (unsigned)(a.nb1 * a.nb2 * a.npairs));
+  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(a);
+  CGD_LAUNCH_CHECK();
+  return 0;
+}
+
+constexpr int SM_MAXV = 8;  // 8 x half8 per lane -> T <= 2048
+// in place: S[row, :T] (fp16 logits, un-scaled) -> P = softmax(scale * S) ; lse[row] = logsumexp(scale * S)
+__global__ void softmax_fwd_kernel(__half* __restrict__ S, float* __restrict__ lse, int64_t rows, int T, int64_t Tp, float scale) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  __half* s = S + row * Tp;
+  const int nv = T / 8;
+  float v[SM_MAXV][8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < SM_MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nv) {
+      unpack8(ld8(s + vi * 8), v[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[k][j] *= scale;
+        mx = fmaxf(mx, v[k][j]);
+      }
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < SM_MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[k][j] = __expf(v[k][j] - mx);
+        sum += v[k][j];
+      }
+    }
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  if (lane == 0 && lse) lse[row] = mx + __logf(sum);
+#pragma unroll
+  for (int k = 0; k < SM_MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[k][j] *= inv;
+      st8(s + vi * 8, pack8(v[k]));
+    }
+  }
+}
+// in place on dP: dS = P * (dP - sum_k P*dP) * scale
+__global__ void softmax_bwd_kernel(const __half* __restrict__ P, __half* __restrict__ dP, int64_t rows, int T, int64_t Tp, float scale) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __half* p = P + row * Tp;
+  __half* d = dP + row * Tp;
+  const int nv = T / 8;
+  float pv[SM_MAXV][8], dv[SM_MAXV][8];
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < SM_MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nv) {
+      unpack8(ld8(p + vi * 8), pv[k]);
+      unpack8(ld8(d + vi * 8), dv[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot = fmaf(pv[k][j], dv[k][j], dot);
+    }
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int k = 0; k < SM_MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dv[k][j] = pv[k][j] * (dv[k][j] - dot) * scale;
+      st8(d + vi * 8, pack8(dv[k]));
+    }
+  }
+}
+int launch_softmax_fwd(const CgdOp& op, cudaStream_t st) {
+  const int64_t rows = op.i[0], T = op.i[1], Tp = op.i[2];
+  CGD_CHECK_ARG(rows > 0 && T > 0 && T % 8 == 0 && T <= 8 * 32 * SM_MAXV && Tp >= T && Tp % 8 == 0 && op.p[0], "softmax: unsupported shape");
+  softmax_fwd_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>((__half*)op.p[0], (float*)op.p[1], rows, (int)T, Tp, op.f[0]);
+  CGD_LAUNCH_CHECK();
+  return 0;
+}
+int launch_softmax_bwd(const CgdOp& op, cudaStream_t st) {
+  const int64_t rows = op.i[0], T = op.i[1], Tp = op.i[2];
+  CGD_CHECK_ARG(rows > 0 && T > 0 && T % 8 == 0 && T <= 8 * 32 * SM_MAXV && Tp >= T && Tp % 8 == 0 && op.p[0] && op.p[1], "softmax bwd: unsupported shape");
+  softmax_bwd_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>((const __half*)op.p[0], (__half*)op.p[1], rows, (int)T, Tp, op.f[0]);
+  CGD_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace cgd

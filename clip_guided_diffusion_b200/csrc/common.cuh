@@ -72,10 +72,13 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return red[0];
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+// sigmoid with the SFU exp + approximate reciprocal (2 MUFU ops, ~2 ulp): these run per element in the HBM-bound
+// normalisation kernels, where the IEEE divide sequence (~10 instructions) was a visible share of the issue slots
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return v * sigmoid_fast(v); }
 // d silu(v)/dv
 __device__ __forceinline__ float silu_grad_f(float v) {
-  const float s = 1.f / (1.f + __expf(-v));
+  const float s = sigmoid_fast(v);
   return s * (1.f + v * (1.f - s));
 }
 

@@ -272,9 +272,8 @@ __global__ void conv_splitk_reduce_kernel(const ConvTcParams p, int m_tiles) {
 // cross-check the tcgen05 path layer by layer and so a tcgen05 regression cannot block bring-up of the
 // rest of the step; never selected by the shipped plans (impl = 0).
 __global__ void conv_simt_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, const ConvTcParams p,
-                                 int64_t a_sn, int64_t a_sh, int64_t a_sw) {
+                                 int64_t a_sn, int64_t a_sh, int64_t a_sw, int64_t ldb, int64_t b_sh, int64_t b_sn) {
   const int64_t total = (int64_t)p.NB * p.H * p.W * p.Cout;
-  const int K = p.taps * p.Cin;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int co = (int)(idx % p.Cout);
     int64_t pix = idx / p.Cout;
@@ -288,7 +287,7 @@ __global__ void conv_simt_kernel(const __half* __restrict__ A, const __half* __r
       const int yy = h + dy, xx = w + dx;
       if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
       const __half2* a = reinterpret_cast<const __half2*>(A + n * a_sn + yy * a_sh + xx * a_sw);
-      const __half2* wr = reinterpret_cast<const __half2*>(Wp + (int64_t)co * K + (int64_t)tap * p.Cin);
+      const __half2* wr = reinterpret_cast<const __half2*>(Wp + (int64_t)co * ldb + (int64_t)tap * p.Cin + (int64_t)h * b_sh + (int64_t)n * b_sn);
       for (int c = 0; c < p.Cin / 2; ++c) {
         const float2 av = __half22float2(a[c]), wv = __half22float2(wr[c]);
         acc = fmaf(av.x, wv.x, acc);
@@ -375,6 +374,7 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   L.A = reinterpret_cast<const __half*>(op.p[0]);
   L.Wp = reinterpret_cast<const __half*>(op.p[1]);
   L.a_sn = op.i[7]; L.a_sh = op.i[8]; L.a_sw = op.i[9];
+  L.ldb = op.i[22] > 0 ? op.i[22] : taps * Cin; L.b_sh = op.i[20]; L.b_sn = op.i[21];
   L.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   p.ws_rows = ((L.m_tiles + 1) / 2) * 2 * BM;
   L.n_tiles = (int)(Npad / BN);
@@ -393,17 +393,27 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
                   (int)r, (long long)Cin, (long long)W, (long long)H, (long long)NB, (long long)strides[0], (long long)strides[1],
                   (long long)strides[2], p.TW, p.TH, p.TN);
   }
+  const int64_t ldb = op.i[22] > 0 ? op.i[22] : taps * Cin;
+  p.b_batched = (op.i[20] != 0 || op.i[21] != 0) ? 1 : 0;
+  CGD_CHECK_ARG(ldb % 8 == 0 && op.i[20] % 8 == 0 && op.i[21] % 8 == 0, "conv: B strides must be multiples of 8 elements");
+  if (p.b_batched) CGD_CHECK_ARG(p.TH == 1 && p.TN == 1 && p.tiles_w % 2 == 0 && L.impl != 2 && L.m_tiles >= 2,
+                                 "conv: batched-B GEMMs need W %% 256 == 0 (one (h, n) per CTA pair) and the pair kernel");
   {
     const cuuint64_t K = (cuuint64_t)(taps * Cin);
     cuuint64_t dims[2] = {K, (cuuint64_t)Npad};
-    cuuint64_t strides[1] = {K * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)ldb * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, op.p[1], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
-    cuuint32_t box2[2] = {64, (cuuint32_t)(BN / 2)};
-    r = enc(&L.tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, op.p[1], dims, strides, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    // pair kernel: 4-D map (K, rows, h, n) so batched GEMMs pick their B matrix by the tile's (h, n); plain weights use (0, 0)
+    const cuuint64_t row_bytes = (cuuint64_t)ldb * 2 * (cuuint64_t)Npad;
+    cuuint64_t dims4[4] = {K, (cuuint64_t)Npad, (cuuint64_t)(p.b_batched ? H : 1), (cuuint64_t)(p.b_batched ? NB : 1)};
+    cuuint64_t strides4[3] = {(cuuint64_t)ldb * 2, p.b_batched ? (cuuint64_t)op.i[20] * 2 : row_bytes, p.b_batched ? (cuuint64_t)op.i[21] * 2 : row_bytes};
+    cuuint32_t box4[4] = {64, (cuuint32_t)(BN / 2), 1, 1};
+    cuuint32_t estr4[4] = {1, 1, 1, 1};
+    r = enc(&L.tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, op.p[1], dims4, strides4, box4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W half) failed with %d", (int)r);
   }
@@ -434,12 +444,13 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
     ConvTcParams p = L.p;
     p.splits = 1;
-    conv_simt_kernel<<<blocks, 256, 0, st>>>(L.A, L.Wp, p, L.a_sn, L.a_sh, L.a_sw);
+    conv_simt_kernel<<<blocks, 256, 0, st>>>(L.A, L.Wp, p, L.a_sn, L.a_sh, L.a_sw, L.ldb, L.b_sh, L.b_sn);
     CGD_LAUNCH_CHECK();
     return 0;
   }
   int rc = 0;
   if (conv_use_pair_kernel(L)) rc = conv_tc2_launch(L, st);
+  else if (L.p.b_batched) { set_error("conv: batched-B GEMM reached the single-CTA kernel"); return -1; }
   else
   switch (L.BN) {
     case 16: rc = launch_tc<16>(L, st); break;

@@ -14,6 +14,7 @@ struct ConvTcParams {
   int tiles_w, tiles_h, tiles_n;
   int kblocks, splits, kb_per_split; // K loop = taps * Cin/64 blocks, optionally split over gridDim.z
   int out_f32;
+  int b_batched;                     // B operand indexed by the tile's (h, n) (batched GEMM: attention)
   int ws_rows;                       // rows per split in the split-K workspace (= even-rounded m_tiles * 128)
   int64_t out_sn, out_sh, out_sw;    // output / residual strides in elements (channel contiguous)
   int64_t res_sn, res_sh, res_sw;
@@ -32,6 +33,7 @@ struct ConvTcLaunch {
   const __half* A;
   const __half* Wp;
   int64_t a_sn, a_sh, a_sw;
+  int64_t ldb, b_sh, b_sn;
 };
 
 int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L);

@@ -116,7 +116,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             dx = tap % 3 - 1;
           }
           tma2_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], cb * BK2, w0 + dx, h0 + dy, n0);
-          tma2_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK2, bcol);
+          tma2_load_4d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK2, bcol, p.b_batched ? h0 : 0, p.b_batched ? n0 : 0);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           else mbar_arrive_remote(&full_bar[stage], 0);
           if (++stage == Cfg::kStages) {
@@ -194,18 +194,33 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       } else {
         const int64_t o_off = (int64_t)n * p.out_sn + (int64_t)h * p.out_sh + (int64_t)w * p.out_sw;
         const int64_t r_off = (int64_t)n * p.res_sn + (int64_t)h * p.res_sh + (int64_t)w * p.res_sw;
+        // the residual is read ahead of use (one 16-column chunk = 32 B per row in flight while the previous one is
+        // converted and stored): un-prefetched, its ~800-cycle global loads serialised 16x per tile and made residual layers
+        // epilogue-bound (141 us vs 103 us on the 256x256 layer)
+        half8 rnext[2];
+        const bool vec_ok = !p.out_f32 && p.out_sc == 1;
+        const bool use_res = p.res != nullptr && row_ok && vec_ok;
+        if (use_res && ncol0 + 16 <= p.Cout) {
+          rnext[0] = ld8(p.res + r_off + ncol0);
+          rnext[1] = ld8(p.res + r_off + ncol0 + 8);
+        }
 #pragma unroll 1
         for (int c = 0; c < BN; c += 16) {
           uint32_t v[16];
           __syncwarp();
           tc_ld_32x16(taddr_row + c, v);
+          half8 rcur[2] = {rnext[0], rnext[1]};
+          if (use_res && c + 16 < BN && ncol0 + c + 32 <= p.Cout) {
+            rnext[0] = ld8(p.res + r_off + ncol0 + c + 16);
+            rnext[1] = ld8(p.res + r_off + ncol0 + c + 24);
+          }
           tc_ld_wait();
           const int col = ncol0 + c;
           if (row_ok && col < p.Cout) {
             float a[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] = __uint_as_float(v[j]);
-            if (col + 16 <= p.Cout && !p.out_f32 && p.out_sc == 1) {
+            if (col + 16 <= p.Cout && vec_ok) {
               if (p.bias) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
@@ -215,8 +230,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
               if (p.res) {
                 float rr[16];
-                unpack8(ld8(p.res + r_off + col), rr);
-                unpack8(ld8(p.res + r_off + col + 8), rr + 8);
+                unpack8(rcur[0], rr);
+                unpack8(rcur[1], rr + 8);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) a[j] += rr[j];
               }

@@ -24,6 +24,32 @@ static GnGeom gn_geom(int C) {
   return g;
 }
 
+// Deterministic block reduction of per-thread channel sums into the 32 groups: every thread parks its 8 channel sums in
+// shared memory ([pixel lane][channel], PP * C <= 2048 floats), then thread g adds the PP * (C/32) = 64 values of group g in
+// a fixed order.  (Shared float atomics would make the statistics -- and everything downstream -- run-to-run different.)
+__device__ __forceinline__ void block_group_reduce(const float* s, const float* q, int C, int col, int pl, int PP, float* red_s,
+                                                   float* red_q, float* gs, float* gq) {
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red_s[pl * C + col * 8 + j] = s[j];
+    red_q[pl * C + col * 8 + j] = q[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int cpg = C / 32, g = threadIdx.x;
+    float as = 0.f, aq = 0.f;
+    for (int l = 0; l < PP; ++l)
+      for (int c = 0; c < cpg; ++c) {
+        as += red_s[l * C + g * cpg + c];
+        aq += red_q[l * C + g * cpg + c];
+      }
+    gs[g] = as;
+    gq[g] = aq;
+  }
+  __syncthreads();
+}
+
 // Fixed-order (deterministic) fold of [nchunk][32][2] partials by the whole block: thread t sums chunks t/32, t/32 + nthr/32, ...
 // for group t%32 in fp64, then the per-part sums are combined in ascending part order.
 __device__ __forceinline__ void fold_partials(const float* part, int nchunk, double* out_s, double* out_q) {
@@ -70,6 +96,7 @@ __device__ __forceinline__ void fold_partials(const float* part, int nchunk, dou
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partials, float* __restrict__ stats,
                                 unsigned int* __restrict__ counters, int HW, int C, int64_t ld, int nchunk, float eps) {
   __shared__ float gs[32], gq[32];
+  __shared__ float red_s[2048], red_q[2048];
   __shared__ double fold_s[32], fold_q[32];
   __shared__ int is_last;
   const int n = blockIdx.y, chunk = blockIdx.x;
@@ -77,7 +104,6 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
   const int cpg = C / 32;
   const int ppc = (HW + nchunk - 1) / nchunk;
   const int p0 = chunk * ppc, p1 = min(HW, p0 + ppc);
-  if (threadIdx.x < 32) gs[threadIdx.x] = gq[threadIdx.x] = 0.f;
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
@@ -101,25 +127,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
     }
   }
   __syncthreads();
-  {  // fold the thread's 8 channels into their (1..8) groups, one shared atomic per run
-    int g_prev = (col * 8) / cpg;
-    float as = 0.f, aq = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (col * 8 + j) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&gs[g_prev], as);
-        atomicAdd(&gq[g_prev], aq);
-        as = aq = 0.f;
-        g_prev = g;
-      }
-      as += s[j];
-      aq += q[j];
-    }
-    atomicAdd(&gs[g_prev], as);
-    atomicAdd(&gq[g_prev], aq);
-  }
-  __syncthreads();
+  block_group_reduce(s, q, C, col, pl, PP, red_s, red_q, gs, gq);
   if (threadIdx.x < 32) {
     float* o = partials + (((int64_t)n * nchunk + chunk) * 32 + threadIdx.x) * 2;
     o[0] = gs[threadIdx.x];
@@ -204,6 +212,7 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
                                     float* __restrict__ partials, float* __restrict__ sums, unsigned int* __restrict__ counters,
                                     int HW, int C, int64_t ld_dy, int64_t ldx, int nchunk, int silu) {
   __shared__ float gs[32], gq[32];
+  __shared__ float red_s[2048], red_q[2048];
   __shared__ double fold_s[32], fold_q[32];
   __shared__ int is_last;
   const int n = blockIdx.y, chunk = blockIdx.x;
@@ -211,7 +220,6 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
   const int cpg = C / 32;
   const int ppc = (HW + nchunk - 1) / nchunk;
   const int p0 = chunk * ppc, p1 = min(HW, p0 + ppc);
-  if (threadIdx.x < 32) gs[threadIdx.x] = gq[threadIdx.x] = 0.f;
   float A[8], Bc[8], G[8], mu[8], rs[8];
   gn_coeffs(stats, gamma, beta, emb, n, C, col, A, Bc, G, mu, rs);
   float s[8], q[8];
@@ -246,25 +254,7 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
     }
   }
   __syncthreads();
-  {
-    int g_prev = (col * 8) / cpg;
-    float as = 0.f, aq = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (col * 8 + j) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&gs[g_prev], as);
-        atomicAdd(&gq[g_prev], aq);
-        as = aq = 0.f;
-        g_prev = g;
-      }
-      as += s[j];
-      aq += q[j];
-    }
-    atomicAdd(&gs[g_prev], as);
-    atomicAdd(&gq[g_prev], aq);
-  }
-  __syncthreads();
+  block_group_reduce(s, q, C, col, pl, PP, red_s, red_q, gs, gq);
   if (threadIdx.x < 32) {
     float* o = partials + (((int64_t)n * nchunk + chunk) * 32 + threadIdx.x) * 2;
     o[0] = gs[threadIdx.x];

@@ -17,6 +17,9 @@ int launch_add(const CgdOp& op, cudaStream_t st);
 int launch_copy(const CgdOp& op, cudaStream_t st);
 int launch_attn_fwd(const CgdOp& op, cudaStream_t st);
 int launch_attn_bwd(const CgdOp& op, cudaStream_t st);
+int launch_transpose(const CgdOp& op, cudaStream_t st);
+int launch_softmax_fwd(const CgdOp& op, cudaStream_t st);
+int launch_softmax_bwd(const CgdOp& op, cudaStream_t st);
 int launch_linear_small(const CgdOp& op, cudaStream_t st);
 int launch_timestep_emb(const CgdOp& op, cudaStream_t st);
 int launch_label_add(const CgdOp& op, cudaStream_t st);

@@ -135,6 +135,7 @@ class Plan:
         self._tape: list[Callable[[], None]] = []
         self._grads: dict = {}
         self.conv_impl = conv_impl
+        self.tc_attention = True  # long sequences (T % 256 == 0) on the tcgen05 GEMM kernel
         self.arena: Optional[th.Tensor] = None
         self.handle = None
         self._c_ops = None
@@ -211,15 +212,18 @@ class Plan:
 
     # ------------------------------------------------------------------ conv / GEMM
     def _emit_conv(self, x_ptr, x_strides, NB, H, W, Cin, wbuf, npad, Cout, taps, bias, res_ptr, res_strides, out_ptr, out_strides,
-                   out_f32=False, out_sc=1, tag=""):
+                   out_f32=False, out_sc=1, tag="", b_ptr=None, b_batch=(0, 0), ldb=0):
+        """b_ptr / b_batch / ldb: batched-GEMM mode (attention): the B operand is a strided activation matrix selected by the
+        tile's (h, n) instead of a packed weight."""
         m_tiles = conv_tile_count(NB, H, W)
         bn = pick_bn(npad, m_tiles)
         kblocks = taps * Cin // 64
         splits = pick_splits(m_tiles, npad // bn, kblocks, npad)
         ws = self.new(splits * ((m_tiles + 1) // 2 * 2) * 128 * npad, "f", "splitk_ws") if splits > 1 else None
-        i = [NB, H, W, Cin, Cout, npad, taps, *x_strides, *out_strides, *(res_strides or (0, 0, 0)), bn, splits, self.conv_impl, out_sc]
+        i = [NB, H, W, Cin, Cout, npad, taps, *x_strides, *out_strides, *(res_strides or (0, 0, 0)), bn, splits, self.conv_impl, out_sc,
+             b_batch[0], b_batch[1], ldb]
         self.emit("CONV", flags=1 if out_f32 else 0, i=i,
-                  p=[x_ptr, self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws)], tag=tag)
+                  p=[x_ptr, b_ptr if b_ptr is not None else self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws)], tag=tag)
 
     @staticmethod
     def _strides(a: Act):
@@ -343,6 +347,8 @@ class Plan:
         C = qkv.C // 3
         d = C // heads
         assert d == 64, "attention kernels support head dim 64"
+        if T % 256 == 0 and self.tc_attention and self.conv_impl in (0, 1, 3):
+            return self._attention_tc(qkv, heads, T, nbatch, legacy_order, name)
         out = Act(self.new(nbatch * T * C, "h", name), 0, qkv.N, qkv.H, qkv.W, C, C)
         lse = self.new(nbatch * heads * T, "f", name + "_lse")
         if legacy_order:
@@ -366,6 +372,62 @@ class Plan:
             self.emit("ATTN_BWD", i=ii, f=[scale],
                       p=[q, k, v, self._ap(out), self._ap(do), self._bp(lse), (dqkv.buf, qo), (dqkv.buf, ko), (dqkv.buf, vo), self._bp(delta)],
                       tag="d_" + name)
+            self.add_grad(qkv, dqkv)
+
+        self._tape.append(bwd)
+        return out
+
+    def _attention_tc(self, qkv: Act, heads: int, T: int, B: int, legacy_order: bool, name: str) -> Act:
+        """softmax(Q K^T / sqrt(d)) V for T % 256 == 0 as batched tcgen05 GEMMs (S and P materialised in fp16 like the
+        reference's einsum / softmax(w.float()).type(dtype)), transposes so that every operand is K-major, row softmax."""
+        C = qkv.C // 3
+        d, ld = 64, qkv.ld
+        hs, qo, ko, vo = (3 * d, 0, d, 2 * d) if legacy_order else (d, 0, C, 2 * C)
+        scale = 1.0 / math.sqrt(d)
+        q, k, v = ((qkv.buf, qkv.eoff + o) for o in (qo, ko, vo))
+        qkv_str = (T * ld, hs, ld)          # (batch, head, row) strides of a q / k / v view
+        tt_str = (heads * T * T, T * T, T)  # [B, heads, T, T] matrices
+        dt_str = (d * T, heads * d * T)     # per-head / per-batch strides of [B, heads, d, T] transposes
+        out = Act(self.new(B * T * C, "h", name), 0, qkv.N, qkv.H, qkv.W, C, C)
+        o_str = (T * C, d, C)
+        S = self.new(B * heads * T * T, "h", name + "_P")
+        lse = self.new(B * heads * T, "f", name + "_lse")
+        Vt = self.new(B * heads * d * T, "h", name + "_Vt")
+        rows = B * heads * T
+
+        def gemm(a_ptr, a_str, K, b_ptr, b_ld, b_batch, N, o_ptr, o_strides, tag):
+            self._emit_conv(a_ptr, a_str, B, heads, T, K, None, N, N, 1, None, None, None, o_ptr, o_strides, tag=tag,
+                            b_ptr=b_ptr, b_batch=b_batch, ldb=b_ld)
+
+        def transpose(pairs, R, Cc, tag):
+            ii = [B, heads, R, Cc] + [0] * 9 + [R]
+            pp = []
+            for j, (src, sstr, dst) in enumerate(pairs):
+                ii[4 + 3 * j: 7 + 3 * j] = list(sstr)
+                pp += [src, (dst, 0)]
+            self.emit("TRANSPOSE", i=ii, p=pp, tag=tag)
+
+        transpose([(v, qkv_str, Vt)], T, d, name + ".Vt")
+        gemm(q, qkv_str, d, k, ld, (hs, T * ld), T, (S, 0), tt_str, name + ".QK^T")
+        self.emit("SOFTMAX_FWD", i=[rows, T, T], f=[scale], p=[(S, 0), (lse, 0)], tag=name + ".softmax")
+        gemm((S, 0), tt_str, T, (Vt, 0), T, dt_str, d, self._ap(out), o_str, name + ".PV")
+
+        def bwd():
+            do = self.grad_of(out)
+            if do is None:
+                return
+            assert do.ld == C
+            dOt, Kt, Qt = (self.new(B * heads * d * T, "h", name + n_) for n_ in ("_dOt", "_Kt", "_Qt"))
+            transpose([(self._ap(do), o_str, dOt), (k, qkv_str, Kt), (q, qkv_str, Qt)], T, d, "d_" + name + ".T1")
+            dP = self.new(B * heads * T * T, "h", name + "_dS")
+            gemm(self._ap(do), o_str, d, v, ld, (hs, T * ld), T, (dP, 0), tt_str, "d_" + name + ".dP")
+            self.emit("SOFTMAX_BWD", i=[rows, T, T], f=[scale], p=[(S, 0), (dP, 0)], tag="d_" + name + ".softmax")
+            Pt, dSt = (self.new(B * heads * T * T, "h", name + n_) for n_ in ("_Pt", "_dSt"))
+            transpose([((S, 0), tt_str, Pt), ((dP, 0), tt_str, dSt)], T, T, "d_" + name + ".T2")
+            dqkv = Act(self.new(B * T * ld, "h", "d_" + name), 0, qkv.N, qkv.H, qkv.W, qkv.C, ld)
+            gemm((Pt, 0), tt_str, T, (dOt, 0), T, dt_str, d, (dqkv.buf, vo), qkv_str, "d_" + name + ".dV")
+            gemm((dP, 0), tt_str, T, (Kt, 0), T, dt_str, d, (dqkv.buf, qo), qkv_str, "d_" + name + ".dQ")
+            gemm((dSt, 0), tt_str, T, (Qt, 0), T, dt_str, d, (dqkv.buf, ko), qkv_str, "d_" + name + ".dK")
             self.add_grad(qkv, dqkv)
 
         self._tape.append(bwd)

@@ -59,6 +59,8 @@ enum {
    *   i7..9 A strides (n,h,w)  i10..12 out strides  i13..15 res strides  i16 BN  i17 splits
    *   i18 impl (0 = tcgen05, 1 = SIMT verification kernel)  i19 out channel stride (0/1 = contiguous; >1 only
    *   with scalar stores, e.g. fp32 NCHW outputs of the UNet head / stem dgrad)
+   *   i20, i21 batched-GEMM mode: element strides of the B operand per h / per n index (0, 0 = one shared weight matrix);
+   *   i22 row stride of B (0 = taps*Cin).  Batched mode needs W % 256 == 0 (attention: A = Q/P/dS..., B = K/V^T/...)
    *   flags: 1 = out is fp32 */
   CGD_OP_CONV = 1,
   /* GroupNorm(32) statistics: per (image, chunk, group) partial sum / sum of squares; the last block per image
@@ -150,6 +152,16 @@ enum {
   CGD_OP_SAMPLE_DDIM = 28,
   /* fp16 copy of a [rows, C] block: p0 src p1 dst ; i0 rows i1 C i2 lds i3 ldd */
   CGD_OP_COPY = 29,
+  /* batched fp16 transpose, up to three (src, dst) pairs per launch: dst[b1][b2][c][r] = src[b1][b2][r][c]
+   * p0 src0 p1 dst0 p2 src1 p3 dst1 p4 src2 p5 dst2 (unused pairs null) ; i0 nb1 i1 nb2 i2 R i3 C
+   * i4..6 src0 strides (b1, b2, row)  i7..9 src1  i10..12 src2 ; i13 Rp (dst row stride; dst dense [nb1][nb2][C][Rp]) */
+  CGD_OP_TRANSPOSE = 30,
+  /* row softmax in place: S (fp16 un-scaled logits [rows, Tp]) -> P = softmax(f0 * S[:, :T]) ; p1 lse(f [rows])|0
+   * p0 S ; i0 rows i1 T i2 Tp ; f0 scale.  With CGD_OP_CONV (batched B) this is the tensor-core attention of the
+   * 32x32 / 16x16 UNet levels ([3P] QKVAttention(Legacy): softmax(w.float()).type(w.dtype)). */
+  CGD_OP_SOFTMAX_FWD = 31,
+  /* softmax backward in place on dP: dS = P * (dP - rowsum(P * dP)) * f0 ; p0 P p1 dP ; i0 rows i1 T i2 Tp */
+  CGD_OP_SOFTMAX_BWD = 32,
   CGD_OP__COUNT
 };
 
