@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" surface of libcgd_b200.so (include/cgd_b200.h): plans (op lists with pre-encoded
 // TMA descriptors), per-op dispatch, network / step aliases and stand-alone operator entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -9,8 +10,18 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "ops.cuh"
+#include "pdl.cuh"
 
 namespace cgd {
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CGD_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
@@ -43,6 +54,8 @@ static int dispatch(const CgdOp& op, const ConvTcLaunch* conv, cudaStream_t st) 
     case CGD_OP_TRANSPOSE: return launch_transpose(op, st);
     case CGD_OP_SOFTMAX_FWD: return launch_softmax_fwd(op, st);
     case CGD_OP_SOFTMAX_BWD: return launch_softmax_bwd(op, st);
+    case CGD_OP_GN_FWD_FUSED: return launch_gn_fwd_fused(op, st);
+    case CGD_OP_GN_BWD_FUSED: return launch_gn_bwd_fused(op, st);
     case CGD_OP_LINEAR_SMALL: return launch_linear_small(op, st);
     case CGD_OP_TIMESTEP_EMB: return launch_timestep_emb(op, st);
     case CGD_OP_LABEL_ADD: return launch_label_add(op, st);

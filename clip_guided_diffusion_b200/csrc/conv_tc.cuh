@@ -16,6 +16,7 @@ struct ConvTcParams {
   int out_f32;
   int b_batched;                     // B operand indexed by the tile's (h, n) (batched GEMM: attention)
   int ws_rows;                       // rows per split in the split-K workspace (= even-rounded m_tiles * 128)
+  int dbg;                           // CGD_CONV_DBG (profiling experiments only): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue stores
   int64_t out_sn, out_sh, out_sw;    // output / residual strides in elements (channel contiguous)
   int64_t res_sn, res_sh, res_sw;
   int64_t out_sc;                    // output channel stride (1 except for NCHW fp32 outputs; scalar-store paths only)

@@ -12,6 +12,7 @@
 // full barrier (peer-bit-masked address); the leader's single MMA thread issues the MMAs and multicasts tcgen05.commit to
 // the empty barriers / tmem_full barriers of both CTAs.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -115,9 +116,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             dy = tap / 3 - 1;
             dx = tap % 3 - 1;
           }
-          tma2_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], cb * BK2, w0 + dx, h0 + dy, n0);
-          tma2_load_4d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK2, bcol, p.b_batched ? h0 : 0, p.b_batched ? n0 : 0);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          if (!(p.dbg & 1)) {
+            tma2_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], cb * BK2, w0 + dx, h0 + dy, n0);
+            tma2_load_4d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK2, bcol, p.b_batched ? h0 : 0, p.b_batched ? n0 : 0);
+          }
+          if (leader) mbar_expect_tx(&full_bar[stage], (p.dbg & 1) ? 0u : 2 * Cfg::kStageBytes);
           else mbar_arrive_remote(&full_bar[stage], 0);
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -144,6 +147,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
           const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+          if (!(p.dbg & 2))
 #pragma unroll
           for (int k = 0; k < BK2 / 16; ++k)
             tc2_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > tl.kb0 || k > 0) ? 1u : 0u);
@@ -171,7 +175,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const Tile2 tl = decode_tile(p, t, n_tiles, pair_tiles, rank);
       const int tw_i = tl.mt % p.tiles_w, th_i = (tl.mt / p.tiles_w) % p.tiles_h, tn_i = tl.mt / (p.tiles_w * p.tiles_h);
       const int w = tw_i * p.TW + r % p.TW, h = th_i * p.TH + (r / p.TW) % p.TH, n = tn_i * p.TN + r / (p.TW * p.TH);
-      const bool row_ok = (n < p.NB) && (h < p.H) && (w < p.W);
+      const bool row_ok = (n < p.NB) && (h < p.H) && (w < p.W) && !(p.dbg & 4);
       const int ncol0 = tl.n_tile * BN;
       const int acc = iter & 1;
       mbar_wait(&tmem_full_bar[acc], (iter >> 1) & 1);
@@ -272,8 +276,15 @@ static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   }
   const int pair_tiles = (L.m_tiles + 1) / 2;
   const int total = pair_tiles * L.n_tiles * L.p.splits;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("CGD_CONV_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  ConvTcParams prm = L.p;
+  prm.dbg = dbg;
   const int clusters = std::min(total, 74);  // 148 SMs = 74 TPC pairs
-  conv_tc2_kernel<BN><<<2 * clusters, kThreads2, Cfg::kSmemBytes, st>>>(L.tmA, L.tmB2, L.p, L.n_tiles, pair_tiles, total);
+  conv_tc2_kernel<BN><<<2 * clusters, kThreads2, Cfg::kSmemBytes, st>>>(L.tmA, L.tmB2, prm, L.n_tiles, pair_tiles, total);
   CGD_LAUNCH_CHECK();
   return 0;
 }

@@ -127,8 +127,29 @@ def pick_splits(m_tiles, n_tiles, kblocks, npad, ws_cap_bytes=16 << 20) -> int:
     return -(-kblocks // per)
 
 
+def gn_fused_cluster(N: int, HW: int, C: int, maxv: int) -> int:
+    """Cluster size (CTAs along the pixel dimension) of the single-launch GroupNorm kernels (csrc/norm_fused.cu), or 0 when the
+    (image, group) slab does not fit: 512 threads, 16-byte vectors, at most `maxv` vectors per thread (16 forward, 8 backward),
+    clusters of at most 8 CTAs.  Beyond the minimum, the cluster grows until the grid has ~one CTA per SM."""
+    if C % 256 != 0 or C > 4096:
+        return 0
+    cpg = C // 32
+    gpc = 16 // cpg if cpg < 16 else 1
+    vpp = gpc * cpg // 8
+    pp = 512 // vpp
+    cs = 1
+    while cs <= 8 and -(-HW // cs) > maxv * pp:
+        cs *= 2
+    if cs > 8:
+        return 0
+    while cs < 8 and (32 // gpc) * cs * N < 128 and -(-HW // (2 * cs)) >= pp:
+        cs *= 2
+    return cs
+
+
 class Plan:
     def __init__(self, conv_impl: int = 0):
+        self.fused_gn = True  # single-launch GroupNorm where the slab fits a cluster (csrc/norm_fused.cu)
         self.ops: list[PlanOp] = []
         self._size = 0
         self._consts: list[tuple[Buf, th.Tensor]] = []
@@ -259,31 +280,43 @@ class Plan:
     # ------------------------------------------------------------------ GroupNorm (+SiLU, +scale/shift)
     def group_norm(self, x: Act, gamma: Buf, beta: Buf, emb: Optional[tuple] = None, silu=True, eps=1e-5, name="gn") -> Act:
         N, HW, C = x.N, x.HW, x.C
-        pp = max(1, 256 // (C // 8))
-        nchunk = int(min(max(1, -(-HW // (pp * 16))), max(1, 296 // N)))
-        partials = self.new(N * nchunk * 64, "f", name + "_part")
-        stats = self.new(N * 64, "f", name + "_stats")
-        counters = self.new(N, "u32", name + "_cnt")
         y = self.act(N, x.H, x.W, C, name)
+        stats = self.new(N * 64, "f", name + "_stats")
         embp = self._bp(emb[0], emb[1]) if emb is not None else None
-        self.emit("GN_STATS", i=[N, HW, C, x.ld, nchunk], f=[eps], p=[self._ap(x), self._bp(partials), self._bp(stats), self._bp(counters)], tag=name)
-        self.emit("GN_APPLY", flags=1 if silu else 0, i=[N, HW, C, x.ld, nchunk, y.ld], f=[eps],
-                  p=[self._ap(x), self._bp(stats), self._bp(gamma), self._bp(beta), embp, self._ap(y)], tag=name)
+        cs_f = gn_fused_cluster(N, HW, C, 16) if self.fused_gn else 0
+        if cs_f:
+            self.emit("GN_FWD_FUSED", flags=1 if silu else 0, i=[N, HW, C, x.ld, y.ld, cs_f], f=[eps],
+                      p=[self._ap(x), self._bp(gamma), self._bp(beta), embp, self._ap(y), self._bp(stats)], tag=name)
+        else:
+            pp = max(1, 256 // (C // 8))
+            nchunk = int(min(max(1, -(-HW // (pp * 16))), max(1, 296 // N)))
+            partials = self.new(N * nchunk * 64, "f", name + "_part")
+            counters = self.new(N, "u32", name + "_cnt")
+            self.emit("GN_STATS", i=[N, HW, C, x.ld, nchunk], f=[eps], p=[self._ap(x), self._bp(partials), self._bp(stats), self._bp(counters)], tag=name)
+            self.emit("GN_APPLY", flags=1 if silu else 0, i=[N, HW, C, x.ld, nchunk, y.ld], f=[eps],
+                      p=[self._ap(x), self._bp(stats), self._bp(gamma), self._bp(beta), embp, self._ap(y)], tag=name)
 
         def bwd():
             dy = self.grad_of(y)
             if dy is None:
                 return
-            bpart = self.new(N * nchunk * 64, "f", name + "_bpart")
-            sums = self.new(N * 64, "f", name + "_bsums")
-            bcnt = self.new(N, "u32", name + "_bcnt")
             common = [self._ap(dy), self._ap(x), self._bp(stats), self._bp(gamma), self._bp(beta), embp]
-            self.emit("GN_BWD_STATS", flags=1 if silu else 0, i=[N, HW, C, dy.ld, x.ld, nchunk], f=[eps],
-                      p=common + [self._bp(bpart), self._bp(sums), self._bp(bcnt)], tag="d_" + name)
+            cs_b = gn_fused_cluster(N, HW, C, 8) if self.fused_gn else 0
             cur, has = self.writable_grad(x)
             dx = cur if has else self.act(N, x.H, x.W, C, "d_" + name)
-            self.emit("GN_BWD_APPLY", flags=(1 if silu else 0) | (2 if has else 0), i=[N, HW, C, dy.ld, x.ld, nchunk, dx.ld], f=[eps],
-                      p=common + [self._bp(sums), self._ap(dx)], tag="d_" + name)
+            fl = (1 if silu else 0) | (2 if has else 0)
+            if cs_b:
+                self.emit("GN_BWD_FUSED", flags=fl, i=[N, HW, C, dy.ld, x.ld, dx.ld, cs_b], f=[eps], p=common + [self._ap(dx)], tag="d_" + name)
+            else:
+                pp = max(1, 256 // (C // 8))
+                nchunk = int(min(max(1, -(-HW // (pp * 16))), max(1, 296 // N)))
+                bpart = self.new(N * nchunk * 64, "f", name + "_bpart")
+                sums = self.new(N * 64, "f", name + "_bsums")
+                bcnt = self.new(N, "u32", name + "_bcnt")
+                self.emit("GN_BWD_STATS", flags=1 if silu else 0, i=[N, HW, C, dy.ld, x.ld, nchunk], f=[eps],
+                          p=common + [self._bp(bpart), self._bp(sums), self._bp(bcnt)], tag="d_" + name)
+                self.emit("GN_BWD_APPLY", flags=fl, i=[N, HW, C, dy.ld, x.ld, nchunk, dx.ld], f=[eps],
+                          p=common + [self._bp(sums), self._ap(dx)], tag="d_" + name)
             self._grads[x.key()] = dx
 
         self._tape.append(bwd)

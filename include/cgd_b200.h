@@ -162,6 +162,16 @@ enum {
   CGD_OP_SOFTMAX_FWD = 31,
   /* softmax backward in place on dP: dS = P * (dP - rowsum(P * dP)) * f0 ; p0 P p1 dP ; i0 rows i1 T i2 Tp */
   CGD_OP_SOFTMAX_BWD = 32,
+  /* single-launch GroupNorm(32) forward for activations whose (image, group) slab fits one thread-block cluster's
+   * registers (C % 256 == 0, ceil(HW / CS) <= 16 * 512 / vectors-per-pixel): exact two-pass statistics exchanged through
+   * distributed shared memory, y = silu?( GN(x)*(1+scale)+shift ), stats written for the backward.
+   * p0 x(h) p1 gamma(f) p2 beta(f) p3 emb(f [N,2C])|0 p4 y(h) p5 stats(f [N,32,2] = mean, rstd)
+   * i0 N i1 HW i2 C i3 ldx i4 ldy i5 CS (cluster size 1|2|4|8 along the pixels) ; f0 eps ; flags 1 = SiLU */
+  CGD_OP_GN_FWD_FUSED = 33,
+  /* single-launch backward of the above (same math as GN_BWD_STATS + GN_BWD_APPLY; slab limit 8 * 512 / vectors-per-pixel)
+   * p0 dy p1 x p2 stats p3 gamma p4 beta p5 emb|0 p6 dx(h) ; i0 N i1 HW i2 C i3 ld_dy i4 ldx i5 ld_dx i6 CS
+   * flags 1 = SiLU, 2 = accumulate into dx */
+  CGD_OP_GN_BWD_FUSED = 34,
   CGD_OP__COUNT
 };
 

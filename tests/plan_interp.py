@@ -147,6 +147,29 @@ class Interp:
         dx = self.V(op.p[7], (N, HW, C), (HW * ld_dx, ld_dx, 1))
         dx.copy_(dx.float() + r if op.flags & 2 else r)
 
+    def op_GN_FWD_FUSED(self, op):
+        N, HW, C, ldx, ldy = op.i[:5]
+        x = self.V(op.p[0], (N, HW, C), (HW * ldx, ldx, 1))
+        xd = x.double().view(N, HW, 32, C // 32)
+        st = self.V(op.p[5], (N, 32, 2), (64, 2, 1))
+        st[:, :, 0] = xd.mean(dim=(1, 3)).float()
+        st[:, :, 1] = (1.0 / th.sqrt(xd.var(dim=(1, 3), unbiased=False) + op.f[0])).float()
+        A, Bc, _, _, _ = self._gn_affine(op, op.p[5], op.p[1], op.p[2], op.p[3], N, C)
+        v = x.float() * A[:, None] + Bc[:, None]
+        if op.flags & 1:
+            v = F.silu(v)
+        self.V(op.p[4], (N, HW, C), (HW * ldy, ldy, 1)).copy_(v)
+
+    def op_GN_BWD_FUSED(self, op):
+        N, HW, C, dxh, xh, rstd = self._gn_bwd_common(op)
+        cpg = C // 32
+        m1 = dxh.double().view(N, HW, 32, cpg).mean(dim=(1, 3)).float().repeat_interleave(cpg, dim=1)[:, None]
+        m2 = (dxh * xh).double().view(N, HW, 32, cpg).mean(dim=(1, 3)).float().repeat_interleave(cpg, dim=1)[:, None]
+        r = rstd[:, None] * (dxh - m1 - xh * m2)
+        ld_dx = op.i[5]
+        dx = self.V(op.p[6], (N, HW, C), (HW * ld_dx, ld_dx, 1))
+        dx.copy_(dx.float() + r if op.flags & 2 else r)
+
     def op_POOL2(self, op):
         N, H, W, C, ldx, ldy = op.i[:6]
         x = self.V(op.p[0], (N, H, W, C), (H * W * ldx, W * ldx, ldx, 1)).float()
