@@ -7,6 +7,7 @@
 // operands are addressed by (batch, row, head) strides so both the legacy per-head [q|k|v] interleave and the
 // [q..|k..|v..] order read straight out of the fused qkv GEMM output.
 #include "common.cuh"
+#include "pdl.cuh"
 #include "ops.cuh"
 
 namespace cgd {
@@ -78,6 +79,8 @@ __device__ __forceinline__ float row16_sum(float v) {
 }
 
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float sm[];
   float* QsT = sm;
   float* KsT = QsT + AT * ALD;
@@ -151,6 +154,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
 
 // delta[b,h,q] = sum_d dO[q,d] * O[q,d]; one warp per row
 __global__ void attn_delta_kernel(const AttnArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int64_t total = (int64_t)a.B * a.heads * a.T;
@@ -167,6 +172,8 @@ __global__ void attn_delta_kernel(const AttnArgs a) {
 
 // dK, dV for one key tile: loop over query tiles
 __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const AttnArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float sm[];
   float* KsT = sm;
   float* VsT = KsT + AT * ALD;
@@ -236,6 +243,8 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const AttnArgs a) {
 
 // dQ for one query tile: loop over key tiles
 __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const AttnArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float sm[];
   float* QsT = sm;
   float* dOT = QsT + AT * ALD;
@@ -324,7 +333,7 @@ int launch_attn_fwd(const CgdOp& op, cudaStream_t st) {
     CGD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     set = true;
   }
-  attn_fwd_kernel<<<dim3((unsigned)ceil_div(a.T, AT), a.heads, a.B), 256, smem, st>>>(a);
+  CGD_CUDA(launch_pdl(attn_fwd_kernel, dim3((unsigned)ceil_div(a.T, AT), a.heads, a.B), dim3(256), smem, st, a));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -340,12 +349,12 @@ int launch_attn_bwd(const CgdOp& op, cudaStream_t st) {
     set = true;
   }
   const int64_t rows = (int64_t)a.B * a.heads * a.T;
-  attn_delta_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(a);
+  CGD_CUDA(launch_pdl(attn_delta_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, st, a));
   CGD_LAUNCH_CHECK();
   const dim3 grid((unsigned)ceil_div(a.T, AT), a.heads, a.B);
-  attn_bwd_dkv_kernel<<<grid, 256, smem_kv, st>>>(a);
+  CGD_CUDA(launch_pdl(attn_bwd_dkv_kernel, dim3(grid), dim3(256), smem_kv, st, a));
   CGD_LAUNCH_CHECK();
-  attn_bwd_dq_kernel<<<grid, 256, smem_q, st>>>(a);
+  CGD_CUDA(launch_pdl(attn_bwd_dq_kernel, dim3(grid), dim3(256), smem_q, st, a));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -367,6 +376,8 @@ struct TransposeArgs {
 };
 // dst[b1][b2][c][r] = src[b1][b2][r][c]; 32x32 tiles through shared memory, coalesced both ways
 __global__ void transpose_kernel(const TransposeArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __half tile[32][34];
   int z = blockIdx.z;
   const int pair = z % a.npairs;
@@ -399,7 +410,7 @@ int launch_transpose(const CgdOp& op, cudaStream_t st) {
   }
   CGD_CHECK_ARG(a.npairs > 0, "transpose: no operands");
   dim3 grid((unsigned)ceil_div(a.R, 32), (unsigned)ceil_div(a.C, 32), (unsigned)(a.nb1 * a.nb2 * a.npairs));
-  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(a);
+  CGD_CUDA(launch_pdl(transpose_kernel, dim3(grid), dim3(32, 8), 0, st, a));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -407,6 +418,8 @@ int launch_transpose(const CgdOp& op, cudaStream_t st) {
 constexpr int SM_MAXV = 8;  // 8 x half8 per lane -> T <= 2048
 // in place: S[row, :T] (fp16 logits, un-scaled) -> P = softmax(scale * S) ; lse[row] = logsumexp(scale * S)
 __global__ void softmax_fwd_kernel(__half* __restrict__ S, float* __restrict__ lse, int64_t rows, int T, int64_t Tp, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -454,6 +467,8 @@ __global__ void softmax_fwd_kernel(__half* __restrict__ S, float* __restrict__ l
 }
 // in place on dP: dS = P * (dP - sum_k P*dP) * scale
 __global__ void softmax_bwd_kernel(const __half* __restrict__ P, __half* __restrict__ dP, int64_t rows, int T, int64_t Tp, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -486,14 +501,14 @@ __global__ void softmax_bwd_kernel(const __half* __restrict__ P, __half* __restr
 int launch_softmax_fwd(const CgdOp& op, cudaStream_t st) {
   const int64_t rows = op.i[0], T = op.i[1], Tp = op.i[2];
   CGD_CHECK_ARG(rows > 0 && T > 0 && T % 8 == 0 && T <= 8 * 32 * SM_MAXV && Tp >= T && Tp % 8 == 0 && op.p[0], "softmax: unsupported shape");
-  softmax_fwd_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>((__half*)op.p[0], (float*)op.p[1], rows, (int)T, Tp, op.f[0]);
+  CGD_CUDA(launch_pdl(softmax_fwd_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, st, (__half*)op.p[0], (float*)op.p[1], rows, (int)T, Tp, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 int launch_softmax_bwd(const CgdOp& op, cudaStream_t st) {
   const int64_t rows = op.i[0], T = op.i[1], Tp = op.i[2];
   CGD_CHECK_ARG(rows > 0 && T > 0 && T % 8 == 0 && T <= 8 * 32 * SM_MAXV && Tp >= T && Tp % 8 == 0 && op.p[0] && op.p[1], "softmax bwd: unsupported shape");
-  softmax_bwd_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>((const __half*)op.p[0], (__half*)op.p[1], rows, (int)T, Tp, op.f[0]);
+  CGD_CUDA(launch_pdl(softmax_bwd_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], rows, (int)T, Tp, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }

@@ -17,11 +17,13 @@
 // Small-M layers (8x8, 16x16 feature maps with K up to 18k) use split-K over gridDim.z with an fp32
 // workspace and a reduce kernel, so that the weight stream is spread over many SMs.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "pdl.cuh"
 #include "tc_ptx.cuh"
 
 namespace cgd {
@@ -85,6 +87,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer
@@ -213,6 +217,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // split-K second pass: sum partials, add bias / residual, store.  One thread per 4 consecutive columns (float4 partial
 // loads, splits unrolled by 4 for memory-level parallelism).
 __global__ void conv_splitk_reduce_kernel(const ConvTcParams p, int m_tiles) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int cq = (p.Cout + 3) / 4;
   const int64_t total = (int64_t)m_tiles * BM * cq;
   const size_t split_stride = (size_t)p.ws_rows * p.Npad;
@@ -273,6 +279,8 @@ __global__ void conv_splitk_reduce_kernel(const ConvTcParams p, int m_tiles) {
 // rest of the step; never selected by the shipped plans (impl = 0).
 __global__ void conv_simt_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, const ConvTcParams p,
                                  int64_t a_sn, int64_t a_sh, int64_t a_sw, int64_t ldb, int64_t b_sh, int64_t b_sn) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t total = (int64_t)p.NB * p.H * p.W * p.Cout;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int co = (int)(idx % p.Cout);
@@ -417,6 +425,30 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W half) failed with %d", (int)r);
   }
+  // pair-kernel epilogue through shared memory + TMA tensor stores: same 4-D box geometry as the A operand, so rows outside
+  // the image are clipped by the TMA unit; needs fp16 channel-contiguous output and whole 64-channel chunks
+  p.epi_tma = (conv_use_pair_kernel(L) && !p.out_f32 && p.out_sc == 1 && p.splits == 1 && BN >= 64 && Cout % 64 == 0) ? 1 : 0;
+  if (const char* e = getenv("CGD_CONV_EPI_TMA")) if (e[0] == '0') p.epi_tma = 0;
+  if (p.epi_tma) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint64_t ostr[3] = {(cuuint64_t)p.out_sw * 2, (cuuint64_t)p.out_sh * 2, (cuuint64_t)p.out_sn * 2};
+    CUresult r = enc(&L.tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, p.out, dims, ostr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+    if (p.res) {
+      cuuint64_t rstr[3] = {(cuuint64_t)p.res_sw * 2, (cuuint64_t)p.res_sh * 2, (cuuint64_t)p.res_sn * 2};
+      r = enc(&L.tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)p.res, dims, rstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(res) failed with %d", (int)r);
+    } else {
+      L.tmRes = L.tmOut;
+    }
+  } else {
+    L.tmOut = L.tmA;  // unused, but kernel parameters must be valid descriptors
+    L.tmRes = L.tmA;
+  }
   return 0;
 }
 
@@ -429,8 +461,7 @@ static int launch_tc(const ConvTcLaunch& L, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(L.m_tiles, L.n_tiles, L.p.splits);
-  conv_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(L.tmA, L.tmB, L.p);
-  CGD_LAUNCH_CHECK();
+  CGD_CUDA(launch_pdl(conv_tc_kernel<BN>, grid, dim3(kThreads), Cfg::kSmemBytes, st, L.tmA, L.tmB, L.p));
   return 0;
 }
 
@@ -444,8 +475,7 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
     ConvTcParams p = L.p;
     p.splits = 1;
-    conv_simt_kernel<<<blocks, 256, 0, st>>>(L.A, L.Wp, p, L.a_sn, L.a_sh, L.a_sw, L.ldb, L.b_sh, L.b_sn);
-    CGD_LAUNCH_CHECK();
+    CGD_CUDA(launch_pdl(conv_simt_kernel, dim3(blocks), dim3(256), 0, st, L.A, L.Wp, p, L.a_sn, L.a_sh, L.a_sw, L.ldb, L.b_sh, L.b_sn));
     return 0;
   }
   int rc = 0;
@@ -465,8 +495,7 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
   if (L.p.splits > 1) {
     const int64_t total = (int64_t)L.m_tiles * BM * ((L.p.Cout + 3) / 4);
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 8);
-    conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(L.p, L.m_tiles);
-    CGD_LAUNCH_CHECK();
+    CGD_CUDA(launch_pdl(conv_splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, L.p, L.m_tiles));
   }
   return 0;
 }

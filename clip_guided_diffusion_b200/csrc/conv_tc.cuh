@@ -16,6 +16,7 @@ struct ConvTcParams {
   int out_f32;
   int b_batched;                     // B operand indexed by the tile's (h, n) (batched GEMM: attention)
   int ws_rows;                       // rows per split in the split-K workspace (= even-rounded m_tiles * 128)
+  int epi_tma;                       // pair kernel: outputs leave through shared memory + TMA tensor stores (fp16, Cout % 64 == 0)
   int dbg;                           // CGD_CONV_DBG (profiling experiments only): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue stores
   int64_t out_sn, out_sh, out_sw;    // output / residual strides in elements (channel contiguous)
   int64_t res_sn, res_sh, res_sw;
@@ -29,6 +30,7 @@ struct ConvTcParams {
 struct ConvTcLaunch {
   CUtensorMap tmA, tmB;              // A: 4-D pixel box; B: [BN x 64] weight slice (single-CTA kernel)
   CUtensorMap tmB2;                  // B: [BN/2 x 64] half slice per CTA of a pair (cta_group::2 kernel)
+  CUtensorMap tmOut, tmRes;          // pair kernel epilogue: [64 ch x TW x TH x TN] boxes of the output / residual
   ConvTcParams p;
   int BN, impl, m_tiles, n_tiles;
   const __half* A;

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "pdl.cuh"
 #include "tc_ptx.cuh"
 
 namespace cgd {
@@ -26,15 +27,20 @@ constexpr int BM2 = 128, BK2 = 64;
 constexpr int kThreads2 = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
 constexpr int kEpiThreads2 = 128;
 
+constexpr int kEpiChunkBytes = BM2 * 64 * 2;  // one [128 rows x 64 channels] fp16 staging tile (SWIZZLE_128B)
+
 template <int BN>
 struct Tc2Cfg {
   static constexpr int kABytes = BM2 * BK2 * 2;          // 16 KB: this CTA's 128 pixel rows
   static constexpr int kBBytes = (BN / 2) * BK2 * 2;     // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  // epilogue staging: 2 output tiles (TMA store sources) + 2 residual tiles (TMA load destinations)
+  static constexpr int kEpiBytes = BN >= 64 ? 4 * kEpiChunkBytes : 0;
+  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - kEpiBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
 };
 
 struct Tile2 {
@@ -55,18 +61,20 @@ __device__ __forceinline__ Tile2 decode_tile(const ConvTcParams& p, int t, int n
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, int n_tiles,
-                int pair_tiles, int total_tiles) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                const __grid_constant__ CUtensorMap tmRes, const ConvTcParams p, int n_tiles, int pair_tiles, int total_tiles) {
   using Cfg = Tc2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;  // [out 0][out 1][res 0][res 1], 1024-byte aligned tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::kAccStages);
+  uint64_t* res_full_bar = tmem_empty_bar + Cfg::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -76,6 +84,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.epi_tma) {
+      tma_prefetch_desc(&tmOut);
+      if (p.res) tma_prefetch_desc(&tmRes);
+    }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's copy is the one used: one arrive per CTA (+ the TMA transaction bytes)
       mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
@@ -83,6 +95,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int a = 0; a < Cfg::kAccStages; ++a) {
       mbar_init(&tmem_full_bar[a], 1);                  // multicast tcgen05.commit
       mbar_init(&tmem_empty_bar[a], 2 * kEpiThreads2);  // leader's copy: every epilogue thread of both CTAs
+      mbar_init(&res_full_bar[a], 1);                   // residual staging tile landed (TMA transaction bytes)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -96,6 +109,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail (pdl.cuh)
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer (one thread per CTA)
@@ -171,6 +187,109 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     int iter = 0;
+    if constexpr (BN >= 64) {
+      if (p.epi_tma) {
+        // Accumulator -> registers -> (+bias, +residual) -> fp16 -> 128B-swizzled staging tile -> one TMA tensor store per
+        // [128 pixel x 64 channel] chunk.  Measured on B200 (profiles/r01_conv_microbench_v1.txt): the per-thread 16-byte row stores
+        // this replaces (32 partially written lines per warp instruction) bounded the 256x256 3x3 layer at 104 us, against
+        // 62 us for the same kernel with its stores disabled; the 1x1 layers ran at 24 -> 138 us.
+        constexpr int kChunks = BN / 64;
+        const bool issuer = threadIdx.x == 64;  // warp 2, lane 0: issues every TMA store / residual load of this CTA
+        const bool has_res = p.res != nullptr;
+        uint8_t* st_out = smem_epi;
+        uint8_t* st_res = smem_epi + 2 * kEpiChunkBytes;
+        auto tile_origin = [&](int tt, int& w0, int& h0, int& n0, int& ncol0) {
+          const Tile2 tl = decode_tile(p, tt, n_tiles, pair_tiles, rank);
+          const int tw_i = tl.mt % p.tiles_w, th_i = (tl.mt / p.tiles_w) % p.tiles_h, tn_i = tl.mt / (p.tiles_w * p.tiles_h);
+          w0 = tw_i * p.TW;
+          h0 = th_i * p.TH;
+          n0 = tn_i * p.TN;
+          ncol0 = tl.n_tile * BN;
+        };
+        auto issue_res = [&](int tt, int c, int buf) {  // issuer only
+          int w0, h0, n0, ncol0;
+          tile_origin(tt, w0, h0, n0, ncol0);
+          mbar_expect_tx(&res_full_bar[buf], kEpiChunkBytes);
+          tma_load_4d(st_res + buf * kEpiChunkBytes, &tmRes, &res_full_bar[buf], ncol0 + c * 64, w0, h0, n0);
+        };
+        if (issuer && has_res) {  // the first two residual chunks of this CTA's tile sequence
+          int tt = cluster_id, c = 0;
+          for (int k = 0; k < 2 && tt < total_tiles; ++k) {
+            issue_res(tt, c, k);
+            if (++c == kChunks) {
+              c = 0;
+              tt += n_clusters;
+            }
+          }
+        }
+        uint32_t g = 0;  // running chunk counter of this CTA: staging buffer = g & 1
+        const uint32_t sw = (uint32_t)(r & 7);
+        for (int t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
+          int w0, h0, n0, ncol0;
+          tile_origin(t, w0, h0, n0, ncol0);
+          const int acc = iter & 1;
+          mbar_wait(&tmem_full_bar[acc], (iter >> 1) & 1);
+          tc_fence_after();
+          const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+          for (int c = 0; c < kChunks; ++c, ++g) {
+            const int buf = (int)(g & 1u);
+            const int col = ncol0 + c * 64;
+            uint32_t v[64];
+            __syncwarp();  // reconverge (issuer-only branch below): the TMEM load is warp-collective (.sync.aligned)
+            tc_ld_32x32(taddr_row + c * 64, v);
+            tc_ld_32x32(taddr_row + c * 64 + 32, v + 32);
+            if (has_res) mbar_wait(&res_full_bar[buf], (g >> 1) & 1u);
+            tc_ld_wait();
+            if (c == kChunks - 1) {  // accumulator fully read: hand it back to the MMA thread before the stores
+              tc_fence_before();
+              mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+            }
+            // staging tile `buf` is free once the store issued two chunks ago has read it
+            if (issuer) bulk_wait_group_read<1>();
+            named_bar_sync(1, kEpiThreads2);
+            uint8_t* orow = st_out + buf * kEpiChunkBytes + r * 128;
+            const uint8_t* rrow = st_res + buf * kEpiChunkBytes + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // 8 channels = one 16-byte unit of the 128-byte row, unit index XOR (row & 7)
+              float a[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] = __uint_as_float(v[j * 8 + e]);
+              if (p.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j * 8 + 4));
+                a[0] += b0.x; a[1] += b0.y; a[2] += b0.z; a[3] += b0.w;
+                a[4] += b1.x; a[5] += b1.y; a[6] += b1.z; a[7] += b1.w;
+              }
+              const uint32_t unit = ((uint32_t)j ^ sw) * 16;
+              if (has_res) {
+                float rr[8];
+                unpack8(*reinterpret_cast<const half8*>(rrow + unit), rr);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += rr[e];
+              }
+              *reinterpret_cast<half8*>(orow + unit) = pack8(a);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiThreads2);
+            if (issuer) {
+              if (!(p.dbg & 4)) tma_store_4d(st_out + buf * kEpiChunkBytes, &tmOut, col, w0, h0, n0);
+              bulk_commit_group();
+              if (has_res) {  // residual tile `buf` has been consumed by every thread: refill it for chunk g + 2
+                int tt = t, c2 = c + 2;
+                while (c2 >= kChunks) {
+                  c2 -= kChunks;
+                  tt += n_clusters;
+                }
+                if (tt < total_tiles) issue_res(tt, c2, buf);
+              }
+            }
+          }
+        }
+        if (issuer) bulk_wait_group<0>();
+      }
+    }
+    if (!p.epi_tma)
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
       const Tile2 tl = decode_tile(p, t, n_tiles, pair_tiles, rank);
       const int tw_i = tl.mt % p.tiles_w, th_i = (tl.mt / p.tiles_w) % p.tiles_h, tn_i = tl.mt / (p.tiles_w * p.tiles_h);
@@ -284,8 +403,7 @@ static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   ConvTcParams prm = L.p;
   prm.dbg = dbg;
   const int clusters = std::min(total, 74);  // 148 SMs = 74 TPC pairs
-  conv_tc2_kernel<BN><<<2 * clusters, kThreads2, Cfg::kSmemBytes, st>>>(L.tmA, L.tmB2, prm, L.n_tiles, pair_tiles, total);
-  CGD_LAUNCH_CHECK();
+  CGD_CUDA(launch_pdl(conv_tc2_kernel<BN>, dim3(2 * clusters), dim3(kThreads2), Cfg::kSmemBytes, st, L.tmA, L.tmB2, L.tmOut, L.tmRes, prm, L.n_tiles, pair_tiles, total));
   return 0;
 }
 

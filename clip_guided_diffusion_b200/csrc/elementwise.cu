@@ -4,6 +4,7 @@
 // (SURVEY.md K6, K7, K8, K15): 128-bit vectorised, coalesced along channels, grid-stride loops sized to a
 // multiple of the 148 SMs.
 #include "common.cuh"
+#include "pdl.cuh"
 #include "ops.cuh"
 
 namespace cgd {
@@ -19,6 +20,8 @@ static inline int ew_blocks(int64_t work_items, int threads = 256) {
 // ---- 2x2 pooling (sum * scale) on pixel-major [N,H,W,C]
 __global__ void pool2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C, int64_t ldx,
                              int64_t ldy, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int V = C / 8, Ho = H / 2, Wo = W / 2;
   const int64_t total = (int64_t)N * Ho * Wo * V;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -42,6 +45,8 @@ __global__ void pool2_kernel(const __half* __restrict__ x, __half* __restrict__ 
 // ---- nearest x2 up-sampling (* scale)
 __global__ void up2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C, int64_t ldx,
                            int64_t ldy, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int V = C / 8, Ho = H * 2, Wo = W * 2;
   const int64_t total = (int64_t)N * Ho * Wo * V;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -62,6 +67,8 @@ __global__ void up2_kernel(const __half* __restrict__ x, __half* __restrict__ y,
 }
 __global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ c, int64_t rows, int C,
                            int64_t lda, int64_t ldb, int64_t ldc) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int V = C / 8;
   const int64_t total = rows * V;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -76,6 +83,8 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
   }
 }
 __global__ void copy_kernel(const __half* __restrict__ a, __half* __restrict__ c, int64_t rows, int C, int64_t lda, int64_t ldc) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int V = C / 8;
   const int64_t total = rows * V;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -88,31 +97,31 @@ __global__ void copy_kernel(const __half* __restrict__ a, __half* __restrict__ c
 int launch_pool2(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], H = op.i[1], W = op.i[2], C = op.i[3], ldx = op.i[4], ldy = op.i[5];
   CGD_CHECK_ARG(N > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1], "pool2: bad args");
-  pool2_kernel<<<ew_blocks(N * (H / 2) * (W / 2) * (C / 8)), 256, 0, st>>>((const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W,
-                                                                        (int)C, ldx, ldy, op.f[0]);
+  CGD_CUDA(launch_pdl(pool2_kernel, dim3(ew_blocks(N * (H / 2) * (W / 2) * (C / 8))), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W,
+                                                                        (int)C, ldx, ldy, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 int launch_up2(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], H = op.i[1], W = op.i[2], C = op.i[3], ldx = op.i[4], ldy = op.i[5];
   CGD_CHECK_ARG(N > 0 && H > 0 && W > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1], "up2: bad args");
-  up2_kernel<<<ew_blocks(N * H * W * 4 * (C / 8)), 256, 0, st>>>((const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W, (int)C,
-                                                                ldx, ldy, op.f[0]);
+  CGD_CUDA(launch_pdl(up2_kernel, dim3(ew_blocks(N * H * W * 4 * (C / 8))), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W, (int)C,
+                                                                ldx, ldy, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 int launch_add(const CgdOp& op, cudaStream_t st) {
   const int64_t rows = op.i[0], C = op.i[1];
   CGD_CHECK_ARG(rows > 0 && C % 8 == 0 && op.i[2] % 8 == 0 && op.i[3] % 8 == 0 && op.i[4] % 8 == 0 && op.p[0] && op.p[1] && op.p[2], "add: bad args");
-  add_kernel<<<ew_blocks(rows * (C / 8)), 256, 0, st>>>((const __half*)op.p[0], (const __half*)op.p[1], (__half*)op.p[2], rows, (int)C,
-                                                       op.i[2], op.i[3], op.i[4]);
+  CGD_CUDA(launch_pdl(add_kernel, dim3(ew_blocks(rows * (C / 8))), dim3(256), 0, st, (const __half*)op.p[0], (const __half*)op.p[1], (__half*)op.p[2], rows, (int)C,
+                                                       op.i[2], op.i[3], op.i[4]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 int launch_copy(const CgdOp& op, cudaStream_t st) {
   const int64_t rows = op.i[0], C = op.i[1];
   CGD_CHECK_ARG(rows > 0 && C % 8 == 0 && op.i[2] % 8 == 0 && op.i[3] % 8 == 0 && op.p[0] && op.p[1], "copy: bad args");
-  copy_kernel<<<ew_blocks(rows * (C / 8)), 256, 0, st>>>((const __half*)op.p[0], (__half*)op.p[1], rows, (int)C, op.i[2], op.i[3]);
+  CGD_CUDA(launch_pdl(copy_kernel, dim3(ew_blocks(rows * (C / 8))), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], rows, (int)C, op.i[2], op.i[3]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -120,6 +129,8 @@ int launch_copy(const CgdOp& op, cudaStream_t st) {
 // ---- layout conversion at the sampler boundary
 // fp32 NCHW [N,C,HW] -> fp16 pixel-major [N*HW, ld], channels >= C zero-filled
 __global__ void nchw_to_pm_kernel(const float* __restrict__ src, __half* __restrict__ dst, int N, int C, int64_t HW, int64_t ld, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int V = (int)(ld / 8);
   const int64_t total = (int64_t)N * HW * V;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -139,6 +150,8 @@ __global__ void nchw_to_pm_kernel(const float* __restrict__ src, __half* __restr
 template <typename T>
 __global__ void pm_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int64_t HW, int64_t ld, float scale,
                                   int accumulate) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t total = (int64_t)N * C * HW;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = idx % HW;
@@ -152,7 +165,7 @@ __global__ void pm_to_nchw_kernel(const T* __restrict__ src, float* __restrict__
 int launch_nchw_to_pm(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], C = op.i[1], HW = op.i[2], ld = op.i[3];
   CGD_CHECK_ARG(N > 0 && C > 0 && HW > 0 && ld % 8 == 0 && C <= ld && op.p[0] && op.p[1], "nchw_to_pm: bad args");
-  nchw_to_pm_kernel<<<ew_blocks(N * HW * (ld / 8)), 256, 0, st>>>((const float*)op.p[0], (__half*)op.p[1], (int)N, (int)C, HW, ld, op.f[0]);
+  CGD_CUDA(launch_pdl(nchw_to_pm_kernel, dim3(ew_blocks(N * HW * (ld / 8))), dim3(256), 0, st, (const float*)op.p[0], (__half*)op.p[1], (int)N, (int)C, HW, ld, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -161,15 +174,17 @@ int launch_pm_to_nchw(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(N > 0 && C > 0 && HW > 0 && C <= ld && op.p[0] && op.p[1], "pm_to_nchw: bad args");
   const int acc = (op.flags & 2) ? 1 : 0;
   if (op.flags & 1)
-    pm_to_nchw_kernel<float><<<ew_blocks(N * C * HW), 256, 0, st>>>((const float*)op.p[0], (float*)op.p[1], (int)N, (int)C, HW, ld, op.f[0], acc);
+    CGD_CUDA(launch_pdl(pm_to_nchw_kernel<float>, dim3(ew_blocks(N * C * HW)), dim3(256), 0, st, (const float*)op.p[0], (float*)op.p[1], (int)N, (int)C, HW, ld, op.f[0], acc));
   else
-    pm_to_nchw_kernel<__half><<<ew_blocks(N * C * HW), 256, 0, st>>>((const __half*)op.p[0], (float*)op.p[1], (int)N, (int)C, HW, ld, op.f[0], acc);
+    CGD_CUDA(launch_pdl(pm_to_nchw_kernel<__half>, dim3(ew_blocks(N * C * HW)), dim3(256), 0, st, (const __half*)op.p[0], (float*)op.p[1], (int)N, (int)C, HW, ld, op.f[0], acc));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 
 // ---- timestep / class embeddings ([3P] guided_diffusion.nn.timestep_embedding, UNetModel.label_emb)
 __global__ void timestep_emb_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim, float tscale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * half) return;
@@ -182,6 +197,8 @@ __global__ void timestep_emb_kernel(const float* __restrict__ t, float* __restri
   if ((dim & 1) && i == 0) out[(int64_t)b * dim + dim - 1] = 0.f;
 }
 __global__ void label_add_kernel(float* __restrict__ emb, const float* __restrict__ table, const int64_t* __restrict__ y, int B, int D) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * D) return;
   const int b = idx / D, d = idx % D;
@@ -190,20 +207,22 @@ __global__ void label_add_kernel(float* __restrict__ emb, const float* __restric
 int launch_timestep_emb(const CgdOp& op, cudaStream_t st) {
   const int64_t B = op.i[0], dim = op.i[1];
   CGD_CHECK_ARG(B > 0 && dim >= 2 && op.p[0] && op.p[1], "timestep_emb: bad args");
-  timestep_emb_kernel<<<(unsigned)ceil_div(B * (dim / 2), 128), 128, 0, st>>>((const float*)op.p[0], (float*)op.p[1], (int)B, (int)dim, op.f[0]);
+  CGD_CUDA(launch_pdl(timestep_emb_kernel, dim3((unsigned)ceil_div(B * (dim / 2), 128)), dim3(128), 0, st, (const float*)op.p[0], (float*)op.p[1], (int)B, (int)dim, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 int launch_label_add(const CgdOp& op, cudaStream_t st) {
   const int64_t B = op.i[0], D = op.i[1];
   CGD_CHECK_ARG(B > 0 && D > 0 && op.p[0] && op.p[1] && op.p[2], "label_add: bad args");
-  label_add_kernel<<<(unsigned)ceil_div(B * D, 256), 256, 0, st>>>((float*)op.p[0], (const float*)op.p[1], (const int64_t*)op.p[2], (int)B, (int)D);
+  CGD_CUDA(launch_pdl(label_add_kernel, dim3((unsigned)ceil_div(B * D, 256)), dim3(256), 0, st, (float*)op.p[0], (const float*)op.p[1], (const int64_t*)op.p[2], (int)B, (int)D));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 
 // ---- QuickGELU ([3P] clip.model.QuickGELU): a = u * sigmoid(1.702 u)
 __global__ void qgelu_fwd_kernel(const __half* __restrict__ u, __half* __restrict__ a, int64_t nvec) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (int64_t)gridDim.x * blockDim.x) {
     float v[8];
     unpack8(ld8(u + idx * 8), v);
@@ -213,6 +232,8 @@ __global__ void qgelu_fwd_kernel(const __half* __restrict__ u, __half* __restric
   }
 }
 __global__ void qgelu_bwd_kernel(const __half* __restrict__ da, const __half* __restrict__ u, __half* __restrict__ du, int64_t nvec) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (int64_t)gridDim.x * blockDim.x) {
     float v[8], d[8];
     unpack8(ld8(u + idx * 8), v);
@@ -228,20 +249,22 @@ __global__ void qgelu_bwd_kernel(const __half* __restrict__ da, const __half* __
 int launch_qgelu_fwd(const CgdOp& op, cudaStream_t st) {
   const int64_t n = op.i[0];
   CGD_CHECK_ARG(n > 0 && n % 8 == 0 && op.p[0] && op.p[1], "qgelu: bad args");
-  qgelu_fwd_kernel<<<ew_blocks(n / 8), 256, 0, st>>>((const __half*)op.p[0], (__half*)op.p[1], n / 8);
+  CGD_CUDA(launch_pdl(qgelu_fwd_kernel, dim3(ew_blocks(n / 8)), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], n / 8));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 int launch_qgelu_bwd(const CgdOp& op, cudaStream_t st) {
   const int64_t n = op.i[0];
   CGD_CHECK_ARG(n > 0 && n % 8 == 0 && op.p[0] && op.p[1] && op.p[2], "qgelu bwd: bad args");
-  qgelu_bwd_kernel<<<ew_blocks(n / 8), 256, 0, st>>>((const __half*)op.p[0], (const __half*)op.p[1], (__half*)op.p[2], n / 8);
+  CGD_CUDA(launch_pdl(qgelu_bwd_kernel, dim3(ew_blocks(n / 8)), dim3(256), 0, st, (const __half*)op.p[0], (const __half*)op.p[1], (__half*)op.p[2], n / 8));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 
 // ---- ViT token assembly ([3P] VisionTransformer.forward: cat(class_embedding, patches) + positional_embedding)
 __global__ void vit_embed_kernel(__half* __restrict__ tok, const float* __restrict__ cls, const float* __restrict__ pos, int n, int T, int w) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int V = w / 8;
   const int64_t total = (int64_t)n * T * V;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -266,7 +289,7 @@ __global__ void vit_embed_kernel(__half* __restrict__ tok, const float* __restri
 int launch_vit_embed(const CgdOp& op, cudaStream_t st) {
   const int64_t n = op.i[0], T = op.i[1], w = op.i[2];
   CGD_CHECK_ARG(n > 0 && T > 0 && w % 8 == 0 && op.p[0] && op.p[1] && op.p[2], "vit_embed: bad args");
-  vit_embed_kernel<<<ew_blocks(n * T * (w / 8)), 256, 0, st>>>((__half*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], (int)n, (int)T, (int)w);
+  CGD_CUDA(launch_pdl(vit_embed_kernel, dim3(ew_blocks(n * T * (w / 8))), dim3(256), 0, st, (__half*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], (int)n, (int)T, (int)w));
   CGD_LAUNCH_CHECK();
   return 0;
 }

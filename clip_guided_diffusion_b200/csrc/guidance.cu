@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "pdl.cuh"
 #include "ops.cuh"
 
 namespace cgd {
@@ -31,6 +32,8 @@ __device__ __forceinline__ void pool_bin(int o, int S, int cs, int& s, int& e) {
 // one thread per output element, written directly in ViT patch order (row k*B+b, patch, (c,ky,kx))
 __global__ void cutouts_fwd_kernel(const float* __restrict__ x, const int* __restrict__ coords, __half* __restrict__ out, int B, int H,
                                    int W, int cutn, int cs, int P, int Kpad, float3 mean, float3 stdv) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int g = cs / P, G2 = g * g, PP = P * P;
   const int64_t total = (int64_t)cutn * B * G2 * Kpad;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -65,6 +68,8 @@ __global__ void cutouts_fwd_kernel(const float* __restrict__ x, const int* __res
 // ---------------------------------------------------------------- cutouts backward (gather, no atomics)
 __global__ void cutouts_bwd_kernel(const __half* __restrict__ dpatch, const int* __restrict__ coords, float* __restrict__ dx, int B, int H,
                                    int W, int cutn, int cs, int P, int Kpad, float3 stdv, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int g = cs / P, G2 = g * g, PP = P * P;
   const int64_t total = (int64_t)B * 3 * H * W;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -112,18 +117,18 @@ int launch_cutouts_fwd(const CgdOp& op, cudaStream_t st) {
   if (int rc = cutout_check(op)) return rc;
   const int64_t B = op.i[0], cutn = op.i[3], cs = op.i[4], P = op.i[5], Kpad = op.i[6];
   const int64_t total = cutn * B * (cs / P) * (cs / P) * Kpad;
-  cutouts_fwd_kernel<<<gw_blocks(total), 256, 0, st>>>((const float*)op.p[0], (const int*)op.p[1], (__half*)op.p[2], (int)B, (int)op.i[1],
+  CGD_CUDA(launch_pdl(cutouts_fwd_kernel, dim3(gw_blocks(total)), dim3(256), 0, st, (const float*)op.p[0], (const int*)op.p[1], (__half*)op.p[2], (int)B, (int)op.i[1],
                                                       (int)op.i[2], (int)cutn, (int)cs, (int)P, (int)Kpad,
-                                                      make_float3(op.f[0], op.f[1], op.f[2]), make_float3(op.f[3], op.f[4], op.f[5]));
+                                                      make_float3(op.f[0], op.f[1], op.f[2]), make_float3(op.f[3], op.f[4], op.f[5])));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 int launch_cutouts_bwd(const CgdOp& op, cudaStream_t st) {
   if (int rc = cutout_check(op)) return rc;
   const int64_t B = op.i[0], H = op.i[1], W = op.i[2];
-  cutouts_bwd_kernel<<<gw_blocks(B * 3 * H * W), 256, 0, st>>>((const __half*)op.p[0], (const int*)op.p[1], (float*)op.p[2], (int)B, (int)H,
+  CGD_CUDA(launch_pdl(cutouts_bwd_kernel, dim3(gw_blocks(B * 3 * H * W)), dim3(256), 0, st, (const __half*)op.p[0], (const int*)op.p[1], (float*)op.p[2], (int)B, (int)H,
                                                               (int)W, (int)op.i[3], (int)op.i[4], (int)op.i[5], (int)op.i[6],
-                                                              make_float3(op.f[3], op.f[4], op.f[5]), op.f[6]);
+                                                              make_float3(op.f[3], op.f[4], op.f[5]), op.f[6]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -133,6 +138,8 @@ int launch_cutouts_bwd(const CgdOp& op, cudaStream_t st) {
 __global__ void spherical_kernel(const float* __restrict__ emb, const float* __restrict__ tgt, const float* __restrict__ wts,
                                  float* __restrict__ demb, float* __restrict__ loss, int cutn, int B, int P, int D, float cgs,
                                  float gscale) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float sh[];  // [nw] partial losses
   const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float wl = 0.f;
@@ -190,9 +197,9 @@ int launch_spherical(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(B == 1 || P == 1, "spherical: the reference's broadcast (cgd/cgd.py:196-200) is only defined for batch==1 or one prompt (got B=%lld, P=%lld)",
                 (long long)B, (long long)P);
   CGD_CHECK_ARG(op.p[0] && op.p[1] && op.p[2] && op.p[3] && op.p[4], "spherical: null pointer");
-  spherical_kernel<<<(unsigned)B, 256, 8 * sizeof(float), st>>>((const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2],
+  CGD_CUDA(launch_pdl(spherical_kernel, dim3((unsigned)B), dim3(256), 8 * sizeof(float), st, (const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2],
                                                                (float*)op.p[3], (float*)op.p[4], (int)cutn, (int)B, (int)P, (int)D, op.f[0],
-                                                               op.f[1]);
+                                                               op.f[1]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -201,6 +208,8 @@ int launch_spherical(const CgdOp& op, cudaStream_t st) {
 __global__ void pmv_blend_kernel(const float* __restrict__ x, const float* __restrict__ mo, const float* __restrict__ sc,
                                  float* __restrict__ x0o, float* __restrict__ meano, float* __restrict__ varo, float* __restrict__ lvo,
                                  float* __restrict__ xino, int B, int64_t HW, float* __restrict__ zero_buf, int nzero) {
+  pdl_wait();
+  pdl_launch_dependents();
   const float a = sc[CGD_SC_SQRT_RECIP_AC], bb = sc[CGD_SC_SQRT_RECIPM1_AC], c1 = sc[CGD_SC_POST_COEF1], c2 = sc[CGD_SC_POST_COEF2];
   const float minl = sc[CGD_SC_MIN_LOG], maxl = sc[CGD_SC_MAX_LOG], fac = sc[CGD_SC_FAC], omf = sc[CGD_SC_ONE_MINUS_FAC];
   if (zero_buf && blockIdx.x == 0 && threadIdx.x < nzero) zero_buf[threadIdx.x] = 0.f;
@@ -226,9 +235,9 @@ int launch_pmv_blend(const CgdOp& op, cudaStream_t st) {
   const int64_t B = op.i[0], HW = op.i[1];
   CGD_CHECK_ARG(B > 0 && HW > 0 && op.p[0] && op.p[1] && op.p[2] && op.p[3], "pmv_blend: bad args");
   CGD_CHECK_ARG(op.i[2] >= 0 && op.i[2] <= 256, "pmv_blend: zero-buffer length out of range");
-  pmv_blend_kernel<<<gw_blocks(B * 3 * HW), 256, 0, st>>>((const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], (float*)op.p[3],
+  CGD_CUDA(launch_pdl(pmv_blend_kernel, dim3(gw_blocks(B * 3 * HW)), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], (float*)op.p[3],
                                                         (float*)op.p[4], (float*)op.p[5], (float*)op.p[6], (float*)op.p[7], (int)B, HW,
-                                                        (float*)op.p[8], (int)op.i[2]);
+                                                        (float*)op.p[8], (int)op.i[2]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -238,6 +247,8 @@ int launch_pmv_blend(const CgdOp& op, cudaStream_t st) {
 __global__ void guide_grad_kernel(const float* __restrict__ xin, const float* __restrict__ x0, const float* __restrict__ gclip,
                                   const float* __restrict__ sc, __half* __restrict__ seed, float* __restrict__ dxd, float* __restrict__ loss,
                                   int B, int H, int W, int64_t ld, float tvs, float rs, float ss, float seed_scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[32];
   const int b = blockIdx.y;
   const int64_t HW = (int64_t)H * W, per = 3 * HW;
@@ -284,9 +295,9 @@ int launch_guide_grad(const CgdOp& op, cudaStream_t st) {
   const int64_t B = op.i[0], H = op.i[1], W = op.i[2], ld = op.i[3];
   CGD_CHECK_ARG(B > 0 && H > 0 && W > 0 && ld >= 3 && op.p[0] && op.p[1] && op.p[3] && op.p[4] && op.p[5], "guide_grad: bad args");
   int chunks = (int)std::min<int64_t>(ceil_div(3 * H * W, 256 * 4), std::max<int64_t>(1, 592 / B));
-  guide_grad_kernel<<<dim3(chunks, (unsigned)B), 256, 0, st>>>((const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2],
+  CGD_CUDA(launch_pdl(guide_grad_kernel, dim3(chunks, (unsigned)B), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2],
                                                               (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (float*)op.p[6], (int)B,
-                                                              (int)H, (int)W, ld, op.f[0], op.f[1], op.f[2], op.f[3]);
+                                                              (int)H, (int)W, ld, op.f[0], op.f[1], op.f[2], op.f[3]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -295,6 +306,8 @@ int launch_guide_grad(const CgdOp& op, cudaStream_t st) {
 constexpr int FG_BLOCKS = 128;
 __global__ void final_grad_kernel(const float* __restrict__ dxd, const float* __restrict__ dxu, float* __restrict__ g, int64_t n,
                                   float inv_scale, float* __restrict__ ws) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[32];
   float ssq = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -308,6 +321,8 @@ __global__ void final_grad_kernel(const float* __restrict__ dxd, const float* __
   if (threadIdx.x == 0 && ws) ws[blockIdx.x] = ssq;
 }
 __global__ void magnitude_clamp_kernel(float* __restrict__ g, int64_t n, const float* __restrict__ ws, int nparts, float max_rms) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float s_scale;
   if (threadIdx.x == 0) {
     double tot = 0.0;
@@ -325,10 +340,10 @@ int launch_final_grad(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(n > 0 && op.p[0] && op.p[2], "final_grad: bad args");
   const bool mag = op.flags & 1;
   if (mag) CGD_CHECK_ARG(op.p[3] != nullptr, "final_grad: magnitude clamp needs a %d-float workspace", FG_BLOCKS);
-  final_grad_kernel<<<FG_BLOCKS, 256, 0, st>>>((const float*)op.p[0], (const float*)op.p[1], (float*)op.p[2], n, op.f[0], (float*)op.p[3]);
+  CGD_CUDA(launch_pdl(final_grad_kernel, dim3(FG_BLOCKS), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (float*)op.p[2], n, op.f[0], (float*)op.p[3]));
   CGD_LAUNCH_CHECK();
   if (mag) {
-    magnitude_clamp_kernel<<<FG_BLOCKS, 256, 0, st>>>((float*)op.p[2], n, (const float*)op.p[3], FG_BLOCKS, op.f[1]);
+    CGD_CUDA(launch_pdl(magnitude_clamp_kernel, dim3(FG_BLOCKS), dim3(256), 0, st, (float*)op.p[2], n, (const float*)op.p[3], FG_BLOCKS, op.f[1]));
     CGD_LAUNCH_CHECK();
   }
   return 0;
@@ -338,6 +353,8 @@ int launch_final_grad(const CgdOp& op, cudaStream_t st) {
 __global__ void sample_ancestral_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ lv,
                                         const float* __restrict__ g, const float* __restrict__ noise, const float* __restrict__ sc,
                                         float* __restrict__ out, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   const float nz = sc[CGD_SC_NONZERO];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float m = mean[i];
@@ -347,6 +364,8 @@ __global__ void sample_ancestral_kernel(const float* __restrict__ mean, const fl
 }
 __global__ void sample_ddim_kernel(const float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ g,
                                    const float* __restrict__ noise, const float* __restrict__ sc, float* __restrict__ out, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   const float a = sc[CGD_SC_SQRT_RECIP_AC], bb = sc[CGD_SC_SQRT_RECIPM1_AC], s1m = sc[CGD_SC_SQRT_1M_AC];
   const float ac = sc[CGD_SC_AC], acp = sc[CGD_SC_AC_PREV], eta = sc[CGD_SC_ETA], nz = sc[CGD_SC_NONZERO];
   const float sigma = eta * sqrtf((1.f - acp) / (1.f - ac)) * sqrtf(1.f - ac / acp);
@@ -366,16 +385,16 @@ __global__ void sample_ddim_kernel(const float* __restrict__ x, const float* __r
 int launch_sample_ancestral(const CgdOp& op, cudaStream_t st) {
   const int64_t n = op.i[0];
   CGD_CHECK_ARG(n > 0 && op.p[0] && op.p[1] && op.p[2] && op.p[4] && op.p[5] && op.p[6], "sample_ancestral: bad args");
-  sample_ancestral_kernel<<<gw_blocks(n), 256, 0, st>>>((const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], (const float*)op.p[3],
-                                                       (const float*)op.p[4], (const float*)op.p[5], (float*)op.p[6], n);
+  CGD_CUDA(launch_pdl(sample_ancestral_kernel, dim3(gw_blocks(n)), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], (const float*)op.p[3],
+                                                       (const float*)op.p[4], (const float*)op.p[5], (float*)op.p[6], n));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 int launch_sample_ddim(const CgdOp& op, cudaStream_t st) {
   const int64_t n = op.i[0];
   CGD_CHECK_ARG(n > 0 && op.p[0] && op.p[1] && op.p[3] && op.p[4] && op.p[5], "sample_ddim: bad args");
-  sample_ddim_kernel<<<gw_blocks(n), 256, 0, st>>>((const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], (const float*)op.p[3],
-                                                  (const float*)op.p[4], (float*)op.p[5], n);
+  CGD_CUDA(launch_pdl(sample_ddim_kernel, dim3(gw_blocks(n)), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], (const float*)op.p[3],
+                                                  (const float*)op.p[4], (float*)op.p[5], n));
   CGD_LAUNCH_CHECK();
   return 0;
 }

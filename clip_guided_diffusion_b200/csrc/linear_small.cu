@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "pdl.cuh"
 #include "ops.cuh"
 
 namespace cgd {
@@ -16,6 +17,8 @@ constexpr int LS_MT = 8;  // rows of x per block
 template <typename XT>
 __global__ void linear_small_kernel(const XT* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias, void* __restrict__ y,
                                     int M, int K, int N, int64_t ldx, int64_t ldy, int silu_in, int accumulate, int y_half) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float xs[];  // [LS_MT][K]
   const int m0 = blockIdx.y * LS_MT, mt = min(LS_MT, M - m0);
   for (int i = threadIdx.x; i < mt * K; i += blockDim.x) {
@@ -72,13 +75,13 @@ int launch_linear_small(const CgdOp& op, cudaStream_t st) {
   if (xh) {
     static bool set = false;
     if (!set) { CGD_CUDA(cudaFuncSetAttribute(linear_small_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); set = true; }
-    linear_small_kernel<__half><<<grid, 256, smem, st>>>((const __half*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], op.p[3], (int)M, (int)K,
-                                                        (int)N, ldx, ldy, silu, acc, yh);
+    CGD_CUDA(launch_pdl(linear_small_kernel<__half>, dim3(grid), dim3(256), smem, st, (const __half*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], op.p[3], (int)M, (int)K,
+                                                        (int)N, ldx, ldy, silu, acc, yh));
   } else {
     static bool set = false;
     if (!set) { CGD_CUDA(cudaFuncSetAttribute(linear_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); set = true; }
-    linear_small_kernel<float><<<grid, 256, smem, st>>>((const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], op.p[3], (int)M, (int)K,
-                                                       (int)N, ldx, ldy, silu, acc, yh);
+    CGD_CUDA(launch_pdl(linear_small_kernel<float>, dim3(grid), dim3(256), smem, st, (const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], op.p[3], (int)M, (int)K,
+                                                       (int)N, ldx, ldy, silu, acc, yh));
   }
   CGD_LAUNCH_CHECK();
   return 0;

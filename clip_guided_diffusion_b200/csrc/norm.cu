@@ -6,6 +6,7 @@
 // (per-chunk partials combined in a fixed order by the last block to finish, no float atomics in
 // global memory), 128-bit vectorised and coalesced along the channel dimension.
 #include "common.cuh"
+#include "pdl.cuh"
 #include "ops.cuh"
 
 namespace cgd {
@@ -95,6 +96,8 @@ __device__ __forceinline__ void fold_partials(const float* part, int nchunk, dou
 // pass 1: per-(image, chunk, group) sum and sum of squares; last block per image folds the chunks.
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partials, float* __restrict__ stats,
                                 unsigned int* __restrict__ counters, int HW, int C, int64_t ld, int nchunk, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float gs[32], gq[32];
   __shared__ float red_s[2048], red_q[2048];
   __shared__ double fold_s[32], fold_q[32];
@@ -178,6 +181,8 @@ __device__ __forceinline__ void gn_coeffs(const float* stats, const float* gamma
 __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ emb, __half* __restrict__ y, int HW,
                                 int C, int64_t ldx, int64_t ldy, int silu) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int n = blockIdx.y;
   const int V = C / 8, col = threadIdx.x % V, pl = threadIdx.x / V, PP = blockDim.x / V;
   float A[8], Bc[8], G[8], mu[8], rs[8];
@@ -211,6 +216,8 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
                                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ emb,
                                     float* __restrict__ partials, float* __restrict__ sums, unsigned int* __restrict__ counters,
                                     int HW, int C, int64_t ld_dy, int64_t ldx, int nchunk, int silu) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float gs[32], gq[32];
   __shared__ float red_s[2048], red_q[2048];
   __shared__ double fold_s[32], fold_q[32];
@@ -281,6 +288,8 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ dy, const __half*
                                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ emb,
                                     const float* __restrict__ sums, __half* __restrict__ dx, int HW, int C, int64_t ld_dy,
                                     int64_t ldx, int64_t ld_dx, int silu, int accumulate) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int n = blockIdx.y;
   const int V = C / 8, col = threadIdx.x % V, pl = threadIdx.x / V, PP = blockDim.x / V;
   const int cpg = C / 32;
@@ -345,8 +354,8 @@ int launch_gn_stats(const CgdOp& op, cudaStream_t st) {
   if (int rc = gn_check(op, C, HW, N)) return rc;
   CGD_CHECK_ARG(nchunk >= 1 && ld % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[3], "gn_stats: bad args");
   const GnGeom g = gn_geom((int)C);
-  gn_stats_kernel<<<dim3((unsigned)nchunk, (unsigned)N), g.threads, 0, st>>>(
-      (const __half*)op.p[0], (float*)op.p[1], (float*)op.p[2], (unsigned int*)op.p[3], (int)HW, (int)C, ld, (int)nchunk, op.f[0]);
+  CGD_CUDA(launch_pdl(gn_stats_kernel, dim3((unsigned)nchunk, (unsigned)N), dim3(g.threads), 0, st, 
+      (const __half*)op.p[0], (float*)op.p[1], (float*)op.p[2], (unsigned int*)op.p[3], (int)HW, (int)C, ld, (int)nchunk, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -356,9 +365,9 @@ int launch_gn_apply(const CgdOp& op, cudaStream_t st) {
   if (int rc = gn_check(op, C, HW, N)) return rc;
   CGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[3] && op.p[5], "gn_apply: bad args");
   const GnGeom g = gn_geom((int)C);
-  gn_apply_kernel<<<dim3(gn_apply_chunks(HW, N, g.PP), (unsigned)N), g.threads, 0, st>>>(
+  CGD_CUDA(launch_pdl(gn_apply_kernel, dim3(gn_apply_chunks(HW, N, g.PP), (unsigned)N), dim3(g.threads), 0, st, 
       (const __half*)op.p[0], (const float*)op.p[1], (const float*)op.p[2], (const float*)op.p[3], (const float*)op.p[4],
-      (__half*)op.p[5], (int)HW, (int)C, ldx, ldy, op.flags & 1);
+      (__half*)op.p[5], (int)HW, (int)C, ldx, ldy, op.flags & 1));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -369,10 +378,10 @@ int launch_gn_bwd_stats(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(nchunk >= 1 && ld_dy % 8 == 0 && ldx % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[6] && op.p[7] && op.p[8],
                 "gn_bwd_stats: bad args");
   const GnGeom g = gn_geom((int)C);
-  gn_bwd_stats_kernel<<<dim3((unsigned)nchunk, (unsigned)N), g.threads, 0, st>>>(
+  CGD_CUDA(launch_pdl(gn_bwd_stats_kernel, dim3((unsigned)nchunk, (unsigned)N), dim3(g.threads), 0, st, 
       (const __half*)op.p[0], (const __half*)op.p[1], (const float*)op.p[2], (const float*)op.p[3], (const float*)op.p[4],
       (const float*)op.p[5], (float*)op.p[6], (float*)op.p[7], (unsigned int*)op.p[8], (int)HW, (int)C, ld_dy, ldx, (int)nchunk,
-      op.flags & 1);
+      op.flags & 1));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -383,10 +392,10 @@ int launch_gn_bwd_apply(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(ld_dy % 8 == 0 && ldx % 8 == 0 && ld_dx % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[6] && op.p[7],
                 "gn_bwd_apply: bad args");
   const GnGeom g = gn_geom((int)C);
-  gn_bwd_apply_kernel<<<dim3(gn_apply_chunks(HW, N, g.PP), (unsigned)N), g.threads, 0, st>>>(
+  CGD_CUDA(launch_pdl(gn_bwd_apply_kernel, dim3(gn_apply_chunks(HW, N, g.PP), (unsigned)N), dim3(g.threads), 0, st, 
       (const __half*)op.p[0], (const __half*)op.p[1], (const float*)op.p[2], (const float*)op.p[3], (const float*)op.p[4],
       (const float*)op.p[5], (const float*)op.p[6], (__half*)op.p[7], (int)HW, (int)C, ld_dy, ldx, ld_dx, op.flags & 1,
-      (op.flags & 2) ? 1 : 0);
+      (op.flags & 2) ? 1 : 0));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -397,6 +406,8 @@ constexpr int LN_MAXV = 8;  // 8 vectors of 8 halves per lane -> w <= 2048
 
 __global__ void ln_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                               __half* __restrict__ y, float* __restrict__ stats, int rows, int w, int64_t ldx, int64_t ldy, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nv = w / 8;
@@ -444,6 +455,8 @@ __global__ void ln_fwd_kernel(const __half* __restrict__ x, const float* __restr
 __global__ void ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const float* __restrict__ gamma,
                               const float* __restrict__ stats, __half* __restrict__ dx, int rows, int w, int64_t ld_dy, int64_t ldx,
                               int64_t ld_dx, int accumulate) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nv = w / 8;
@@ -489,8 +502,8 @@ int launch_ln_fwd(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(rows > 0 && w % 8 == 0 && w <= 8 * 32 * LN_MAXV && ldx % 8 == 0 && ldy % 8 == 0, "layernorm: unsupported shape rows=%lld w=%lld",
                 (long long)rows, (long long)w);
   CGD_CHECK_ARG(op.p[0] && op.p[1] && op.p[2] && op.p[3], "layernorm: null pointer");
-  ln_fwd_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>((const __half*)op.p[0], (const float*)op.p[1], (const float*)op.p[2],
-                                                           (__half*)op.p[3], (float*)op.p[4], (int)rows, (int)w, ldx, ldy, op.f[0]);
+  CGD_CUDA(launch_pdl(ln_fwd_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, st, (const __half*)op.p[0], (const float*)op.p[1], (const float*)op.p[2],
+                                                           (__half*)op.p[3], (float*)op.p[4], (int)rows, (int)w, ldx, ldy, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -499,9 +512,9 @@ int launch_ln_bwd(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(rows > 0 && w % 8 == 0 && w <= 8 * 32 * LN_MAXV && ld_dy % 8 == 0 && ldx % 8 == 0 && ld_dx % 8 == 0,
                 "layernorm bwd: unsupported shape");
   CGD_CHECK_ARG(op.p[0] && op.p[1] && op.p[2] && op.p[3] && op.p[4], "layernorm bwd: null pointer");
-  ln_bwd_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>((const __half*)op.p[0], (const __half*)op.p[1], (const float*)op.p[2],
+  CGD_CUDA(launch_pdl(ln_bwd_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, st, (const __half*)op.p[0], (const __half*)op.p[1], (const float*)op.p[2],
                                                            (const float*)op.p[3], (__half*)op.p[4], (int)rows, (int)w, ld_dy, ldx,
-                                                           ld_dx, (op.flags & 2) ? 1 : 0);
+                                                           ld_dx, (op.flags & 2) ? 1 : 0));
   CGD_LAUNCH_CHECK();
   return 0;
 }
