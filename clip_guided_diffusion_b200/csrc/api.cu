@@ -56,6 +56,8 @@ static int dispatch(const CgdOp& op, const ConvTcLaunch* conv, cudaStream_t st) 
     case CGD_OP_SOFTMAX_BWD: return launch_softmax_bwd(op, st);
     case CGD_OP_GN_FWD_FUSED: return launch_gn_fwd_fused(op, st);
     case CGD_OP_GN_BWD_FUSED: return launch_gn_bwd_fused(op, st);
+    case CGD_OP_GN_FWD_GRID: return launch_gn_fwd_grid(op, st);
+    case CGD_OP_GN_BWD_GRID: return launch_gn_bwd_grid(op, st);
     case CGD_OP_LINEAR_SMALL: return launch_linear_small(op, st);
     case CGD_OP_TIMESTEP_EMB: return launch_timestep_emb(op, st);
     case CGD_OP_LABEL_ADD: return launch_label_add(op, st);

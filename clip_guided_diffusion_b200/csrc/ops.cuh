@@ -11,6 +11,8 @@ int launch_gn_bwd_stats(const CgdOp& op, cudaStream_t st);
 int launch_gn_bwd_apply(const CgdOp& op, cudaStream_t st);
 int launch_gn_fwd_fused(const CgdOp& op, cudaStream_t st);
 int launch_gn_bwd_fused(const CgdOp& op, cudaStream_t st);
+int launch_gn_fwd_grid(const CgdOp& op, cudaStream_t st);
+int launch_gn_bwd_grid(const CgdOp& op, cudaStream_t st);
 int launch_ln_fwd(const CgdOp& op, cudaStream_t st);
 int launch_ln_bwd(const CgdOp& op, cudaStream_t st);
 int launch_pool2(const CgdOp& op, cudaStream_t st);

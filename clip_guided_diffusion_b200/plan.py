@@ -78,15 +78,22 @@ def _round_up(a, b):
     return (a + b - 1) // b * b
 
 
-def pick_bn(npad: int, m_tiles: int) -> int:
+def pick_bn(npad: int, m_tiles: int, kblocks: int = 1 << 30) -> int:
     """Output-channel tile width.  The CTA-pair kernel runs ceil(tiles / 74) rounds of 74 clusters (148 SMs); wide tiles
     amortise the A-operand traffic and the per-tile epilogue, narrow ones fill the machine: maximise utilisation x a
-    per-width efficiency prior (measured ordering on B200: 256 > 192 > 128 > 64)."""
+    per-width efficiency prior (measured ordering on B200: 256 > 192 > 128 > 64).
+    Short-K GEMMs (<= 16 K-blocks: 1x1 convs, the ViT's K = 768 Linears) that fit one round are latency-bound, not
+    tensor-bound: the narrowest tile that still fits one round wins and split-K (a second launch) never pays
+    (profiles/r01_conv_sweep_v1.txt: 768->768 at M = 800 runs 7.7 us with BN 64 against 17.2 us with BN 256 + split 2)."""
     cands = [b for b in (256, 192, 128, 64, 32, 16) if npad % b == 0]
     big = [b for b in cands if b >= 64]
     if not big:
         return cands[0]
     pair_tiles = (m_tiles + 1) // 2
+    if kblocks <= 16:
+        one_round = [b for b in big if pair_tiles * (npad // b) <= 74]
+        if one_round:
+            return min(one_round)
     eff = {256: 1.0, 192: 0.95, 128: 0.85, 64: 0.6}
     best, best_score = big[0], -1.0
     for b in big:
@@ -118,7 +125,7 @@ def pick_splits(m_tiles, n_tiles, kblocks, npad, ws_cap_bytes=16 << 20) -> int:
     6 K-blocks (of 64) per tile so the TMA/MMA pipeline amortises its fill, bound the fp32 partial workspace."""
     tiles = ((m_tiles + 1) // 2) * n_tiles if m_tiles >= 2 else m_tiles * n_tiles
     slots = 74 if m_tiles >= 2 else 148
-    if tiles * 2 > slots or kblocks < 12:
+    if tiles * 2 > slots or kblocks <= 16:
         return 1
     s = min(kblocks // 6, slots // tiles, 32)
     cap = ws_cap_bytes // (((m_tiles + 1) // 2 * 2) * 128 * npad * 4)
@@ -129,26 +136,41 @@ def pick_splits(m_tiles, n_tiles, kblocks, npad, ws_cap_bytes=16 << 20) -> int:
 
 def gn_fused_cluster(N: int, HW: int, C: int, maxv: int) -> int:
     """Cluster size (CTAs along the pixel dimension) of the single-launch GroupNorm kernels (csrc/norm_fused.cu), or 0 when the
-    (image, group) slab does not fit: 512 threads, 16-byte vectors, at most `maxv` vectors per thread (16 forward, 8 backward),
-    clusters of at most 8 CTAs.  Beyond the minimum, the cluster grows until the grid has ~one CTA per SM."""
-    if C % 256 != 0 or C > 4096:
+    two-pass kernels are the better choice.  512 threads, 16-byte vectors, at most `maxv` vectors per thread (16 forward,
+    8 backward), clusters of at most 4 CTAs.  Measured on B200 (profiles/r01_gn_microbench_v1.txt): a CTA reads only its groups'
+    channels of every pixel (32-128 contiguous bytes), so beyond ~4 MB per image the partial-line traffic loses against the
+    full-row two-pass kernels; below, the single launch wins by 2-4x."""
+    if C % 256 != 0 or C > 4096 or HW * C > (2 << 20):
         return 0
     cpg = C // 32
     gpc = 16 // cpg if cpg < 16 else 1
     vpp = gpc * cpg // 8
     pp = 512 // vpp
     cs = 1
-    while cs <= 8 and -(-HW // cs) > maxv * pp:
+    while cs <= 4 and -(-HW // cs) > maxv * pp:
         cs *= 2
-    if cs > 8:
+    if cs > 4:
         return 0
-    while cs < 8 and (32 // gpc) * cs * N < 128 and -(-HW // (2 * cs)) >= pp:
+    while cs < 4 and (32 // gpc) * cs * N < 128 and -(-HW // (2 * cs)) >= pp:
         cs *= 2
     return cs
 
 
+N_SMS = 148  # B200
+
+
+def gn_grid_ctas(N: int, HW: int, C: int) -> int:
+    """CTAs per image of the persistent GroupNorm kernels (csrc/norm_grid.cu): one 512-thread CTA per SM, every CTA at least
+    one pass of its pixel lanes; 0 when the batch alone exceeds the SM count (two-pass kernels then)."""
+    if C % 64 != 0 or C > 2048 or N > N_SMS:
+        return 0
+    pp = 512 // (C // 8)
+    return max(1, min(N_SMS // N, HW // pp))
+
+
 class Plan:
     def __init__(self, conv_impl: int = 0):
+        self.grid_gn = True  # single persistent launch with a grid barrier for the large GroupNorms (csrc/norm_grid.cu)
         self.fused_gn = True  # single-launch GroupNorm where the slab fits a cluster (csrc/norm_fused.cu)
         self.ops: list[PlanOp] = []
         self._size = 0
@@ -237,8 +259,8 @@ class Plan:
         """b_ptr / b_batch / ldb: batched-GEMM mode (attention): the B operand is a strided activation matrix selected by the
         tile's (h, n) instead of a packed weight."""
         m_tiles = conv_tile_count(NB, H, W)
-        bn = pick_bn(npad, m_tiles)
         kblocks = taps * Cin // 64
+        bn = pick_bn(npad, m_tiles, kblocks)
         splits = pick_splits(m_tiles, npad // bn, kblocks, npad)
         ws = self.new(splits * ((m_tiles + 1) // 2 * 2) * 128 * npad, "f", "splitk_ws") if splits > 1 else None
         i = [NB, H, W, Cin, Cout, npad, taps, *x_strides, *out_strides, *(res_strides or (0, 0, 0)), bn, splits, self.conv_impl, out_sc,
@@ -284,9 +306,15 @@ class Plan:
         stats = self.new(N * 64, "f", name + "_stats")
         embp = self._bp(emb[0], emb[1]) if emb is not None else None
         cs_f = gn_fused_cluster(N, HW, C, 16) if self.fused_gn else 0
+        gn_g = gn_grid_ctas(N, HW, C) if self.grid_gn else 0
         if cs_f:
             self.emit("GN_FWD_FUSED", flags=1 if silu else 0, i=[N, HW, C, x.ld, y.ld, cs_f], f=[eps],
                       p=[self._ap(x), self._bp(gamma), self._bp(beta), embp, self._ap(y), self._bp(stats)], tag=name)
+        elif gn_g:
+            partials = self.new(N * gn_g * 64, "f", name + "_part")
+            bar = self.new(2, "u32", name + "_bar")
+            self.emit("GN_FWD_GRID", flags=1 if silu else 0, i=[N, HW, C, x.ld, y.ld, gn_g], f=[eps],
+                      p=[self._ap(x), self._bp(gamma), self._bp(beta), embp, self._ap(y), self._bp(stats), self._bp(partials), self._bp(bar)], tag=name)
         else:
             pp = max(1, 256 // (C // 8))
             nchunk = int(min(max(1, -(-HW // (pp * 16))), max(1, 296 // N)))
@@ -307,6 +335,11 @@ class Plan:
             fl = (1 if silu else 0) | (2 if has else 0)
             if cs_b:
                 self.emit("GN_BWD_FUSED", flags=fl, i=[N, HW, C, dy.ld, x.ld, dx.ld, cs_b], f=[eps], p=common + [self._ap(dx)], tag="d_" + name)
+            elif gn_g:
+                bpart = self.new(N * gn_g * 64, "f", name + "_bpart")
+                bbar = self.new(2, "u32", name + "_bbar")
+                self.emit("GN_BWD_GRID", flags=fl, i=[N, HW, C, dy.ld, x.ld, dx.ld, gn_g], f=[eps],
+                          p=common + [self._ap(dx), self._bp(bpart), self._bp(bbar)], tag="d_" + name)
             else:
                 pp = max(1, 256 // (C // 8))
                 nchunk = int(min(max(1, -(-HW // (pp * 16))), max(1, 296 // N)))

@@ -172,6 +172,14 @@ enum {
    * p0 dy p1 x p2 stats p3 gamma p4 beta p5 emb|0 p6 dx(h) ; i0 N i1 HW i2 C i3 ld_dy i4 ldx i5 ld_dx i6 CS
    * flags 1 = SiLU, 2 = accumulate into dx */
   CGD_OP_GN_BWD_FUSED = 34,
+  /* single persistent launch for LARGE activations: statistics pass, grid-wide barrier (generation counted, no reset needed),
+   * apply pass over the same pixel range (L2 hit).  One 512-thread CTA per SM: N * Gn must not exceed the SM count.
+   * p0 x(h) p1 gamma p2 beta p3 emb|0 p4 y(h) p5 stats(f [N,32,2]) p6 partials(f [N,Gn,32,2]) p7 barrier(u32 [2], zero-initialised)
+   * i0 N i1 HW i2 C i3 ldx i4 ldy i5 Gn (CTAs per image) ; f0 eps ; flags 1 = SiLU.  C % 64 == 0 */
+  CGD_OP_GN_FWD_GRID = 35,
+  /* backward of the above: p0 dy p1 x p2 stats p3 gamma p4 beta p5 emb|0 p6 dx(h) p7 partials p8 barrier
+   * i0 N i1 HW i2 C i3 ld_dy i4 ldx i5 ld_dx i6 Gn ; flags 1 = SiLU, 2 = accumulate into dx */
+  CGD_OP_GN_BWD_GRID = 36,
   CGD_OP__COUNT
 };
 

@@ -160,6 +160,12 @@ class Interp:
             v = F.silu(v)
         self.V(op.p[4], (N, HW, C), (HW * ldy, ldy, 1)).copy_(v)
 
+    def op_GN_FWD_GRID(self, op):
+        self.op_GN_FWD_FUSED(op)
+
+    def op_GN_BWD_GRID(self, op):
+        self.op_GN_BWD_FUSED(op)
+
     def op_GN_BWD_FUSED(self, op):
         N, HW, C, dxh, xh, rstd = self._gn_bwd_common(op)
         cpg = C // 32

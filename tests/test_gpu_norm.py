@@ -25,7 +25,9 @@ CASES = [
     (1, 16384, 512, False, True),
     (1, 16384, 768, False, True),   # backward slab too large -> two-pass backward, fused forward
     (1, 900, 256, True, True),      # ragged pixel count
-    (1, 65536, 256, True, True),    # two-pass only
+    (1, 65536, 256, True, True),    # persistent grid kernel (or two-pass)
+    (2, 4096, 192, True, True),     # C = 192: groups straddle the 8-channel vectors (64x64 checkpoint widths)
+    (3, 1024, 64, False, True),
 ]
 
 
@@ -37,13 +39,14 @@ def _ref(x, gamma, beta, emb, silu, eps=1e-5):
     return F.silu(h) if silu else h
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["fused", "twopass"])
+@pytest.mark.parametrize("fused", ["auto", "grid", "twopass"])
 @pytest.mark.parametrize("case", CASES, ids=[f"n{c[0]}_hw{c[1]}_c{c[2]}{'_emb' if c[3] else ''}{'' if c[4] else '_nosilu'}" for c in CASES])
 def test_group_norm_fwd_bwd(case, fused):
     N, HW, C, has_emb, silu = case
     th.manual_seed(0)
     plan = Plan()
-    plan.fused_gn = fused
+    plan.fused_gn = fused == "auto"      # cluster kernel where the slab fits, else the persistent grid kernel
+    plan.grid_gn = fused != "twopass"
     gamma = 1 + 0.2 * th.randn(C)
     beta = 0.1 * th.randn(C)
     emb = 0.3 * th.randn(N, 2 * C) if has_emb else None
@@ -60,10 +63,13 @@ def test_group_norm_fwd_bwd(case, fused):
     plan.finalize("cuda")
     codes = [op.tag for op in plan.ops]
     n_fused = sum(1 for op in plan.ops if op.code in (33, 34))
-    if fused and gn_fused_cluster(N, HW, C, 16):
+    n_grid = sum(1 for op in plan.ops if op.code in (35, 36))
+    if fused == "auto" and gn_fused_cluster(N, HW, C, 16):
         assert n_fused >= 2, codes
-    if not fused:
-        assert n_fused == 0
+    if fused == "grid":
+        assert n_fused == 0 and n_grid == 4, codes
+    if fused == "twopass":
+        assert n_fused == 0 and n_grid == 0
     xv = plan.view(x.buf, (N, HW, C))
     xv.copy_(th.randn(N, HW, C) * 1.5 + 0.3 * th.randn(N, 1, C))
     d1 = plan.view(dy1.buf, (N, HW, C)).normal_()
@@ -86,14 +92,15 @@ def test_group_norm_fwd_bwd(case, fused):
     assert th.isfinite(dx).all() and err < 3e-3, f"dx fused={fused}: rel-to-max {err:.3e}"
 
 
-def test_fused_matches_twopass_statistics():
-    """Both paths must hand the same (mean, rstd) to the backward."""
+def test_all_paths_agree_on_statistics():
+    """Cluster, grid and two-pass kernels must hand the same (mean, rstd) to the backward."""
     N, HW, C = 2, 1024, 512
     outs = []
-    for fused in (True, False):
+    for mode in ("fused", "grid", "twopass"):
         th.manual_seed(1)
         plan = Plan()
-        plan.fused_gn = fused
+        plan.fused_gn = mode == "fused"
+        plan.grid_gn = mode == "grid"
         gb, bb = plan.const(th.ones(C), "f", "g"), plan.const(th.zeros(C), "f", "b")
         x = plan.act(N, 1, HW, C, "x")
         plan.group_norm(x, gb, bb, silu=False, name="gn")
@@ -103,4 +110,5 @@ def test_fused_matches_twopass_statistics():
         th.cuda.synchronize()
         st = [b for b in plan.bufs if b.name == "gn_stats"][0]
         outs.append(plan.view(st, (N, 32, 2)).clone())
-    assert th.allclose(outs[0], outs[1], rtol=2e-5, atol=2e-6), float((outs[0] - outs[1]).abs().max())
+    assert th.allclose(outs[0], outs[2], rtol=2e-5, atol=2e-6), float((outs[0] - outs[2]).abs().max())
+    assert th.allclose(outs[1], outs[2], rtol=2e-5, atol=2e-6), float((outs[1] - outs[2]).abs().max())
