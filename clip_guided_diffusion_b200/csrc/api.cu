@@ -83,7 +83,7 @@ static int dispatch(const CgdOp& op, const ConvTcLaunch* conv, cudaStream_t st) 
 static int op_launches(const CgdOp& op, const ConvTcLaunch* conv) {
   switch (op.code) {
     case CGD_OP_CONV: return conv_tc_num_launches(*conv);
-    case CGD_OP_ATTN_BWD: return 3;
+    case CGD_OP_ATTN_BWD: return attn_bwd_num_launches(op);
     case CGD_OP_FINAL_GRAD: return (op.flags & 1) ? 2 : 1;
     default: return 1;
   }

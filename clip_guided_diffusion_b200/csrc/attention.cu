@@ -6,6 +6,8 @@
 // operands staged through shared memory, online softmax, nothing T x T ever touches HBM).  The q/k/v
 // operands are addressed by (batch, row, head) strides so both the legacy per-head [q|k|v] interleave and the
 // [q..|k..|v..] order read straight out of the fused qkv GEMM output.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "pdl.cuh"
 #include "ops.cuh"
@@ -324,9 +326,24 @@ static int attn_args(const CgdOp& op, AttnArgs& a, bool bwd) {
   return 0;
 }
 
+int attn_small_supported(int64_t T);                            // attention_small.cu: one 64-key tile per head on warp MMAs
+int launch_attn_small_fwd(const CgdOp& op, cudaStream_t st);
+int launch_attn_small_bwd(const CgdOp& op, cudaStream_t st);
+static bool attn_use_small(int64_t T) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("CGD_ATTN_SMALL");
+    off = (e && e[0] == '0') ? 1 : 0;
+  }
+  return !off && attn_small_supported(T);
+}
+
+int attn_bwd_num_launches(const CgdOp& op) { return attn_use_small(op.i[2]) ? 1 : 3; }
+
 int launch_attn_fwd(const CgdOp& op, cudaStream_t st) {
   AttnArgs a{};
   if (int rc = attn_args(op, a, false)) return rc;
+  if (attn_use_small(a.T)) return launch_attn_small_fwd(op, st);
   const int smem = 4 * AT * ALD * (int)sizeof(float);
   static bool set = false;
   if (!set) {
@@ -341,6 +358,7 @@ int launch_attn_fwd(const CgdOp& op, cudaStream_t st) {
 int launch_attn_bwd(const CgdOp& op, cudaStream_t st) {
   AttnArgs a{};
   if (int rc = attn_args(op, a, true)) return rc;
+  if (attn_use_small(a.T)) return launch_attn_small_bwd(op, st);
   const int smem_kv = 8 * AT * ALD * (int)sizeof(float), smem_q = 6 * AT * ALD * (int)sizeof(float);
   static bool set = false;
   if (!set) {

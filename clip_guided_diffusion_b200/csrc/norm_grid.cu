@@ -1,33 +1,42 @@
 // norm_grid.cu -- GroupNorm(32) (+SiLU, +scale/shift) forward and input-gradient for LARGE activations as ONE persistent
-// launch: statistics pass, grid-wide barrier, apply pass.
+// launch: statistics pass, grid-wide barrier, apply pass, both passes fed by a bulk-async-copy (TMA) ring.
 //
-// Why (measured on B200, profiles/r01_gn_microbench_v1.txt): at the 128x128 / 256x256 levels the two-launch kernels of norm.cu
-// reach 0.9 - 1.7 TB/s of the 6.5 TB/s copy bandwidth -- two blocks of 256 threads per SM keep ~5 MB in flight, the grids end
-// in half-empty waves, and the second launch waits for a last-block fold.  Here one CTA per SM (512 threads, 8 independent
-// 128-bit loads per thread in flight = 9.7 MB over the chip) owns a contiguous pixel range of one image across ALL channels
-// (full 128-byte lines), writes its per-group partial sums, meets the other CTAs at a generation-counted grid barrier (every
-// CTA is resident: grid <= SM count, one CTA per SM), folds the partials itself (fixed order, fp64: bit-identical in every
-// CTA) and applies the normalisation to the same pixel range, whose second read is an L2 hit (the tensors are 8 - 67 MB,
-// the L2 is 126 MB).  HBM traffic: x once + y once (forward), dy + x once + dx (backward).
+// Why (measured on B200, profiles/r01_gn_microbench_v1/v2.txt): at the 128x128 / 256x256 levels the two-launch kernels of
+// norm.cu reach 0.9 - 1.7 TB/s of the 6.5 TB/s copy bandwidth (two blocks of 256 threads per SM keep ~5 MB in flight, the grids
+// end in half-empty waves, the second launch waits for a last-block fold), and a first single-launch version whose threads
+// loaded 8 x 16 B each stopped at 2 TB/s: the bytes in flight were bounded by registers.  Here one CTA per SM owns a
+// contiguous pixel range of one image across ALL channels; a producer warp streams it through an 8-stage shared-memory
+// ring with cp.async.bulk (16 KB per stage, 128 KB in flight per SM = 19 MB over the chip, independent of the consumers'
+// registers); 512 consumer threads reduce each stage from shared memory, write per-group partial sums, meet the other CTAs
+// at a generation-counted grid barrier (every CTA is resident: grid <= SM count, one CTA per SM), fold the partials
+// themselves (fixed order, fp64: bit-identical in every CTA) and normalise the same pixel range from a second trip through
+// the ring, whose loads are L2 hits (the tensors are 8 - 67 MB, the L2 is 126 MB) and start while the barrier is still
+// being crossed.  HBM traffic: x once + y once (forward), dy + x once + dx (backward).
 //
 // Replaces [3P] guided-diffusion GroupNorm32 + SiLU + scale-shift and their autograd.
 #include "common.cuh"
 #include "ops.cuh"
 #include "pdl.cuh"
+#include "tc_ptx.cuh"
 
 namespace cgd {
 
-constexpr int kGngThreads = 512;
-constexpr int kGngUnroll = 8;
+constexpr int kGngConsumers = 512;             // warps 0..15
+constexpr int kGngThreads = kGngConsumers + 32; // + producer warp 16
+constexpr int kGngStages = 8;
+constexpr int kGngStageBytes = 16384;          // upper bound; the used part is NT * R * C * 2
+constexpr int kGngBarId = 1;                   // named barrier of the consumer threads
 
-// Generation-counted barrier over all CTAs of the grid.  bar[0] = arrival count (returns to 0), bar[1] = generation (only
-// ever incremented), so the buffer needs no reset between launches or CUDA-graph replays.
+__device__ __forceinline__ void gng_sync() { named_bar_sync(kGngBarId, kGngConsumers); }
+
+// Generation-counted barrier over all CTAs of the grid (consumer threads only).  bar[0] = arrival count (returns to 0),
+// bar[1] = generation (only ever incremented), so the buffer needs no reset between launches or CUDA-graph replays.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
-  __syncthreads();
+  gng_sync();
   if (threadIdx.x == 0) {
     volatile unsigned int* vgen = bar + 1;
     const unsigned int gen = *vgen;  // read before arriving: the generation cannot advance until this CTA has arrived
-    __threadfence();                 // cumulative: publishes the partials written by this CTA's other threads (bar.sync above)
+    __threadfence();                 // cumulative: publishes the partials written by this CTA's other threads (barrier above)
     if (atomicAdd(bar, 1u) == nblocks - 1u) {
       atomicExch(bar, 0u);
       __threadfence();
@@ -37,14 +46,14 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nbl
     }
     __threadfence();
   }
-  __syncthreads();
+  gng_sync();
 }
 
 // 8 channel sums per thread -> 32 group sums of this CTA.  Shared layout [pixel lane][channel]; thread (g = t/16, part = t%16)
 // adds elements part, part+16, ... of group g's PP * cpg values, then the 16 parts are folded by shuffles (fixed order).
 __device__ __forceinline__ void gng_block_reduce(const float* s, const float* q, int C, int col, int pl, int PP, bool active,
                                                  float* red_s, float* red_q, float* gs, float* gq) {
-  __syncthreads();
+  gng_sync();
   if (active) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -52,7 +61,7 @@ __device__ __forceinline__ void gng_block_reduce(const float* s, const float* q,
       red_q[pl * C + col * 8 + j] = q[j];
     }
   }
-  __syncthreads();
+  gng_sync();
   const int cpg = C / 32, g = threadIdx.x >> 4, part = threadIdx.x & 15;
   float as = 0.f, aq = 0.f;
   const int n = PP * cpg;
@@ -70,7 +79,7 @@ __device__ __forceinline__ void gng_block_reduce(const float* s, const float* q,
     gs[g] = as;
     gq[g] = aq;
   }
-  __syncthreads();
+  gng_sync();
 }
 
 // Fold the Gn per-CTA partials of image n (layout [Gn][32][2]) in a fixed order, fp64: thread (g, part) takes CTAs part,
@@ -92,18 +101,87 @@ __device__ __forceinline__ void gng_fold(const float* part_n, int Gn, double* ou
     out_a[g] = da;
     out_b[g] = db;
   }
-  __syncthreads();
+  gng_sync();
 }
 
-struct GngGeom {
-  int V, PP, threads;
+// ---- the ring: NT tensors (1: x; 2: dy, x), R pixel rows of C channels per stage and tensor
+struct GngRing {
+  uint8_t* buf;
+  uint64_t *full, *empty;
+  int R, row_bytes, tensor_bytes;  // rows per stage, C * 2, R * C * 2
 };
-__host__ __device__ inline GngGeom gng_geom(int C) {
-  GngGeom g;
-  g.V = C / 8;
-  g.PP = kGngThreads / g.V;
-  g.threads = kGngThreads;
-  return g;
+
+// Producer warp: `passes` trips over pixels [p0, p1) of the NT source tensors (row strides ld[t] elements).
+template <int NT>
+__device__ __forceinline__ void gng_produce(const GngRing& rg, const __half* const (&src)[NT], const int64_t (&ld)[NT], int C, int p0, int p1,
+                                            int passes) {
+  const int lane = threadIdx.x & 31;
+  const int n_it = (p1 - p0 + rg.R - 1) / rg.R;
+  uint32_t cnt = 0;
+  for (int pass = 0; pass < passes; ++pass) {
+    for (int it = 0; it < n_it; ++it, ++cnt) {
+      const int stage = cnt % kGngStages;
+      const uint32_t parity = (cnt / kGngStages) & 1u;
+      if (lane == 0) mbar_wait(&rg.empty[stage], parity ^ 1u);
+      __syncwarp();
+      const int p = p0 + it * rg.R;
+      const int rows = min(rg.R, p1 - p);
+      if (lane == 0) mbar_expect_tx(&rg.full[stage], (uint32_t)(NT * rows * rg.row_bytes));
+      __syncwarp();
+      uint8_t* dst = rg.buf + stage * kGngStageBytes;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (ld[t] == C) {  // the pixel range is one contiguous block
+          if (lane == t) bulk_load_1d(dst + t * rg.tensor_bytes, src[t] + (int64_t)p * C, (uint32_t)(rows * rg.row_bytes), &rg.full[stage]);
+        } else {           // channel slice of a wider tensor: one copy per pixel row
+          for (int r = lane; r < rows; r += 32)
+            bulk_load_1d(dst + t * rg.tensor_bytes + r * rg.row_bytes, src[t] + (int64_t)(p + r) * ld[t], (uint32_t)rg.row_bytes, &rg.full[stage]);
+        }
+      }
+    }
+  }
+}
+
+// Consumer side of one trip: f(p, v[NT]) for every (pixel row p, 8-channel vector) this thread owns.
+template <int NT, typename F>
+__device__ __forceinline__ void gng_consume(const GngRing& rg, uint32_t& cnt, int p0, int p1, int col, int pl, int PP, bool active, F&& f) {
+  const int lane = threadIdx.x & 31;
+  const int n_it = (p1 - p0 + rg.R - 1) / rg.R;
+  for (int it = 0; it < n_it; ++it, ++cnt) {
+    const int stage = cnt % kGngStages;
+    const uint32_t parity = (cnt / kGngStages) & 1u;
+    mbar_wait(&rg.full[stage], parity);
+    const int p = p0 + it * rg.R;
+    const int rows = min(rg.R, p1 - p);
+    const uint8_t* base = rg.buf + stage * kGngStageBytes + col * 16;
+    if (active) {
+      for (int r = pl; r < rows; r += PP) {
+        half8 v[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) v[t] = *reinterpret_cast<const half8*>(base + t * rg.tensor_bytes + r * rg.row_bytes);
+        f(p + r, v);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rg.empty[stage]);
+  }
+}
+
+__device__ __forceinline__ void gng_ring_init(GngRing& rg, uint8_t* dyn_smem, uint64_t* bars, int C, int NT) {
+  rg.buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 127) & ~uintptr_t(127));
+  rg.full = bars;
+  rg.empty = bars + kGngStages;
+  rg.row_bytes = C * 2;
+  const int V = C / 8, PP = kGngConsumers / V;
+  rg.R = (NT == 1 ? 2 : 1) * PP;  // 16 KB (one tensor) or 2 x 8 KB per stage when C / 8 divides 512
+  rg.tensor_bytes = rg.R * rg.row_bytes;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGngStages; ++s) {
+      mbar_init(&rg.full[s], 1);
+      mbar_init(&rg.empty[s], kGngConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -111,51 +189,44 @@ __global__ void __launch_bounds__(kGngThreads, 1)
 gn_fwd_grid_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ emb, __half* __restrict__ y, float* __restrict__ stats, float* __restrict__ partials,
                    unsigned int* __restrict__ bar, int HW, int C, int64_t ldx, int64_t ldy, int Gn, float eps, int silu) {
-  __shared__ float red_s[kGngThreads * 8], red_q[kGngThreads * 8];
+  extern __shared__ uint8_t gng_dyn[];
+  __shared__ float red_s[kGngConsumers * 8], red_q[kGngConsumers * 8];
   __shared__ float gs[32], gq[32];
   __shared__ double fa[32], fb[32];
   __shared__ float s_mean[32], s_rstd[32];
+  __shared__ __align__(8) uint64_t bars[2 * kGngStages];
   const int n = blockIdx.x / Gn, chunk = blockIdx.x % Gn;
-  const int V = C / 8, PP = kGngThreads / V;
-  const int col = threadIdx.x % V, pl = threadIdx.x / V;
-  const bool active = pl < PP;
+  const int V = C / 8, PP = kGngConsumers / V;
   const int cpg = C / 32;
   const int ppc = (HW + Gn - 1) / Gn;
-  const int p0 = chunk * ppc, p1 = min(HW, p0 + ppc);
-  float ga[8], be[8];
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ga[j] = gamma[col * 8 + j];
-      be[j] = beta[col * 8 + j];
-    }
-  }
+  const int p0 = min(HW, chunk * ppc), p1 = min(HW, p0 + ppc);
+  GngRing rg;
+  gng_ring_init(rg, gng_dyn, bars, C, 1);
+  __syncthreads();
   pdl_wait();
   pdl_launch_dependents();
-  const __half* xb = x + (int64_t)n * HW * ldx + col * 8;
+  const __half* xn = x + (int64_t)n * HW * ldx;
+  if (threadIdx.x >= kGngConsumers) {
+    const __half* const src[1] = {xn};
+    const int64_t ld[1] = {ldx};
+    gng_produce<1>(rg, src, ld, C, p0, p1, 2);
+    return;
+  }
+  const int col = threadIdx.x % V, pl = threadIdx.x / V;
+  const bool active = pl < PP;
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  if (active) {
-    for (int p = p0 + pl; p < p1; p += kGngUnroll * PP) {
-      half8 raw[kGngUnroll];
+  uint32_t cnt = 0;
+  gng_consume<1>(rg, cnt, p0, p1, col, pl, PP, active, [&](int, const half8(&v)[1]) {
+    float f[8];
+    unpack8(v[0], f);
 #pragma unroll
-      for (int u = 0; u < kGngUnroll; ++u)
-        if (p + u * PP < p1) raw[u] = ld8(xb + (int64_t)(p + u * PP) * ldx);
-#pragma unroll
-      for (int u = 0; u < kGngUnroll; ++u) {
-        if (p + u * PP < p1) {
-          float v[8];
-          unpack8(raw[u], v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s[j] += v[j];
-            q[j] = fmaf(v[j], v[j], q[j]);
-          }
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      q[j] = fmaf(f[j], f[j], q[j]);
     }
-  }
+  });
   gng_block_reduce(s, q, C, col, pl, PP, active, red_s, red_q, gs, gq);
   if (threadIdx.x < 32) {
     float* o = partials + (((int64_t)n * Gn + chunk) * 32 + threadIdx.x) * 2;
@@ -177,73 +248,67 @@ gn_fwd_grid_kernel(const __half* __restrict__ x, const float* __restrict__ gamma
       stats[((int64_t)n * 32 + threadIdx.x) * 2 + 1] = rs;
     }
   }
-  __syncthreads();
-  if (!active) return;
+  gng_sync();
   float A[8], Bc[8];
+  if (active) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = col * 8 + j, g = c / cpg;
-    const float mu = s_mean[g], rs = s_rstd[g];
-    float sc1 = 1.f, sh = 0.f;
-    if (emb) {
-      sc1 = 1.f + emb[(int64_t)n * 2 * C + c];
-      sh = emb[(int64_t)n * 2 * C + C + c];
+    for (int j = 0; j < 8; ++j) {
+      const int c = col * 8 + j, g = c / cpg;
+      const float mu = s_mean[g], rs = s_rstd[g];
+      const float ga = gamma[c], be = beta[c];
+      float sc1 = 1.f, sh = 0.f;
+      if (emb) {
+        sc1 = 1.f + emb[(int64_t)n * 2 * C + c];
+        sh = emb[(int64_t)n * 2 * C + C + c];
+      }
+      A[j] = rs * ga * sc1;
+      Bc[j] = (be - mu * rs * ga) * sc1 + sh;
     }
-    A[j] = rs * ga[j] * sc1;
-    Bc[j] = (be[j] - mu * rs * ga[j]) * sc1 + sh;
   }
   __half* yb = y + (int64_t)n * HW * ldy + col * 8;
-  for (int p = p0 + pl; p < p1; p += kGngUnroll * PP) {
-    half8 raw[kGngUnroll];
+  gng_consume<1>(rg, cnt, p0, p1, col, pl, PP, active, [&](int p, const half8(&v)[1]) {
+    float f[8];
+    unpack8(v[0], f);
 #pragma unroll
-    for (int u = 0; u < kGngUnroll; ++u)
-      if (p + u * PP < p1) raw[u] = ld8(xb + (int64_t)(p + u * PP) * ldx);
-#pragma unroll
-    for (int u = 0; u < kGngUnroll; ++u) {
-      if (p + u * PP < p1) {
-        float v[8];
-        unpack8(raw[u], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float t = fmaf(v[j], A[j], Bc[j]);
-          v[j] = silu ? silu_f(t) : t;
-        }
-        st8(yb + (int64_t)(p + u * PP) * ldy, pack8(v));
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float t = fmaf(f[j], A[j], Bc[j]);
+      f[j] = silu ? silu_f(t) : t;
     }
-  }
+    st8(yb + (int64_t)p * ldy, pack8(f));
+  });
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int kGngUnrollB = 4;
-
 __global__ void __launch_bounds__(kGngThreads, 1)
 gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const float* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ emb,
                    __half* __restrict__ dx, float* __restrict__ partials, unsigned int* __restrict__ bar, int HW, int C, int64_t ld_dy,
                    int64_t ldx, int64_t ld_dx, int Gn, int silu, int accumulate) {
-  __shared__ float red_s[kGngThreads * 8], red_q[kGngThreads * 8];
+  extern __shared__ uint8_t gng_dyn[];
+  __shared__ float red_s[kGngConsumers * 8], red_q[kGngConsumers * 8];
   __shared__ float gs[32], gq[32];
   __shared__ double fa[32], fb[32];
   __shared__ float s_m1[32], s_m2[32];
+  __shared__ __align__(8) uint64_t bars[2 * kGngStages];
   const int n = blockIdx.x / Gn, chunk = blockIdx.x % Gn;
-  const int V = C / 8, PP = kGngThreads / V;
-  const int col = threadIdx.x % V, pl = threadIdx.x / V;
-  const bool active = pl < PP;
+  const int V = C / 8, PP = kGngConsumers / V;
   const int cpg = C / 32;
   const int ppc = (HW + Gn - 1) / Gn;
-  const int p0 = chunk * ppc, p1 = min(HW, p0 + ppc);
-  float G[8], Bc[8];
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      G[j] = gamma[col * 8 + j];
-      Bc[j] = beta[col * 8 + j];
-    }
-  }
+  const int p0 = min(HW, chunk * ppc), p1 = min(HW, p0 + ppc);
+  GngRing rg;
+  gng_ring_init(rg, gng_dyn, bars, C, 2);
+  __syncthreads();
   pdl_wait();
   pdl_launch_dependents();
-  float mu[8], rs[8];
+  if (threadIdx.x >= kGngConsumers) {
+    const __half* const src[2] = {dy + (int64_t)n * HW * ld_dy, x + (int64_t)n * HW * ldx};
+    const int64_t ld[2] = {ld_dy, ldx};
+    gng_produce<2>(rg, src, ld, C, p0, p1, 2);
+    return;
+  }
+  const int col = threadIdx.x % V, pl = threadIdx.x / V;
+  const bool active = pl < PP;
+  float G[8], Bc[8], mu[8], rs[8];
   if (active) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -255,44 +320,29 @@ gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
         sc1 = 1.f + emb[(int64_t)n * 2 * C + c];
         sh = emb[(int64_t)n * 2 * C + C + c];
       }
-      const float ga = G[j];
-      G[j] = ga * sc1;                                  // d v / d xhat
-      Bc[j] = (Bc[j] - mu[j] * rs[j] * ga) * sc1 + sh;  // v = x * (rs * G) + Bc
+      const float ga = gamma[c];
+      G[j] = ga * sc1;                                   // d v / d xhat
+      Bc[j] = (beta[c] - mu[j] * rs[j] * ga) * sc1 + sh;  // v = x * (rs * G) + Bc
     }
   }
-  const __half* xb = x + (int64_t)n * HW * ldx + col * 8;
-  const __half* db = dy + (int64_t)n * HW * ld_dy + col * 8;
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  if (active) {
-    for (int p = p0 + pl; p < p1; p += kGngUnrollB * PP) {
-      half8 rx[kGngUnrollB], rd[kGngUnrollB];
+  uint32_t cnt = 0;
+  gng_consume<2>(rg, cnt, p0, p1, col, pl, PP, active, [&](int, const half8(&v)[2]) {
+    float d[8], a[8];
+    unpack8(v[0], d);
+    unpack8(v[1], a);
 #pragma unroll
-      for (int u = 0; u < kGngUnrollB; ++u)
-        if (p + u * PP < p1) {
-          rx[u] = ld8(xb + (int64_t)(p + u * PP) * ldx);
-          rd[u] = ld8(db + (int64_t)(p + u * PP) * ld_dy);
-        }
-#pragma unroll
-      for (int u = 0; u < kGngUnrollB; ++u) {
-        if (p + u * PP < p1) {
-          float v[8], d[8];
-          unpack8(rx[u], v);
-          unpack8(rd[u], d);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float dv = d[j];
-            if (silu) dv *= silu_grad_f(fmaf(v[j], rs[j] * G[j], Bc[j]));
-            const float dxh = dv * G[j];
-            const float xh = (v[j] - mu[j]) * rs[j];
-            s[j] += dxh;
-            q[j] = fmaf(dxh, xh, q[j]);
-          }
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      float dv = d[j];
+      if (silu) dv *= silu_grad_f(fmaf(a[j], rs[j] * G[j], Bc[j]));
+      const float dxh = dv * G[j];
+      const float xh = (a[j] - mu[j]) * rs[j];
+      s[j] += dxh;
+      q[j] = fmaf(dxh, xh, q[j]);
     }
-  }
+  });
   gng_block_reduce(s, q, C, col, pl, PP, active, red_s, red_q, gs, gq);
   if (threadIdx.x < 32) {
     float* o = partials + (((int64_t)n * Gn + chunk) * 32 + threadIdx.x) * 2;
@@ -306,48 +356,36 @@ gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
     s_m1[threadIdx.x] = (float)(fa[threadIdx.x] / m);  // mean(dxhat)
     s_m2[threadIdx.x] = (float)(fb[threadIdx.x] / m);  // mean(dxhat * xhat)
   }
-  __syncthreads();
-  if (!active) return;
+  gng_sync();
   float m1[8], m2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (col * 8 + j) / cpg;
+    const int g = min((col * 8 + j) / cpg, 31);
     m1[j] = s_m1[g];
     m2[j] = s_m2[g];
   }
   __half* ob = dx + (int64_t)n * HW * ld_dx + col * 8;
-  for (int p = p0 + pl; p < p1; p += kGngUnrollB * PP) {
-    half8 rx[kGngUnrollB], rd[kGngUnrollB], ro[kGngUnrollB];
+  gng_consume<2>(rg, cnt, p0, p1, col, pl, PP, active, [&](int p, const half8(&v)[2]) {
+    float d[8], a[8], o[8];
+    if (accumulate) unpack8(ld8(ob + (int64_t)p * ld_dx), o);
+    unpack8(v[0], d);
+    unpack8(v[1], a);
 #pragma unroll
-    for (int u = 0; u < kGngUnrollB; ++u)
-      if (p + u * PP < p1) {
-        rx[u] = ld8(xb + (int64_t)(p + u * PP) * ldx);
-        rd[u] = ld8(db + (int64_t)(p + u * PP) * ld_dy);
-        if (accumulate) ro[u] = ld8(ob + (int64_t)(p + u * PP) * ld_dx);
-      }
-#pragma unroll
-    for (int u = 0; u < kGngUnrollB; ++u) {
-      if (p + u * PP < p1) {
-        float v[8], d[8], o[8];
-        unpack8(rx[u], v);
-        unpack8(rd[u], d);
-        if (accumulate) unpack8(ro[u], o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float dv = d[j];
-          if (silu) dv *= silu_grad_f(fmaf(v[j], rs[j] * G[j], Bc[j]));
-          const float dxh = dv * G[j];
-          const float xh = (v[j] - mu[j]) * rs[j];
-          const float r = rs[j] * (dxh - m1[j] - xh * m2[j]);
-          o[j] = accumulate ? o[j] + r : r;
-        }
-        st8(ob + (int64_t)(p + u * PP) * ld_dx, pack8(o));
-      }
+    for (int j = 0; j < 8; ++j) {
+      float dv = d[j];
+      if (silu) dv *= silu_grad_f(fmaf(a[j], rs[j] * G[j], Bc[j]));
+      const float dxh = dv * G[j];
+      const float xh = (a[j] - mu[j]) * rs[j];
+      const float r = rs[j] * (dxh - m1[j] - xh * m2[j]);
+      o[j] = accumulate ? o[j] + r : r;
     }
-  }
+    st8(ob + (int64_t)p * ld_dx, pack8(o));
+  });
 }
 
 // ------------------------------------------------------------------------------------------------ host
+constexpr int kGngDynSmem = kGngStages * kGngStageBytes + 128;
+
 static int gng_check(const char* what, int64_t N, int64_t HW, int64_t C, int64_t Gn) {
   CGD_CHECK_ARG(N > 0 && HW > 0, "%s: bad dims", what);
   CGD_CHECK_ARG(C >= 64 && C % 64 == 0 && C <= 2048, "%s: C=%lld must be a multiple of 64 in [64, 2048]", what, (long long)C);
@@ -367,7 +405,12 @@ int launch_gn_fwd_grid(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], HW = op.i[1], C = op.i[2], ldx = op.i[3], ldy = op.i[4], Gn = op.i[5];
   if (int rc = gng_check("gn_fwd_grid", N, HW, C, Gn)) return rc;
   CGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[4] && op.p[5] && op.p[6] && op.p[7], "gn_fwd_grid: bad args");
-  CGD_CUDA(launch_pdl(gn_fwd_grid_kernel, dim3((unsigned)(N * Gn)), dim3(kGngThreads), 0, st, (const __half*)op.p[0], (const float*)op.p[1],
+  static bool set = false;
+  if (!set) {
+    CGD_CUDA(cudaFuncSetAttribute(gn_fwd_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGngDynSmem));
+    set = true;
+  }
+  CGD_CUDA(launch_pdl(gn_fwd_grid_kernel, dim3((unsigned)(N * Gn)), dim3(kGngThreads), kGngDynSmem, st, (const __half*)op.p[0], (const float*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (float*)op.p[6], (unsigned int*)op.p[7],
                       (int)HW, (int)C, ldx, ldy, (int)Gn, op.f[0], (int)(op.flags & 1)));
   return 0;
@@ -379,7 +422,12 @@ int launch_gn_bwd_grid(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(ld_dy % 8 == 0 && ldx % 8 == 0 && ld_dx % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[3] && op.p[4] && op.p[6] && op.p[7] &&
                     op.p[8],
                 "gn_bwd_grid: bad args");
-  CGD_CUDA(launch_pdl(gn_bwd_grid_kernel, dim3((unsigned)(N * Gn)), dim3(kGngThreads), 0, st, (const __half*)op.p[0], (const __half*)op.p[1],
+  static bool set = false;
+  if (!set) {
+    CGD_CUDA(cudaFuncSetAttribute(gn_bwd_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGngDynSmem));
+    set = true;
+  }
+  CGD_CUDA(launch_pdl(gn_bwd_grid_kernel, dim3((unsigned)(N * Gn)), dim3(kGngThreads), kGngDynSmem, st, (const __half*)op.p[0], (const __half*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (const float*)op.p[4], (const float*)op.p[5], (__half*)op.p[6],
                       (float*)op.p[7], (unsigned int*)op.p[8], (int)HW, (int)C, ld_dy, ldx, ld_dx, (int)Gn, (int)(op.flags & 1),
                       (int)((op.flags & 2) ? 1 : 0)));

@@ -21,6 +21,7 @@ int launch_add(const CgdOp& op, cudaStream_t st);
 int launch_copy(const CgdOp& op, cudaStream_t st);
 int launch_attn_fwd(const CgdOp& op, cudaStream_t st);
 int launch_attn_bwd(const CgdOp& op, cudaStream_t st);
+int attn_bwd_num_launches(const CgdOp& op);
 int launch_transpose(const CgdOp& op, cudaStream_t st);
 int launch_softmax_fwd(const CgdOp& op, cudaStream_t st);
 int launch_softmax_bwd(const CgdOp& op, cudaStream_t st);

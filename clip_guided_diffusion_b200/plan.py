@@ -406,6 +406,23 @@ class Plan:
         self._tape.append(bwd)
         return y
 
+    def concat_view(self, y: Act, a: Act, b: Act):
+        """`y` = [a | b] where a and b are channel slices of y's own storage, already written there by their producers:
+        no forward op; the backward hands the matching slices of dy to a and b."""
+        assert a.buf is y.buf and b.buf is y.buf and a.eoff == y.eoff and b.eoff == y.eoff + a.C and a.C + b.C == y.C
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            ga, gb = dy.cslice(0, a.C), dy.cslice(a.C, a.C + b.C)
+            ga.frozen = gb.frozen = True
+            self.add_grad(a, ga)
+            self.add_grad(b, gb)
+
+        self._tape.append(bwd)
+        return y
+
     # ------------------------------------------------------------------ attention (head dim 64)
     def attention(self, qkv: Act, heads: int, T: int, nbatch: int, legacy_order: bool, name="attn") -> Act:
         """qkv: [nbatch*T rows, 3C].  legacy_order: per-head [q|k|v] interleave (UNet QKVAttentionLegacy);

@@ -123,20 +123,33 @@ class UNetB200:
     def _conv_w(self, prefix, need_bwd=True, cin_pad=None) -> ConvW:
         return pack_conv(self.plan, self._w(prefix + ".weight"), self._w(prefix + ".bias"), need_bwd=need_bwd, cin_pad=cin_pad, name=prefix)
 
-    def _emb_linear(self, prefix, cout2):
-        """emb_layers: e = Linear(SiLU(emb)) -> [B, 2*Cout] fp32 (x-independent: emitted in the prelude, no backward)."""
-        p = self.plan
-        e = p.new(self.B * cout2, "f", prefix + "_e")
-        ted = 4 * self.cfg.model_channels
-        p.emit("LINEAR_SMALL", flags=1, i=[self.B, ted, cout2, ted, cout2],
-               p=[(self.emb, 0), (self._const(prefix + ".weight"), 0), (self._const(prefix + ".bias"), 0), (e, 0)], tag=prefix)
+    def _resblock_prepare(self, prefix, cout):
+        """Register one ResBlock's emb_layers Linear (e = Linear(SiLU(emb)) -> [B, 2*Cout] fp32, x-independent: no backward).
+        All of them are evaluated by ONE weight-streaming launch in the prelude (`_emit_emb_layers`): ~30 launches of 8 MB fp32
+        each (0.43 ms per step) become one pass over the concatenated fp16 weights (the reference's emb_layers are fp16 too:
+        convert_to_fp16 covers the ResBlocks, cgd/script_util.py:322-323)."""
+        cout2 = 2 * cout
+        e = self.plan.new(self.B * cout2, "f", prefix + ".emb_layers.1_e")
+        self._emb_jobs.append((prefix + ".emb_layers.1", cout2, e))
         return e
 
-    # ------------------------------------------------------------------ blocks (forward builders; backward goes on the tape)
-    def _resblock_prepare(self, prefix, cout):
-        return self._emb_linear(prefix + ".emb_layers.1", 2 * cout)
+    def _emit_emb_layers(self):
+        p = self.plan
+        ted = 4 * self.cfg.model_channels
+        W = th.cat([self._w(k + ".weight") for k, _, _ in self._emb_jobs], dim=0)
+        b = th.cat([self._w(k + ".bias") for k, _, _ in self._emb_jobs], dim=0)
+        base = self._emb_jobs[0][2].off
+        tab = []
+        for _, cout2, e in self._emb_jobs:
+            assert (e.off - base) % 4 == 0
+            off = (e.off - base) // 4
+            tab += [[off + c, cout2] for c in range(cout2)]
+        n_total = W.shape[0]
+        p.emit("LINEAR_SMALL", flags=1 | 16, i=[self.B, ted, n_total, ted, n_total],
+               p=[(self.emb, 0), (p.const(W, "h", "emb_layers.W"), 0), (p.const(b, "f", "emb_layers.b"), 0), (self._emb_jobs[0][2], 0),
+                  (p.const(th.tensor(tab, dtype=th.int32), "i32", "emb_layers.scatter"), 0)], tag="emb_layers (all ResBlocks)")
 
-    def _resblock(self, x: Act, prefix: str, cout: int, e_buf, up=False, down=False) -> Act:
+    def _resblock(self, x: Act, prefix: str, cout: int, e_buf, up=False, down=False, out: Act = None) -> Act:
         p = self.plan
         h = p.group_norm(x, self._const(prefix + ".in_layers.0.weight"), self._const(prefix + ".in_layers.0.bias"), silu=True,
                          name=prefix + ".in_gn")
@@ -150,16 +163,16 @@ class UNetB200:
                          silu=True, name=prefix + ".out_gn")
         if x.C != cout:
             xs = p.conv(xs, self._conv_w(prefix + ".skip_connection"), name=prefix + ".skip")
-        return p.conv(h, self._conv_w(prefix + ".out_layers.3"), res=xs, name=prefix + ".conv2")
+        return p.conv(h, self._conv_w(prefix + ".out_layers.3"), res=xs, out=out, name=prefix + ".conv2")
 
-    def _attnblock(self, x: Act, prefix: str) -> Act:
+    def _attnblock(self, x: Act, prefix: str, out: Act = None) -> Act:
         p, cfg = self.plan, self.cfg
         C = x.C
         heads = cfg.num_heads if cfg.num_head_channels == -1 else C // cfg.num_head_channels
         xn = p.group_norm(x, self._const(prefix + ".norm.weight"), self._const(prefix + ".norm.bias"), silu=False, name=prefix + ".norm")
         qkv = p.conv(xn, self._conv_w(prefix + ".qkv"), name=prefix + ".qkv")
         a = p.attention(qkv, heads, x.HW, x.N, legacy_order=not cfg.use_new_attention_order, name=prefix + ".attn")
-        return p.conv(a, self._conv_w(prefix + ".proj_out"), res=x, name=prefix + ".proj")
+        return p.conv(a, self._conv_w(prefix + ".proj_out"), res=x, out=out, name=prefix + ".proj")
 
     # ------------------------------------------------------------------ whole network
     def _build(self, build_backward: bool):
@@ -189,6 +202,7 @@ class UNetB200:
 
         blocks_in, mid_ch, blocks_out = topology(cfg)
         # scale-shift vectors (prelude ops must precede the trunk)
+        self._emb_jobs = []
         for b in blocks_in:
             b["e"] = self._resblock_prepare(b["prefix"] + ".0", b["cout"])
         mid_e = [self._resblock_prepare("middle_block.0", mid_ch), self._resblock_prepare("middle_block.2", mid_ch)]
@@ -197,29 +211,59 @@ class UNetB200:
             if b["up"]:
                 b["e_up"] = self._resblock_prepare(b["prefix"] + (".2" if b["attn"] else ".1"), b["cout"])
 
+        self._emit_emb_layers()
+
         # ---- forward trunk
         p.mark("unet_fwd")
         x0 = Act(p.new(B * H * W * IN_PAD, "h", "x_pm"), 0, B, H, W, IN_PAD, IN_PAD)
         p.emit("NCHW_TO_PM", i=[B, 3, H * W, IN_PAD], f=[1.0], p=[(self.x_in, 0), (x0.buf, 0)], tag="x->pixel-major")
         stem_w = self._conv_w("input_blocks.0.0", need_bwd=build_backward, cin_pad=IN_PAD)
-        h = p.conv(x0, ConvW(stem_w.fwd, stem_w.fwd_npad, None, 0, stem_w.bias, IN_PAD, stem_w.cout, 9), name="stem")
+        # torch.cat([h, hs.pop()], dim=1) of every output block without a copy: the concatenated tensor of output block k is
+        # allocated when its skip half is produced on the way down; the stem / input-block convs write the skip half and the
+        # preceding block writes the h half straight into it (TMA stores with the wide row stride), consumers read the halves as
+        # strided views.  46 copy launches and 2 x 0.25 GB of traffic per step at 256x256 disappear.
+        n_skips = len(blocks_in) + 1
+        cats = [None] * len(blocks_out)
+
+        def skip_slot(j, Hc, Wc):
+            """storage of hs[j]: the skip half of the output block that will pop it"""
+            k = n_skips - 1 - j
+            bo = blocks_out[k]
+            cats[k] = p.act(B, Hc, Wc, bo["cin"], bo["prefix"] + ".cat")
+            return cats[k].cslice(bo["cin"] - bo["ich"], bo["cin"])
+
+        def h_slot(k):
+            """storage of the h half of output block k (None past the last block)"""
+            if k >= len(blocks_out):
+                return None
+            bo = blocks_out[k]
+            return cats[k].cslice(0, bo["cin"] - bo["ich"])
+
+        h = p.conv(x0, ConvW(stem_w.fwd, stem_w.fwd_npad, None, 0, stem_w.bias, IN_PAD, stem_w.cout, 9), out=skip_slot(0, H, W), name="stem")
         stem_out = h
         hs = [h]
-        for b in blocks_in:
-            h = self._resblock(h, b["prefix"] + ".0", b["cout"], b["e"], down=b["down"])
+        for j, b in enumerate(blocks_in, start=1):
+            Ho, Wo = (h.H // 2, h.W // 2) if b["down"] else (h.H, h.W)
+            slot = skip_slot(j, Ho, Wo)
+            h = self._resblock(h, b["prefix"] + ".0", b["cout"], b["e"], down=b["down"], out=None if b["attn"] else slot)
             if b["attn"]:
-                h = self._attnblock(h, b["prefix"] + ".1")
+                h = self._attnblock(h, b["prefix"] + ".1", out=slot)
             hs.append(h)
         h = self._resblock(h, "middle_block.0", mid_ch, mid_e[0])
         h = self._attnblock(h, "middle_block.1")
-        h = self._resblock(h, "middle_block.2", mid_ch, mid_e[1])
-        for b in blocks_out:
-            h = p.concat(h, hs.pop(), name=b["prefix"] + ".cat")
-            h = self._resblock(h, b["prefix"] + ".0", b["cout"], b["e"])
+        h = self._resblock(h, "middle_block.2", mid_ch, mid_e[1], out=h_slot(0))
+        for k, b in enumerate(blocks_out):
+            skip = hs.pop()
+            assert h.buf is cats[k].buf and skip.buf is cats[k].buf and h.C + skip.C == cats[k].C
+            p.concat_view(cats[k], h, skip)
+            h = cats[k]
+            nxt = h_slot(k + 1)
+            last = "up" if b["up"] else ("attn" if b["attn"] else "res")
+            h = self._resblock(h, b["prefix"] + ".0", b["cout"], b["e"], out=nxt if last == "res" else None)
             if b["attn"]:
-                h = self._attnblock(h, b["prefix"] + ".1")
+                h = self._attnblock(h, b["prefix"] + ".1", out=nxt if last == "attn" else None)
             if b["up"]:
-                h = self._resblock(h, b["prefix"] + (".2" if b["attn"] else ".1"), b["cout"], b["e_up"], up=True)
+                h = self._resblock(h, b["prefix"] + (".2" if b["attn"] else ".1"), b["cout"], b["e_up"], up=True, out=nxt)
         hn = p.group_norm(h, self._const("out.0.weight"), self._const("out.0.bias"), silu=True, name="out.gn")
         head_w = self._conv_w("out.2", need_bwd=build_backward)
         HW = H * W

@@ -96,8 +96,9 @@ enum {
    * i/f as forward (dq/dk/dv use the qkv strides, dout the out strides) */
   CGD_OP_ATTN_BWD = 10,
   /* Small-M fp32 linear: y[M,N] (=|+=) act(x[M,K]) @ W[N,K]^T + b.  time_embed / emb_layers / CLIP head.
-   * p0 x(f|h) p1 W(f) p2 b(f)|0 p3 y(f|h) ; i0 M i1 K i2 N i3 ldx i4 ldy
-   * flags 1 = SiLU on x, 2 = accumulate, 4 = x is fp16, 8 = y is fp16 */
+   * p0 x(f|h) p1 W(f|h) p2 b(f)|0 p3 y(f|h) p4 scatter(i32 [N,2] = element offset of row 0, row stride)|0 ; i0 M i1 K (% 8 == 0)
+   * i2 N i3 ldx i4 ldy ; flags 1 = SiLU on x, 2 = accumulate, 4 = x is fp16, 8 = y is fp16, 16 = W is fp16.
+   * With the scatter table one launch evaluates all ResBlock emb_layers (same x, concatenated W) into per-block [M, N_k] outputs. */
   CGD_OP_LINEAR_SMALL = 11,
   /* sinusoidal timestep embedding: p0 t(f [B]) p1 out(f [B,dim]) ; i0 B i1 dim ; f0 t scale */
   CGD_OP_TIMESTEP_EMB = 12,

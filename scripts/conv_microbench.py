@@ -22,7 +22,7 @@ SHAPES = [  # NB, H, W, Cin, Cout, taps, res
 ]
 force_bn = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 if force_bn:
-    P.pick_bn = lambda npad, m_tiles: force_bn
+    P.pick_bn = lambda npad, m_tiles, kblocks=0: force_bn
 dev = th.device("cuda", 0)
 for (NB, H, W, Cin, Cout, taps, res) in SHAPES:
     th.manual_seed(0)

@@ -23,7 +23,7 @@ for (NB, H, W, Cin, Cout, taps) in SHAPES:
         for sp in (0, 1, 2, 3, 4, 6, 8, 12, 16, 24):  # 0 = the plan's own choice
             if sp > kblocks or (sp > 1 and kblocks // sp < 2):
                 continue
-            P.pick_bn = lambda npad, m_tiles, bn=bn: bn
+            P.pick_bn = lambda npad, m_tiles, kblocks=0, bn=bn: bn
             if sp:
                 P.pick_splits = lambda m_tiles, n_tiles, kb, npad, ws_cap_bytes=0, sp=sp: sp
             else:

@@ -12,9 +12,10 @@ if cs_override:
     orig = P.gn_fused_cluster
     P.gn_fused_cluster = lambda N, HW, C, maxv: (cs_override if orig(N, HW, C, maxv) and -(-HW // cs_override) <= maxv * (512 // max(2, C // 256)) else orig(N, HW, C, maxv))
 for HW, C in SHAPES:
-    for fused in (True, False):
+    for mode in ('auto', 'grid', 'twopass'):
         plan = P.Plan()
-        plan.fused_gn = fused
+        plan.fused_gn = mode == 'auto'
+        plan.grid_gn = mode != 'twopass'
         gb, bb = plan.const(th.ones(C), "f", "g"), plan.const(th.zeros(C), "f", "b")
         eb = plan.const(th.zeros(2 * C), "f", "e")
         nbuf = max(2, min(8, int(200e6 // (HW * C * 8)) + 1))
@@ -48,5 +49,5 @@ for HW, C in SHAPES:
             res.append(f"{a} {t * 1e6:7.1f} us {byts / t / 1e9:7.0f} GB/s")
         kinds = sorted({o.code for o in plan.ops})
         cs = [o.i[5] for o in plan.ops if o.code == 33][:1] + [o.i[6] for o in plan.ops if o.code == 34][:1]
-        print(f"HW {HW:6d} C {C:5d} {'fused' if 33 in kinds else 'twopass':8s} CS{cs}: " + " | ".join(res), flush=True)
+        print(f"HW {HW:6d} C {C:5d} {'fused' if 33 in kinds else ('grid' if 35 in kinds else 'twopass'):8s} CS{cs}: " + " | ".join(res), flush=True)
         del plan

@@ -258,9 +258,18 @@ class Interp:
         x = self.V(op.p[0], (M, K), (ldx, 1)).float()
         if op.flags & 1:
             x = F.silu(x)
-        y = x @ self.V(op.p[1], (N, K), (K, 1)).t()
+        y = x @ self.V(op.p[1], (N, K), (K, 1)).float().t()
         if op.p[2] is not None:
             y = y + self.flat(op.p[2], N)
+        if len(op.p) > 4 and op.p[4] is not None:  # scatter table: column n -> (offset of row 0, row stride)
+            tab = self.V(op.p[4], (N, 2), (2, 1)).long()
+            buf, eoff = op.p[3]
+            flat = self.typed(buf.dt)
+            base = buf.off // _DT[buf.dt][0] + eoff
+            for m in range(M):
+                idx = base + tab[:, 0] + m * tab[:, 1]
+                flat[idx] = (flat[idx].float() + y[m] if op.flags & 2 else y[m]).to(flat.dtype)
+            return
         out = self.V(op.p[3], (M, N), (ldy, 1))
         out.copy_(out.float() + y if op.flags & 2 else y)
 
