@@ -116,6 +116,16 @@ static int plan_create(const CgdOp* ops, int32_t n_ops, Plan** out) {
       pl->convs.push_back(L);
     }
   }
+  // L2 prefetch chain: every conv prefetches the packed weights of the next conv of the list while its own epilogue warps
+  // wait for the accumulator (the 8x8 .. 32x32 layers and the ViT GEMMs are bound by the HBM latency of their weight stream)
+  if (!(getenv("CGD_CONV_PREFETCH") && getenv("CGD_CONV_PREFETCH")[0] == '0')) {
+    for (size_t k = 0; k + 1 < pl->convs.size(); ++k) {
+      const ConvTcLaunch& nx = pl->convs[k + 1];
+      if (nx.impl == 1 || nx.p.b_batched) continue;
+      pl->convs[k].p.pf_ptr = nx.Wp;
+      pl->convs[k].p.pf_bytes = (int64_t)nx.p.Npad * nx.ldb * 2;
+    }
+  }
   *out = pl;
   return 0;
 }

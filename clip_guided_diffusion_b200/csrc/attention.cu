@@ -338,12 +338,23 @@ static bool attn_use_small(int64_t T) {
   return !off && attn_small_supported(T);
 }
 
+int launch_attn_mma_fwd(const CgdOp& op, cudaStream_t st);  // attention_mma.cu: flash attention on warp MMAs (any T)
+int launch_attn_mma_bwd(const CgdOp& op, cudaStream_t st);
+static bool attn_use_mma() {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("CGD_ATTN_MMA");
+    off = (e && e[0] == '0') ? 1 : 0;
+  }
+  return !off;
+}
 int attn_bwd_num_launches(const CgdOp& op) { return attn_use_small(op.i[2]) ? 1 : 3; }
 
 int launch_attn_fwd(const CgdOp& op, cudaStream_t st) {
   AttnArgs a{};
   if (int rc = attn_args(op, a, false)) return rc;
   if (attn_use_small(a.T)) return launch_attn_small_fwd(op, st);
+  if (attn_use_mma()) return launch_attn_mma_fwd(op, st);
   const int smem = 4 * AT * ALD * (int)sizeof(float);
   static bool set = false;
   if (!set) {
@@ -359,6 +370,7 @@ int launch_attn_bwd(const CgdOp& op, cudaStream_t st) {
   AttnArgs a{};
   if (int rc = attn_args(op, a, true)) return rc;
   if (attn_use_small(a.T)) return launch_attn_small_bwd(op, st);
+  if (attn_use_mma()) return launch_attn_mma_bwd(op, st);
   const int smem_kv = 8 * AT * ALD * (int)sizeof(float), smem_q = 6 * AT * ALD * (int)sizeof(float);
   static bool set = false;
   if (!set) {

@@ -72,9 +72,21 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return red[0];
 }
 
-// sigmoid with the SFU exp + approximate reciprocal (2 MUFU ops, ~2 ulp): these run per element in the HBM-bound
-// normalisation kernels, where the IEEE divide sequence (~10 instructions) was a visible share of the issue slots
-__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+// sigmoid on the SFU: ex2.approx.ftz + rcp.approx.ftz (2 MUFU + 2 FP32 ops, ~2 ulp).  These run per element in the
+// HBM-bound normalisation kernels: the libdevice forms (__expf, __fdividef) carry denormal-range guards (FSETP + 2 FMUL per
+// call in SASS) that made GroupNorm-apply issue-bound; with flush-to-zero the limits are exact: v -> -inf gives
+// ex2 = +inf, rcp = 0; v -> +inf gives ex2 = 0, rcp(1) = 1.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float v) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * v)); }
 __device__ __forceinline__ float silu_f(float v) { return v * sigmoid_fast(v); }
 // d silu(v)/dv
 __device__ __forceinline__ float silu_grad_f(float v) {
@@ -100,7 +112,22 @@ __device__ __forceinline__ half8 pack8(const float* f) {
   h.d = __floats2half2_rn(f[6], f[7]);
   return h;
 }
-__device__ __forceinline__ half8 ld8(const __half* p) { return *reinterpret_cast<const half8*>(p); }
-__device__ __forceinline__ void st8(__half* p, const half8& v) { *reinterpret_cast<half8*>(p) = v; }
+// 128-bit accesses go through the built-in uint4: a struct of four __half2 is scalarised by nvcc into four 32-bit LDG / STG
+// (seen in SASS: not one 128-bit access in norm.cu / elementwise.cu), which quarters the bytes per memory instruction
+union Half8Bits {
+  uint4 u;
+  half8 h;
+  __device__ Half8Bits() {}
+};
+__device__ __forceinline__ half8 ld8(const __half* p) {
+  Half8Bits b;
+  b.u = *reinterpret_cast<const uint4*>(p);
+  return b.h;
+}
+__device__ __forceinline__ void st8(__half* p, const half8& v) {
+  Half8Bits b;
+  b.h = v;
+  *reinterpret_cast<uint4*>(p) = b.u;
+}
 
 }  // namespace cgd

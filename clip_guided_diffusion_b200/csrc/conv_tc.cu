@@ -144,6 +144,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int w_off = r % p.TW, h_off = (r / p.TW) % p.TH, n_off = r / (p.TW * p.TH);
     const int n = n0 + n_off, h = h0 + h_off, w = w0 + w_off;
     const bool row_ok = (n < p.NB) && (h < p.H) && (w < p.W);
+    if (p.pf_bytes > 0)
+      l2_prefetch_slice(p.pf_ptr, p.pf_bytes, (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)),
+                        (int)(gridDim.x * gridDim.y * gridDim.z), (int)threadIdx.x - 64, 128);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16);

@@ -187,6 +187,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     int iter = 0;
+    if (p.pf_bytes > 0) l2_prefetch_slice(p.pf_ptr, p.pf_bytes, blockIdx.x, gridDim.x, (int)threadIdx.x - 64, kEpiThreads2);
     if constexpr (BN >= 64) {
       if (p.epi_tma) {
         // Accumulator -> registers -> (+bias, +residual) -> fp16 -> 128B-swizzled staging tile -> one TMA tensor store per

@@ -158,7 +158,7 @@ __device__ __forceinline__ void gng_consume(const GngRing& rg, uint32_t& cnt, in
       for (int r = pl; r < rows; r += PP) {
         half8 v[NT];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) v[t] = *reinterpret_cast<const half8*>(base + t * rg.tensor_bytes + r * rg.row_bytes);
+        for (int t = 0; t < NT; ++t) v[t] = ld8(reinterpret_cast<const __half*>(base + t * rg.tensor_bytes + r * rg.row_bytes));
         f(p + r, v);
       }
     }

@@ -74,6 +74,17 @@ __device__ __forceinline__ void bulk_load_1d(void* smem, const void* gmem, uint3
                "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// L2 prefetch of this CTA's share of [ptr, ptr + bytes): thread `t` of `nthr` takes one 16-byte-aligned piece
+__device__ __forceinline__ void l2_prefetch_slice(const void* ptr, int64_t bytes, int cta, int ncta, int t, int nthr) {
+  const int64_t per_cta = ((bytes + ncta - 1) / ncta + 15) & ~int64_t(15);
+  const int64_t per_thr = ((per_cta + nthr - 1) / nthr + 15) & ~int64_t(15);
+  const int64_t lo = (int64_t)cta * per_cta + (int64_t)t * per_thr;
+  int64_t hi = lo + per_thr;
+  if (hi > (int64_t)(cta + 1) * per_cta) hi = (int64_t)(cta + 1) * per_cta;
+  if (hi > bytes) hi = bytes & ~int64_t(15);
+  if (hi > lo)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(ptr) + lo), "r"((uint32_t)(hi - lo)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

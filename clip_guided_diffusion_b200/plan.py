@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Optional
 
@@ -178,7 +179,9 @@ class Plan:
         self._tape: list[Callable[[], None]] = []
         self._grads: dict = {}
         self.conv_impl = conv_impl
-        self.tc_attention = True  # long sequences (T % 256 == 0) on the tcgen05 GEMM kernel
+        # long sequences (T % 256 == 0) as batched tcgen05 GEMMs + transposes + softmax kernels; superseded by the flash kernels of
+        # csrc/attention_mma.cu (one launch forward, three backward, nothing T x T in HBM), kept for A/B measurements
+        self.tc_attention = os.environ.get("CGD_TC_ATTENTION", "0") == "1"
         self.arena: Optional[th.Tensor] = None
         self.handle = None
         self._c_ops = None

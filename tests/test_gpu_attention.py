@@ -18,7 +18,9 @@ CASES = [  # nbatch, heads, T, legacy
     (2, 3, 64, False),
     (2, 4, 100, True),     # > 64: flash kernels
     (1, 2, 197, False),    # ViT-B/16 token count
-    (1, 4, 256, True),     # batched tcgen05 GEMM path
+    (1, 4, 256, True),     # UNet 16x16 level
+    (1, 8, 1024, True),    # UNet 32x32 level
+    (1, 2, 300, False),    # ragged last tile
 ]
 
 
@@ -41,12 +43,16 @@ def _ref(qkv, heads, legacy):
     return o.reshape(qkv.shape[0], qkv.shape[1], -1)
 
 
+@pytest.mark.parametrize("tc", [False, True], ids=["flash", "tcgen05_gemms"])
 @pytest.mark.parametrize("case", CASES, ids=[f"b{c[0]}_h{c[1]}_t{c[2]}_{'legacy' if c[3] else 'new'}" for c in CASES])
-def test_attention_fwd_bwd(case):
+def test_attention_fwd_bwd(case, tc):
     B, heads, T, legacy = case
+    if tc and T % 256 != 0:
+        pytest.skip("the batched-GEMM path needs T % 256 == 0")
     C = heads * 64
     th.manual_seed(0)
     plan = Plan()
+    plan.tc_attention = tc  # False: flash kernels (attention_small.cu / attention_mma.cu); True: batched tcgen05 GEMMs
     qkv = Act(plan.new(B * T * 3 * C, "h", "qkv"), 0, 1, 1, B * T, 3 * C, 3 * C)
     out = plan.attention(qkv, heads, T, B, legacy_order=legacy, name="attn")
     do = Act(plan.new(B * T * C, "h", "do"), 0, 1, 1, B * T, C, C)
