@@ -83,7 +83,7 @@ def build_engine(device, rank, world):
     usd = pw.seeded_state_dict(pw.unet_param_shapes(ucfg), seed=1234)
     vsd = pw.seeded_state_dict(pw.vit_param_shapes(vcfg), seed=1235)
     eng = pg.GuidedStepB200(ucfg, usd, vcfg, vsd, batch=CFG["per_gpu_batch"], num_cutouts=CFG["cutn"], device=device, rank=rank,
-                            world_size=world)
+                            world_size=world, vit_streams=int(os.environ.get("CGD_VIT_STREAMS", "1")))
     del usd, vsd
     diff = gd.create_gaussian_diffusion(1000, "linear", CFG["respacing"])
     th.manual_seed(0)
@@ -240,7 +240,7 @@ def run_ours(args):
         "launches_per_step": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"], "traffic": traffic,
-                     "kernel": "conv_tc_kernel<256> 256x256x256->256 3x3 (M=65536,N=256,K=2304)", "peak_source": pk["src"] + " burst (kernel timed alone)",
+                     "kernel": "conv_tc2_kernel<256> 256x256x256->256 3x3 (M=65536,N=256,K=2304)", "peak_source": pk["src"] + " burst (kernel timed alone)",
                      "avg_launch_s": t_dom},
         "step_tensor_frac": FLOP_PER_IMAGE_STEP * value / world / (pk["sustained"] * 1e12),
     }

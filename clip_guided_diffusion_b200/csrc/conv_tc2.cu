@@ -34,8 +34,8 @@ struct Tc2Cfg {
   static constexpr int kABytes = BM2 * BK2 * 2;          // 16 KB: this CTA's 128 pixel rows
   static constexpr int kBBytes = (BN / 2) * BK2 * 2;     // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // epilogue staging: 2 output tiles (TMA store sources) + 2 residual tiles (TMA load destinations)
-  static constexpr int kEpiBytes = BN >= 64 ? 4 * kEpiChunkBytes : 0;
+  // epilogue staging: 2 output tiles (TMA store sources); residual tiles are TMA-loaded INTO them and updated in place
+  static constexpr int kEpiBytes = BN >= 64 ? 2 * kEpiChunkBytes : 0;
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - kEpiBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStages = 2;
@@ -68,7 +68,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;  // [out 0][out 1][res 0][res 1], 1024-byte aligned tiles
+  uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;  // [out 0][out 1], 1024-byte aligned tiles
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
@@ -197,8 +197,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr int kChunks = BN / 64;
         const bool issuer = threadIdx.x == 64;  // warp 2, lane 0: issues every TMA store / residual load of this CTA
         const bool has_res = p.res != nullptr;
-        uint8_t* st_out = smem_epi;
-        uint8_t* st_res = smem_epi + 2 * kEpiChunkBytes;
+        uint8_t* st_out = smem_epi;  // residual chunks are TMA-loaded INTO the staging tile and updated in place
         auto tile_origin = [&](int tt, int& w0, int& h0, int& n0, int& ncol0) {
           const Tile2 tl = decode_tile(p, tt, n_tiles, pair_tiles, rank);
           const int tw_i = tl.mt % p.tiles_w, th_i = (tl.mt / p.tiles_w) % p.tiles_h, tn_i = tl.mt / (p.tiles_w * p.tiles_h);
@@ -211,7 +210,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           int w0, h0, n0, ncol0;
           tile_origin(tt, w0, h0, n0, ncol0);
           mbar_expect_tx(&res_full_bar[buf], kEpiChunkBytes);
-          tma_load_4d(st_res + buf * kEpiChunkBytes, &tmRes, &res_full_bar[buf], ncol0 + c * 64, w0, h0, n0);
+          tma_load_4d(st_out + buf * kEpiChunkBytes, &tmRes, &res_full_bar[buf], ncol0 + c * 64, w0, h0, n0);
         };
         if (issuer && has_res) {  // the first two residual chunks of this CTA's tile sequence
           int tt = cluster_id, c = 0;
@@ -246,11 +245,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               tc_fence_before();
               mbar_arrive_remote(&tmem_empty_bar[acc], 0);
             }
-            // staging tile `buf` is free once the store issued two chunks ago has read it
-            if (issuer) bulk_wait_group_read<1>();
-            named_bar_sync(1, kEpiThreads2);
+            // staging tile `buf` is free once the store issued two chunks ago has read it; with a residual that was already
+            // awaited before the residual load into this tile was issued (below), and res_full_bar orders its arrival
+            if (!has_res) {
+              if (issuer) bulk_wait_group_read<1>();
+              named_bar_sync(1, kEpiThreads2);
+            }
             uint8_t* orow = st_out + buf * kEpiChunkBytes + r * 128;
-            const uint8_t* rrow = st_res + buf * kEpiChunkBytes + r * 128;
+            const uint8_t* rrow = orow;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {  // 8 channels = one 16-byte unit of the 128-byte row, unit index XOR (row & 7)
               float a[8];
@@ -276,7 +278,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (issuer) {
               if (!(p.dbg & 4)) tma_store_4d(st_out + buf * kEpiChunkBytes, &tmOut, col, w0, h0, n0);
               bulk_commit_group();
-              if (has_res) {  // residual tile `buf` has been consumed by every thread: refill it for chunk g + 2
+              if (has_res) {  // once this store has read tile `buf`, the residual of chunk g + 2 may land in it
+                bulk_wait_group_read<0>();
                 int tt = t, c2 = c + 2;
                 while (c2 >= kChunks) {
                   c2 -= kChunks;

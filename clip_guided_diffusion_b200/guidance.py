@@ -108,7 +108,7 @@ class GuidedStepB200:
     def __init__(self, unet_cfg: UNetConfig, unet_sd: dict, vit_cfg: ViTConfig = None, vit_sd: dict = None, *, batch: int,
                  height: int = None, width: int = None, num_cutouts: int = 16, max_prompts: int = 1, clip_guidance_scale=1000.0,
                  tv_scale=150.0, range_scale=50.0, sat_scale=0.0, use_magnitude=False, device="cuda", seed_scale=16.0,
-                 vit_grad_scale=1.0, conv_impl=0, rank: int = 0, world_size: int = 1, use_graph: bool = True):
+                 vit_grad_scale=1.0, conv_impl=0, rank: int = 0, world_size: int = 1, use_graph: bool = True, vit_streams: int = 1):
         self.device = th.device(device)
         self.B = batch
         self.rank, self.world = rank, world_size
@@ -150,7 +150,7 @@ class GuidedStepB200:
             self.g_clip = p.new(n3, "f", "g_clip")
             self.dx_direct = p.new(n3, "f", "dx_direct")
             self.fg_ws = p.new(128, "f", "final_grad_ws")
-            self.vit = ViTB200(vit_cfg, vit_sd, n_images=cutn * B, device=device, plan=p)
+            self.vit = ViTB200(vit_cfg, vit_sd, n_images=cutn * B, device=device, plan=p, parts=vit_streams)
             p.mark("cut_fwd")
             p.emit("CUTOUTS_FWD", i=[B, H, W, cutn, cs, ps, kp], f=[*CLIP_MEAN, *CLIP_STD], p=[(self.x_inb, 0), (self.coords, 0), (self.vit.patches, 0)],
                    tag="make_cutouts+normalize")
@@ -185,6 +185,8 @@ class GuidedStepB200:
         pin = self.device.type == "cuda"
         self._stage = th.zeros(self._n_stage, dtype=th.uint8, pin_memory=pin)
         self._graphs = {}
+        self._side_streams = [th.cuda.Stream(device=self.device) for _ in range((self.vit.parts if self.vit is not None else 1) - 1)] \
+            if self.device.type == "cuda" else []
         self._last_out = None
         self._fwd_valid = False
         self.h2d_bytes = 0
@@ -259,8 +261,11 @@ class GuidedStepB200:
             self.plan.run_range("pmv", "cond")
         assert len(coords) == self.cutn, "cutout count is fixed per engine"
         self.v(self.coords, (self.cutn, 3)).copy_(th.tensor(coords, dtype=th.int32), non_blocking=True)
-        for a, b in (("cut_fwd", "sph"), ("vit_fwd", "vit_bwd"), ("sph", "cut_bwd"), ("vit_bwd", "vit_end"), ("cut_bwd", "guide"),
-                     ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g")):
+        self.plan.run_range("cut_fwd", "sph")
+        self._run_vit("fwd")
+        self.plan.run_range("sph", "cut_bwd")
+        self._run_vit("bwd")
+        for a, b in (("cut_bwd", "guide"), ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g")):
             self.plan.run_range(a, b)
         return self.img(self.g)
 
@@ -287,9 +292,9 @@ class GuidedStepB200:
         pr("unet_emb", "unet_bwd")
         pr("pmv", "cond")
         pr("cut_fwd", "sph")
-        pr("vit_fwd", "vit_bwd")
+        self._run_vit("fwd", pr)
         pr("sph", "cut_bwd")
-        pr("vit_bwd", "vit_end")
+        self._run_vit("bwd", pr)
         pr("cut_bwd", "guide")
         pr("guide", "final")
         pr("unet_bwd", "unet_end")
@@ -298,6 +303,23 @@ class GuidedStepB200:
             pr("upd_anc_g", "upd_anc")
         else:
             pr("upd_ddim_g", "upd_ddim")
+
+    def _run_vit(self, which, pr=None):
+        """CLIP forward / backward: one op range, or one per batch slice on parallel streams (fork / join around the current
+        stream; inside CUDA-graph capture this becomes parallel branches of the graph)."""
+        pr = pr or self.plan.run_range
+        ranges = self.vit.part_ranges(which)
+        if len(ranges) == 1 or not self._side_streams or pr != self.plan.run_range:
+            for a, b in ranges:
+                pr(a, b)
+            return
+        main = th.cuda.current_stream()
+        for s, (a, b) in zip(self._side_streams, ranges[1:]):
+            s.wait_stream(main)
+            self.plan.run_range(a, b, stream=s.cuda_stream)
+        self.plan.run_range(*ranges[0])
+        for s in self._side_streams:
+            main.wait_stream(s)
 
     def launches_per_step(self, mode="ddim") -> int:
         m = self.plan.marks

@@ -19,6 +19,10 @@ CASES = [
     ("conv1x1_skip", 1, 32, 32, 512, 256, 1, True, False),
     ("conv3x3_c192", 1, 32, 32, 192, 384, 9, True, False),
     ("conv3x3_c576_bn192", 1, 16, 16, 384, 576, 9, True, True),
+    ("conv3x3_rowseg_128w_c128_res", 1, 8, 128, 128, 256, 9, True, True),     # tile = one 128-pixel row segment (TW = 128, TH = 1)
+    ("conv3x3_rowseg_256w_c256_b2", 2, 6, 256, 256, 256, 9, True, True),
+    ("conv3x3_rowseg_192w_ragged", 1, 5, 192, 128, 128, 9, True, False),      # second tile of each row is half out of the image
+    ("conv3x3_rowseg_c192_bn192", 1, 3, 128, 192, 192, 9, False, True),
     ("linear_m800_qkv", 1, 1, 800, 768, 2304, 1, True, False),
     ("linear_m50", 1, 1, 50, 768, 768, 1, True, True),
     ("linear_k3072", 1, 1, 800, 3072, 768, 1, True, True),

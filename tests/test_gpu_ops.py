@@ -32,10 +32,11 @@ def test_every_op_matches_interpreter(kw):
     assert not failures, f"{len(failures)} of {n} ops differ from the interpreter:\n{msg}"
 
 
+@pytest.mark.parametrize("streams", [1, 2], ids=["vit1stream", "vit2streams"])
 @pytest.mark.parametrize("mode", ["ancestral", "ddim"])
 @pytest.mark.parametrize("fused", [False, True], ids=["eager", "graph"])
-def test_step_parity_vs_oracle(mode, fused):
-    ctx = build_tiny("cuda", conv_impl=IMPL, image=64, use_graph=True)
+def test_step_parity_vs_oracle(mode, fused, streams):
+    ctx = build_tiny("cuda", conv_impl=IMPL, image=64, use_graph=True, cutn=4 if streams == 2 else 3, vit_streams=streams)
     x, y, noise, nseed, coords = make_inputs(ctx)
     o = oracle_step(ctx, mode, x, 14, y, nseed, coords, fac_index=14)
     e = engine_step(ctx, mode, x, 14, y, noise, coords, fac_index=14, fused=fused)
