@@ -127,7 +127,8 @@ def clip_guided_diffusion(
     engine = GuidedStepB200(unet_cfg, unet_sd, vit_cfg, clip_sd, batch=local_b, height=H, width=W, num_cutouts=num_cutouts,
                             max_prompts=target_embeds.shape[0], clip_guidance_scale=clip_guidance_scale, tv_scale=tv_scale,
                             range_scale=range_scale, sat_scale=sat_scale, use_magnitude=use_magnitude, device=device, rank=rank,
-                            world_size=world_size)
+                            world_size=world_size,
+                            cutn_variants=CondFnB200.progressive_counts(num_cutouts) if progressive_cutout else ())
     engine.set_targets(target_embeds, weights)
     make_cutouts = MakeCutouts(cut_size=vit_cfg.input_resolution, num_cutouts=num_cutouts, cutout_size_power=cutout_power, use_augs=use_augs)
     if cached_cutouts:

@@ -348,7 +348,7 @@ static bool attn_use_mma() {
   }
   return !off;
 }
-int attn_bwd_num_launches(const CgdOp& op) { return attn_use_small(op.i[2]) ? 1 : 3; }
+int attn_bwd_num_launches(const CgdOp& op) { return attn_use_small(op.i[2]) ? 1 : (attn_use_mma() ? 2 : 3); }
 
 int launch_attn_fwd(const CgdOp& op, cudaStream_t st) {
   AttnArgs a{};

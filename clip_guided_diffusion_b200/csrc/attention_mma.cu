@@ -6,7 +6,7 @@
 // History (profiles/r01_launches_cfg2_step_v7_warm.csv): the same math as batched tcgen05 GEMMs (S and P materialised, K = 64 per
 // GEMM, explicit transposes, row softmax kernels) cost ~1.3 ms per step in ~110 launches of 7 - 66 TFLOP/s; the fp32 CUDA-core
 // flash kernels before that 4.6 ms.  Structure of the backward (as in attention.cu): delta = rowsum(dO * O); one kernel per key
-// tile accumulates dK, dV over the query tiles; one kernel per query tile accumulates dQ over the key tiles.
+// tile accumulates dK, dV over the query tiles, one CTA per query tile accumulates dQ over the key tiles (same launch).
 #include <cuda_fp16.h>
 
 #include "attn_mma.cuh"
@@ -181,17 +181,15 @@ __device__ __forceinline__ void am_p_ds(float (&s)[8][4], float (&dp)[8][4], flo
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV per key tile
-__global__ void __launch_bounds__(128) attn_mma_bwd_dkv_kernel(const AttnMmaArgs a) {
-  extern __shared__ __align__(16) __half am_dyn[];  // K | V | Q0 | Q1 | dO0 | dO1 | P | dS
+__device__ __forceinline__ void attn_mma_bwd_dkv_body(const AttnMmaArgs& a, __half* am_dyn, int tile_x) {
+  // shared: K | V | Q0 | Q1 | dO0 | dO1 | P | dS
   __half* Ks = am_dyn;
   __half* Vs = am_dyn + AM_TILE;
   __half* Qs = am_dyn + 2 * AM_TILE;
   __half* dOs = am_dyn + 4 * AM_TILE;
   __half* Ps = am_dyn + 6 * AM_TILE;
   __half* dSs = am_dyn + 7 * AM_TILE;
-  pdl_wait();
-  pdl_launch_dependents();
-  const int k0 = blockIdx.x * AS_T, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = tile_x * AS_T, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qoff = (int64_t)b * a.qbs + (int64_t)h * a.qhs;
   const int64_t ooff = (int64_t)b * a.obs + (int64_t)h * a.ohs;
@@ -246,15 +244,13 @@ __global__ void __launch_bounds__(128) attn_mma_bwd_dkv_kernel(const AttnMmaArgs
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dQ per query tile
-__global__ void __launch_bounds__(128) attn_mma_bwd_dq_kernel(const AttnMmaArgs a) {
-  extern __shared__ __align__(16) __half am_dyn[];  // Q | dO | K0 | K1 | V0 | V1
+__device__ __forceinline__ void attn_mma_bwd_dq_body(const AttnMmaArgs& a, __half* am_dyn, int tile_x) {
+  // shared: Q | dO | K0 | K1 | V0 | V1
   __half* Qs = am_dyn;
   __half* dOs = am_dyn + AM_TILE;
   __half* Ks = am_dyn + 2 * AM_TILE;
   __half* Vs = am_dyn + 4 * AM_TILE;
-  pdl_wait();
-  pdl_launch_dependents();
-  const int q0 = blockIdx.x * AS_T, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = tile_x * AS_T, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qoff = (int64_t)b * a.qbs + (int64_t)h * a.qhs;
   const int64_t ooff = (int64_t)b * a.obs + (int64_t)h * a.ohs;
@@ -295,6 +291,16 @@ __global__ void __launch_bounds__(128) attn_mma_bwd_dq_kernel(const AttnMmaArgs 
   as_store_c(dq, a.dq + qoff + (int64_t)q0 * a.qrs, a.qrs, r0, a.T - q0, lane);
 }
 
+// One launch for both: blocks [0, tiles) accumulate dK / dV of a key tile, blocks [tiles, 2 * tiles) dQ of a query tile.  The
+// two halves are independent and each runs four warps per CTA, so side by side they fill the SMs twice as well as back to back.
+__global__ void __launch_bounds__(128) attn_mma_bwd_kernel(const AttnMmaArgs a, int tiles) {
+  extern __shared__ __align__(16) __half am_dyn[];
+  pdl_wait();
+  pdl_launch_dependents();
+  if ((int)blockIdx.x < tiles) attn_mma_bwd_dkv_body(a, am_dyn, (int)blockIdx.x);
+  else attn_mma_bwd_dq_body(a, am_dyn, (int)blockIdx.x - tiles);
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static void am_args(const CgdOp& op, AttnMmaArgs& a, bool bwd) {
   a.B = (int)op.i[0]; a.heads = (int)op.i[1]; a.T = (int)op.i[2];
@@ -319,18 +325,16 @@ int launch_attn_mma_fwd(const CgdOp& op, cudaStream_t st) {
 int launch_attn_mma_bwd(const CgdOp& op, cudaStream_t st) {
   AttnMmaArgs a{};
   am_args(op, a, true);
-  constexpr int smem_kv = 8 * AM_TILE * (int)sizeof(__half), smem_q = 6 * AM_TILE * (int)sizeof(__half);
+  constexpr int smem = 8 * AM_TILE * (int)sizeof(__half);  // the dK / dV half needs 8 tiles, the dQ half 6
   static bool set = false;
   if (!set) {
-    CGD_CUDA(cudaFuncSetAttribute(attn_mma_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
-    CGD_CUDA(cudaFuncSetAttribute(attn_mma_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
+    CGD_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     set = true;
   }
   const int64_t rows = (int64_t)a.B * a.heads * a.T;
   CGD_CUDA(launch_pdl(attn_mma_delta_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, st, a));
-  const dim3 grid((unsigned)ceil_div(a.T, AS_T), a.heads, a.B);
-  CGD_CUDA(launch_pdl(attn_mma_bwd_dkv_kernel, grid, dim3(128), smem_kv, st, a));
-  CGD_CUDA(launch_pdl(attn_mma_bwd_dq_kernel, grid, dim3(128), smem_q, st, a));
+  const int tiles = (int)ceil_div(a.T, AS_T);
+  CGD_CUDA(launch_pdl(attn_mma_bwd_kernel, dim3((unsigned)(2 * tiles), a.heads, a.B), dim3(128), smem, st, a, tiles));
   return 0;
 }
 

@@ -94,6 +94,25 @@ __device__ __forceinline__ float silu_grad_f(float v) {
   return s * (1.f + v * (1.f - s));
 }
 
+// ---------------------------------------------------------------- global-memory barrier among co-resident CTAs
+// bar[0] = arrival count (returns to 0), bar[1] = generation (only ever incremented): reusable across launches / graph replays
+// without a reset.  Called by ONE thread per CTA after a block-level barrier; acquire / release atomics instead of
+// __threadfence(): the three MEMBAR.SC.GPU of a fence-based version cost ~5 us per barrier on B200 (each invalidates the L1),
+// which made a 148-CTA barrier ~7 us (profiles/r01_gn_microbench_v2.txt: 14.5 us for a 1 MB GroupNorm).
+__device__ __forceinline__ void global_barrier_arrive_wait(unsigned int* bar, unsigned int n) {
+  unsigned int gen, old, cur;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");  // before arriving: cannot advance yet
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+  if (old == n - 1u) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
+  } else {
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
+    } while (cur == gen);
+  }
+}
+
 struct __align__(16) half8 {
   __half2 a, b, c, d;
 };

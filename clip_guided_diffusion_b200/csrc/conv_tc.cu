@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "conv_splitk.cuh"
 #include "conv_tc.cuh"
 #include "pdl.cuh"
 #include "tc_ptx.cuh"
@@ -165,6 +166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           *reinterpret_cast<float4*>(ws + c + j) =
               make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
       }
+      if (p.fuse_reduce) splitk_fused_reduce<BN>(p, mt, (int)blockIdx.y, (int)gridDim.y, (int)blockIdx.z, r, n, h, w, row_ok, threadIdx.x == 64);
     } else {
       const int64_t o_off = (int64_t)n * p.out_sn + (int64_t)h * p.out_sh + (int64_t)w * p.out_sw;
       const int64_t r_off = (int64_t)n * p.res_sn + (int64_t)h * p.res_sh + (int64_t)w * p.res_sw;
@@ -380,6 +382,7 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   if (!p.out_f32 && p.out_sc == 1) CGD_CHECK_ARG(op.i[10] % 8 == 0 && op.i[11] % 8 == 0 && op.i[12] % 8 == 0, "conv: fp16 out strides must be multiples of 8");
   if (p.res) CGD_CHECK_ARG(op.i[13] % 8 == 0 && op.i[14] % 8 == 0 && op.i[15] % 8 == 0 && ((uintptr_t)p.res % 16) == 0, "conv: residual must be 16-byte aligned with strides %% 8 == 0");
   if (p.splits > 1) CGD_CHECK_ARG(p.ws != nullptr, "conv: split-K needs a workspace");
+  p.sk_bar = reinterpret_cast<unsigned int*>(op.p[6]);
   L.BN = (int)BN;
   L.impl = (int)op.i[18];
   L.A = reinterpret_cast<const __half*>(op.p[0]);
@@ -427,6 +430,13 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
     r = enc(&L.tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, op.p[1], dims4, strides4, box4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W half) failed with %d", (int)r);
+  }
+  // split-K reduction inside the conv kernel: needs the barrier buffer and every CTA of the launch resident at once
+  {
+    const int64_t units = conv_use_pair_kernel(L) ? (int64_t)((L.m_tiles + 1) / 2) * L.n_tiles * p.splits : (int64_t)L.m_tiles * L.n_tiles * p.splits;
+    p.fuse_reduce = (p.splits > 1 && p.sk_bar != nullptr && units <= (conv_use_pair_kernel(L) ? 74 : 148)) ? 1 : 0;
+    const char* e = getenv("CGD_CONV_FUSE_REDUCE");  // opt-in: see conv_splitk.cuh
+    if (!(e && e[0] == '1')) p.fuse_reduce = 0;
   }
   // pair-kernel epilogue through shared memory + TMA tensor stores: same 4-D box geometry as the A operand, so rows outside
   // the image are clipped by the TMA unit; needs fp16 channel-contiguous output and whole 64-channel chunks
@@ -495,7 +505,7 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
     default: set_error("conv: unsupported BN %d", L.BN); return -1;
   }
   if (rc) return rc;
-  if (L.p.splits > 1) {
+  if (L.p.splits > 1 && !L.p.fuse_reduce) {
     const int64_t total = (int64_t)L.m_tiles * BM * ((L.p.Cout + 3) / 4);
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 8);
     CGD_CUDA(launch_pdl(conv_splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, L.p, L.m_tiles));
@@ -503,6 +513,6 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
   return 0;
 }
 
-int conv_tc_num_launches(const ConvTcLaunch& L) { return (L.impl != 1 && L.p.splits > 1) ? 2 : 1; }
+int conv_tc_num_launches(const ConvTcLaunch& L) { return (L.impl != 1 && L.p.splits > 1 && !L.p.fuse_reduce) ? 2 : 1; }
 
 }  // namespace cgd

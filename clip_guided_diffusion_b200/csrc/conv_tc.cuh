@@ -17,6 +17,8 @@ struct ConvTcParams {
   int b_batched;                     // B operand indexed by the tile's (h, n) (batched GEMM: attention)
   int ws_rows;                       // rows per split in the split-K workspace (= even-rounded m_tiles * 128)
   int epi_tma;                       // pair kernel: outputs leave through shared memory + TMA tensor stores (fp16, Cout % 64 == 0)
+  unsigned int* sk_bar;              // split-K: 2 u32 per (128-pixel tile, channel tile), see conv_splitk.cuh
+  int fuse_reduce;                   // split-K partials are reduced by the conv kernel itself (all CTAs of the launch co-resident)
   const void* pf_ptr;                // next conv's packed weights: prefetched into L2 by the idle epilogue warps (0 = none)
   int64_t pf_bytes;
   int dbg;                           // CGD_CONV_DBG (profiling experiments only): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue stores

@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "conv_splitk.cuh"
 #include "conv_tc.cuh"
 #include "pdl.cuh"
 #include "tc_ptx.cuh"
@@ -318,6 +319,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               *reinterpret_cast<float4*>(ws + c + j) =
                   make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
+        if (p.fuse_reduce) splitk_fused_reduce<BN>(p, tl.mt, tl.n_tile, n_tiles, tl.split, r, n, h, w, row_ok, threadIdx.x == 64);
       } else {
         const int64_t o_off = (int64_t)n * p.out_sn + (int64_t)h * p.out_sh + (int64_t)w * p.out_sw;
         const int64_t r_off = (int64_t)n * p.res_sn + (int64_t)h * p.res_sh + (int64_t)w * p.res_sw;

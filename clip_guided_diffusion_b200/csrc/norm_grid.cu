@@ -23,7 +23,7 @@ namespace cgd {
 
 constexpr int kGngConsumers = 512;             // warps 0..15
 constexpr int kGngThreads = kGngConsumers + 32; // + producer warp 16
-constexpr int kGngStages = 8;
+constexpr int kGngStages = 8;                  // x 16 KB = 128 KB of bulk copies in flight per SM
 constexpr int kGngStageBytes = 16384;          // upper bound; the used part is NT * R * C * 2
 constexpr int kGngBarId = 1;                   // named barrier of the consumer threads
 
@@ -32,20 +32,8 @@ __device__ __forceinline__ void gng_sync() { named_bar_sync(kGngBarId, kGngConsu
 // Generation-counted barrier over all CTAs of the grid (consumer threads only).  bar[0] = arrival count (returns to 0),
 // bar[1] = generation (only ever incremented), so the buffer needs no reset between launches or CUDA-graph replays.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
-  gng_sync();
-  if (threadIdx.x == 0) {
-    volatile unsigned int* vgen = bar + 1;
-    const unsigned int gen = *vgen;  // read before arriving: the generation cannot advance until this CTA has arrived
-    __threadfence();                 // cumulative: publishes the partials written by this CTA's other threads (barrier above)
-    if (atomicAdd(bar, 1u) == nblocks - 1u) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      while (*vgen == gen) __nanosleep(40);
-    }
-    __threadfence();
-  }
+  gng_sync();  // every consumer's partial-sum stores precede thread 0's release below (cumulativity through the barrier)
+  if (threadIdx.x == 0) global_barrier_arrive_wait(bar, nblocks);
   gng_sync();
 }
 
@@ -114,10 +102,9 @@ struct GngRing {
 // Producer warp: `passes` trips over pixels [p0, p1) of the NT source tensors (row strides ld[t] elements).
 template <int NT>
 __device__ __forceinline__ void gng_produce(const GngRing& rg, const __half* const (&src)[NT], const int64_t (&ld)[NT], int C, int p0, int p1,
-                                            int passes) {
+                                            int passes, uint32_t& cnt) {
   const int lane = threadIdx.x & 31;
   const int n_it = (p1 - p0 + rg.R - 1) / rg.R;
-  uint32_t cnt = 0;
   for (int pass = 0; pass < passes; ++pass) {
     for (int it = 0; it < n_it; ++it, ++cnt) {
       const int stage = cnt % kGngStages;
@@ -209,7 +196,8 @@ gn_fwd_grid_kernel(const __half* __restrict__ x, const float* __restrict__ gamma
   if (threadIdx.x >= kGngConsumers) {
     const __half* const src[1] = {xn};
     const int64_t ld[1] = {ldx};
-    gng_produce<1>(rg, src, ld, C, p0, p1, 2);
+    uint32_t pcnt = 0;
+    gng_produce<1>(rg, src, ld, C, p0, p1, 2, pcnt);
     return;
   }
   const int col = threadIdx.x % V, pl = threadIdx.x / V;
@@ -282,14 +270,18 @@ gn_fwd_grid_kernel(const __half* __restrict__ x, const float* __restrict__ gamma
 __global__ void __launch_bounds__(kGngThreads, 1)
 gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const float* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ emb,
-                   __half* __restrict__ dx, float* __restrict__ partials, unsigned int* __restrict__ bar, int HW, int C, int64_t ld_dy,
-                   int64_t ldx, int64_t ld_dx, int Gn, int silu, int accumulate) {
+                   __half* __restrict__ dx, float* __restrict__ partials, unsigned int* __restrict__ bar, __half* __restrict__ tmp, int HW,
+                   int C, int64_t ld_dy, int64_t ldx, int64_t ld_dx, int Gn, int silu, int accumulate) {
+  // `tmp` (optional scratch, dense [N, HW, C] fp16): the first trip stores d xhat = dy * silu'(v) * d v / d xhat once -- the fp16
+  // tensor the reference's autograd holds between SiLU.backward and GroupNorm.backward -- and the second trip streams it back
+  // instead of dy, so SiLU' (2 MUFU + ~10 FP32 ops per element) is not recomputed.  Each CTA re-reads only what it wrote.
   extern __shared__ uint8_t gng_dyn[];
   __shared__ float red_s[kGngConsumers * 8], red_q[kGngConsumers * 8];
   __shared__ float gs[32], gq[32];
   __shared__ double fa[32], fb[32];
   __shared__ float s_m1[32], s_m2[32];
-  __shared__ __align__(8) uint64_t bars[2 * kGngStages];
+  __shared__ __align__(8) uint64_t bars[2 * kGngStages + 1];
+  uint64_t* trip1_done = &bars[2 * kGngStages];
   const int n = blockIdx.x / Gn, chunk = blockIdx.x % Gn;
   const int V = C / 8, PP = kGngConsumers / V;
   const int cpg = C / 32;
@@ -297,13 +289,28 @@ gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
   const int p0 = min(HW, chunk * ppc), p1 = min(HW, p0 + ppc);
   GngRing rg;
   gng_ring_init(rg, gng_dyn, bars, C, 2);
+  if (threadIdx.x == 0) {
+    mbar_init(trip1_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   pdl_wait();
   pdl_launch_dependents();
+  __half* tmp_n = tmp ? tmp + (int64_t)n * HW * C : nullptr;
   if (threadIdx.x >= kGngConsumers) {
     const __half* const src[2] = {dy + (int64_t)n * HW * ld_dy, x + (int64_t)n * HW * ldx};
     const int64_t ld[2] = {ld_dy, ldx};
-    gng_produce<2>(rg, src, ld, C, p0, p1, 2);
+    uint32_t pcnt = 0;
+    if (!tmp) {
+      gng_produce<2>(rg, src, ld, C, p0, p1, 2, pcnt);
+    } else {
+      gng_produce<2>(rg, src, ld, C, p0, p1, 1, pcnt);
+      if ((threadIdx.x & 31) == 0) mbar_wait(trip1_done, 0);  // the consumers' d xhat stores of this CTA's range are visible
+      __syncwarp();
+      const __half* const src2[2] = {tmp_n, x + (int64_t)n * HW * ldx};
+      const int64_t ld2[2] = {C, ldx};
+      gng_produce<2>(rg, src2, ld2, C, p0, p1, 1, pcnt);
+    }
     return;
   }
   const int col = threadIdx.x % V, pl = threadIdx.x / V;
@@ -329,7 +336,7 @@ gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   uint32_t cnt = 0;
-  gng_consume<2>(rg, cnt, p0, p1, col, pl, PP, active, [&](int, const half8(&v)[2]) {
+  gng_consume<2>(rg, cnt, p0, p1, col, pl, PP, active, [&](int p, const half8(&v)[2]) {
     float d[8], a[8];
     unpack8(v[0], d);
     unpack8(v[1], a);
@@ -339,11 +346,23 @@ gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
       if (silu) dv *= silu_grad_f(fmaf(a[j], rs[j] * G[j], Bc[j]));
       const float dxh = dv * G[j];
       const float xh = (a[j] - mu[j]) * rs[j];
-      s[j] += dxh;
+      d[j] = dxh;
       q[j] = fmaf(dxh, xh, q[j]);
     }
+    if (tmp_n) {
+      const half8 h = pack8(d);
+      st8(tmp_n + (int64_t)p * C + col * 8, h);
+      unpack8(h, d);  // the statistics use the rounded values the second trip will read
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += d[j];
   });
+  if (tmp_n) {  // generic-proxy global stores -> async-proxy (cp.async.bulk) reads by this CTA's producer warp
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+  }
   gng_block_reduce(s, q, C, col, pl, PP, active, red_s, red_q, gs, gq);
+  if (tmp_n && threadIdx.x == 0) mbar_arrive(trip1_done);  // after the barriers inside the reduce: every consumer has fenced
   if (threadIdx.x < 32) {
     float* o = partials + (((int64_t)n * Gn + chunk) * 32 + threadIdx.x) * 2;
     o[0] = gs[threadIdx.x];
@@ -372,9 +391,11 @@ gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
     unpack8(v[1], a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float dv = d[j];
-      if (silu) dv *= silu_grad_f(fmaf(a[j], rs[j] * G[j], Bc[j]));
-      const float dxh = dv * G[j];
+      float dxh = d[j];  // with `tmp`: d xhat itself
+      if (!tmp_n) {
+        if (silu) dxh *= silu_grad_f(fmaf(a[j], rs[j] * G[j], Bc[j]));
+        dxh *= G[j];
+      }
       const float xh = (a[j] - mu[j]) * rs[j];
       const float r = rs[j] * (dxh - m1[j] - xh * m2[j]);
       o[j] = accumulate ? o[j] + r : r;
@@ -385,6 +406,7 @@ gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
 
 // ------------------------------------------------------------------------------------------------ host
 constexpr int kGngDynSmem = kGngStages * kGngStageBytes + 128;
+constexpr int kGngCtasPerSm = 1;  // measured: two CTAs per SM (56 registers, 4 stages) ran 1.4 - 1.9x SLOWER (296-way barrier, spills)
 
 static int gng_check(const char* what, int64_t N, int64_t HW, int64_t C, int64_t Gn) {
   CGD_CHECK_ARG(N > 0 && HW > 0, "%s: bad dims", what);
@@ -395,9 +417,17 @@ static int gng_check(const char* what, int64_t N, int64_t HW, int64_t C, int64_t
     CGD_CUDA(cudaGetDevice(&dev));
     CGD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  // the grid barrier needs every CTA resident: one 512-thread CTA per SM
-  CGD_CHECK_ARG(Gn >= 1 && N * Gn <= sms, "%s: %lld x %lld CTAs exceed the %d SMs (grid barrier needs a resident grid)", what, (long long)N,
-                (long long)Gn, sms);
+  // the grid barrier needs every CTA resident: one 544-thread CTA per SM
+  CGD_CHECK_ARG(Gn >= 1 && N * Gn <= kGngCtasPerSm * sms, "%s: %lld x %lld CTAs exceed %d per SM x %d SMs (grid barrier needs a resident grid)",
+                what, (long long)N, (long long)Gn, kGngCtasPerSm, sms);
+  return 0;
+}
+template <typename K>
+static int gng_prepare(K kernel) {
+  CGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGngDynSmem));
+  int occ = 0;
+  CGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kGngThreads, kGngDynSmem));
+  CGD_CHECK_ARG(occ >= kGngCtasPerSm, "groupnorm grid kernel: only %d CTA(s) per SM fit, the grid barrier assumes %d", occ, kGngCtasPerSm);
   return 0;
 }
 
@@ -407,7 +437,7 @@ int launch_gn_fwd_grid(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[4] && op.p[5] && op.p[6] && op.p[7], "gn_fwd_grid: bad args");
   static bool set = false;
   if (!set) {
-    CGD_CUDA(cudaFuncSetAttribute(gn_fwd_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGngDynSmem));
+    if (int rc = gng_prepare(gn_fwd_grid_kernel)) return rc;
     set = true;
   }
   CGD_CUDA(launch_pdl(gn_fwd_grid_kernel, dim3((unsigned)(N * Gn)), dim3(kGngThreads), kGngDynSmem, st, (const __half*)op.p[0], (const float*)op.p[1],
@@ -424,12 +454,12 @@ int launch_gn_bwd_grid(const CgdOp& op, cudaStream_t st) {
                 "gn_bwd_grid: bad args");
   static bool set = false;
   if (!set) {
-    CGD_CUDA(cudaFuncSetAttribute(gn_bwd_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGngDynSmem));
+    if (int rc = gng_prepare(gn_bwd_grid_kernel)) return rc;
     set = true;
   }
   CGD_CUDA(launch_pdl(gn_bwd_grid_kernel, dim3((unsigned)(N * Gn)), dim3(kGngThreads), kGngDynSmem, st, (const __half*)op.p[0], (const __half*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (const float*)op.p[4], (const float*)op.p[5], (__half*)op.p[6],
-                      (float*)op.p[7], (unsigned int*)op.p[8], (int)HW, (int)C, ld_dy, ldx, ld_dx, (int)Gn, (int)(op.flags & 1),
+                      (float*)op.p[7], (unsigned int*)op.p[8], (__half*)op.p[9], (int)HW, (int)C, ld_dy, ldx, ld_dx, (int)Gn, (int)(op.flags & 1),
                       (int)((op.flags & 2) ? 1 : 0)));
   return 0;
 }

@@ -108,7 +108,8 @@ class GuidedStepB200:
     def __init__(self, unet_cfg: UNetConfig, unet_sd: dict, vit_cfg: ViTConfig = None, vit_sd: dict = None, *, batch: int,
                  height: int = None, width: int = None, num_cutouts: int = 16, max_prompts: int = 1, clip_guidance_scale=1000.0,
                  tv_scale=150.0, range_scale=50.0, sat_scale=0.0, use_magnitude=False, device="cuda", seed_scale=16.0,
-                 vit_grad_scale=1.0, conv_impl=0, rank: int = 0, world_size: int = 1, use_graph: bool = True, vit_streams: int = 1):
+                 vit_grad_scale=1.0, conv_impl=0, rank: int = 0, world_size: int = 1, use_graph: bool = True, vit_streams: int = 1,
+                 cutn_variants: tuple = ()):
         self.device = th.device(device)
         self.B = batch
         self.rank, self.world = rank, world_size
@@ -151,15 +152,25 @@ class GuidedStepB200:
             self.dx_direct = p.new(n3, "f", "dx_direct")
             self.fg_ws = p.new(128, "f", "final_grad_ws")
             self.vit = ViTB200(vit_cfg, vit_sd, n_images=cutn * B, device=device, plan=p, parts=vit_streams)
-            p.mark("cut_fwd")
-            p.emit("CUTOUTS_FWD", i=[B, H, W, cutn, cs, ps, kp], f=[*CLIP_MEAN, *CLIP_STD], p=[(self.x_inb, 0), (self.coords, 0), (self.vit.patches, 0)],
-                   tag="make_cutouts+normalize")
-            p.mark("sph")
-            p.emit("SPHERICAL", i=[cutn, B, self.P, D], f=[self.scales["cgs"], self.vit_grad_scale],
-                   p=[(self.vit.embeds, 0), (self.targets, 0), (self.weights, 0), (self.vit.d_embeds, 0), (self.loss, 0)], tag="spherical_dist_loss")
-            p.mark("cut_bwd")
-            p.emit("CUTOUTS_BWD", i=[B, H, W, cutn, cs, ps, kp], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
-                   p=[(self.vit.d_patches, 0), (self.coords, 0), (self.g_clip, 0)], tag="d_make_cutouts")
+            # further cutout counts of the same engine (progressive_cutout, cgd/cgd.py:167-175): own activations and op ranges
+            # ("...@c" marks), shared packed weights; the default count keeps the un-suffixed marks
+            self.vits = {cutn: self.vit}
+            for c in sorted(set(int(v) for v in cutn_variants) - {cutn}):
+                if not 0 < c < cutn:
+                    raise ValueError(f"cutn_variants must lie in (0, {cutn}), got {c}")
+                self.vits[c] = ViTB200(vit_cfg, vit_sd, n_images=c * B, device=device, plan=p, parts=vit_streams, suffix=f"@{c}", share=self.vit)
+            for c in sorted(self.vits, key=lambda v: v == cutn):  # the default count last: its ranges end at "guide"
+                sfx, vt = ("" if c == cutn else f"@{c}"), self.vits[c]
+                p.mark("cut_fwd" + sfx)
+                p.emit("CUTOUTS_FWD", i=[B, H, W, c, cs, ps, kp], f=[*CLIP_MEAN, *CLIP_STD], p=[(self.x_inb, 0), (self.coords, 0), (vt.patches, 0)],
+                       tag="make_cutouts+normalize")
+                p.mark("sph" + sfx)
+                p.emit("SPHERICAL", i=[c, B, self.P, D], f=[self.scales["cgs"], self.vit_grad_scale],
+                       p=[(vt.embeds, 0), (self.targets, 0), (self.weights, 0), (vt.d_embeds, 0), (self.loss, 0)], tag="spherical_dist_loss")
+                p.mark("cut_bwd" + sfx)
+                p.emit("CUTOUTS_BWD", i=[B, H, W, c, cs, ps, kp], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
+                       p=[(vt.d_patches, 0), (self.coords, 0), (self.g_clip, 0)], tag="d_make_cutouts")
+                p.mark("cut_end" + sfx)
             p.mark("guide")
             p.emit("GUIDE_GRAD", i=[B, H, W, IN_PAD], f=[self.scales["tv"], self.scales["rng"], self.scales["sat"], self.seed_scale],
                    p=[(self.x_inb, 0), (self.x0, 0), (self.g_clip, 0), (self.sc, 0), (self.unet.seed, 0), (self.dx_direct, 0), (self.loss, B)],
@@ -259,13 +270,14 @@ class GuidedStepB200:
             sc = diffusion.scalar_table(self._cur_t, fac_index)
             self._push_scalars(sc)
             self.plan.run_range("pmv", "cond")
-        assert len(coords) == self.cutn, "cutout count is fixed per engine"
-        self.v(self.coords, (self.cutn, 3)).copy_(th.tensor(coords, dtype=th.int32), non_blocking=True)
-        self.plan.run_range("cut_fwd", "sph")
-        self._run_vit("fwd")
-        self.plan.run_range("sph", "cut_bwd")
-        self._run_vit("bwd")
-        for a, b in (("cut_bwd", "guide"), ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g")):
+        cutn = len(coords)
+        sfx = self._sfx(cutn)
+        self.v(self.coords, (self.cutn, 3))[:cutn].copy_(th.tensor(coords, dtype=th.int32), non_blocking=True)
+        self.plan.run_range("cut_fwd" + sfx, "sph" + sfx)
+        self._run_vit("fwd", None, cutn)
+        self.plan.run_range("sph" + sfx, "cut_bwd" + sfx)
+        self._run_vit("bwd", None, cutn)
+        for a, b in (("cut_bwd" + sfx, "cut_end" + sfx), ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g")):
             self.plan.run_range(a, b)
         return self.img(self.g)
 
@@ -287,15 +299,23 @@ class GuidedStepB200:
         return (isinstance(cond_fn, CondFnB200) and cond_fn.engine is self and not clip_denoised and denoised_fn is None
                 and cond_fn.fusable())
 
-    def _run_all(self, mode, runner=None):
+    def _sfx(self, cutn):
+        if cutn is None or cutn == self.cutn:
+            return ""
+        if cutn not in self.vits:
+            raise ValueError(f"engine built for cutout counts {sorted(self.vits)}, got {cutn}")
+        return f"@{cutn}"
+
+    def _run_all(self, mode, runner=None, cutn=None):
         pr = runner or self.plan.run_range
+        sfx = self._sfx(cutn)
         pr("unet_emb", "unet_bwd")
         pr("pmv", "cond")
-        pr("cut_fwd", "sph")
-        self._run_vit("fwd", pr)
-        pr("sph", "cut_bwd")
-        self._run_vit("bwd", pr)
-        pr("cut_bwd", "guide")
+        pr("cut_fwd" + sfx, "sph" + sfx)
+        self._run_vit("fwd", pr, cutn)
+        pr("sph" + sfx, "cut_bwd" + sfx)
+        self._run_vit("bwd", pr, cutn)
+        pr("cut_bwd" + sfx, "cut_end" + sfx)
         pr("guide", "final")
         pr("unet_bwd", "unet_end")
         pr("final", "upd_anc_g")
@@ -304,11 +324,11 @@ class GuidedStepB200:
         else:
             pr("upd_ddim_g", "upd_ddim")
 
-    def _run_vit(self, which, pr=None):
+    def _run_vit(self, which, pr=None, cutn=None):
         """CLIP forward / backward: one op range, or one per batch slice on parallel streams (fork / join around the current
         stream; inside CUDA-graph capture this becomes parallel branches of the graph)."""
         pr = pr or self.plan.run_range
-        ranges = self.vit.part_ranges(which)
+        ranges = self.vits[self.cutn if cutn is None else cutn].part_ranges(which)
         if len(ranges) == 1 or not self._side_streams or pr != self.plan.run_range:
             for a, b in ranges:
                 pr(a, b)
@@ -350,9 +370,9 @@ class GuidedStepB200:
         o += n
         self.h2d_bytes += SC["COUNT"] * 4 + self.B * 4
         if self.cutn:
-            n = self.cutn * 12
+            n = len(coords) * 12
             st[o:o + n].view(th.int32).copy_(th.tensor(coords, dtype=th.int32).view(-1))
-            self.v(self.coords).view(th.uint8).copy_(st[o:o + n], non_blocking=True)
+            self.v(self.coords).view(th.uint8)[:n].copy_(st[o:o + n], non_blocking=True)
             self.h2d_bytes += n
 
     def fused_step(self, diffusion, mode, t_index, img, y, cond_fn, eta=0.0) -> dict:
@@ -366,21 +386,23 @@ class GuidedStepB200:
         # RNG order: ancestral draws before cond_fn, DDIM after (values are identical either way: the generator is only
         # consumed by this draw within a step; cutout windows come from the CPU generator)
         self.draw_noise()
-        self.replay(mode)
+        self.replay(mode, len(coords) if self.cutn else None)
         return {"sample": self.img(self.sample).clone(), "pred_xstart": self.img(self.x0).clone()}
 
-    def replay(self, mode):
+    def replay(self, mode, cutn=None):
+        if cutn == self.cutn:
+            cutn = None
         if not self.use_graph:
-            self._run_all(mode)
+            self._run_all(mode, None, cutn)
             return
-        g = self._graphs.get(mode)
+        g = self._graphs.get((mode, cutn))
         if g is None:
-            self._run_all(mode)  # warm-up: sets kernel attributes, touches every buffer
+            self._run_all(mode, None, cutn)  # warm-up: sets kernel attributes, touches every buffer
             th.cuda.synchronize()
             g = th.cuda.CUDAGraph()
             with th.cuda.graph(g):
-                self._run_all(mode)
-            self._graphs[mode] = g
+                self._run_all(mode, None, cutn)
+            self._graphs[(mode, cutn)] = g
         g.replay()
 
     def losses(self) -> dict:
@@ -401,7 +423,23 @@ class CondFnB200:
         self.cached_cutouts, self.reduce_clip, self.progressive_cutout = cached_cutouts, reduce_clip, progressive_cutout
         self.current_timestep = diffusion.num_timesteps - 1  # cgd/cgd.py:265
         if progressive_cutout:
-            raise NotImplementedError("progressive_cutout changes the per-step cutout count; one engine has a fixed cutn (SURVEY 8f next)")
+            missing = set(self.progressive_counts(engine.cutn)) - set(engine.vits)
+            if missing:
+                raise ValueError(f"progressive_cutout needs an engine built with cutn_variants={self.progressive_counts(engine.cutn)}")
+
+    @staticmethod
+    def progressive_counts(num_cutouts: int) -> tuple:
+        """the three cutout counts of the reference's schedule (cgd/cgd.py:167-175)"""
+        return (max(4, num_cutouts // 4), max(8, num_cutouts // 2), num_cutouts)
+
+    def current_cutn(self) -> int:
+        n = self.engine.cutn
+        if not self.progressive_cutout:
+            return n
+        total = self.diffusion.num_timesteps
+        pct = (total - self.current_timestep) / total
+        lo, mid, hi = self.progressive_counts(n)
+        return lo if pct < 0.3 else (mid if pct < 0.7 else hi)
 
     def fusable(self):
         return not self.reduce_clip
@@ -410,7 +448,7 @@ class CondFnB200:
         self.current_timestep -= 1
 
     def next_coords(self, H, W):
-        return self.make_cutouts.coords_for(H, W, use_cache=self.cached_cutouts, num_cutouts_override=self.engine.cutn)
+        return self.make_cutouts.coords_for(H, W, use_cache=self.cached_cutouts, num_cutouts_override=self.current_cutn())
 
     def __call__(self, x, t, out, y=None):
         eng = self.engine

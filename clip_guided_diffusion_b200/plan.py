@@ -161,7 +161,7 @@ N_SMS = 148  # B200
 
 
 def gn_grid_ctas(N: int, HW: int, C: int) -> int:
-    """CTAs per image of the persistent GroupNorm kernels (csrc/norm_grid.cu): one 512-thread CTA per SM, every CTA at least
+    """CTAs per image of the persistent GroupNorm kernels (csrc/norm_grid.cu): one resident CTA per SM, every CTA at least
     one pass of its pixel lanes; 0 when the batch alone exceeds the SM count (two-pass kernels then)."""
     if C % 64 != 0 or C > 2048 or N > N_SMS:
         return 0
@@ -171,6 +171,7 @@ def gn_grid_ctas(N: int, HW: int, C: int) -> int:
 
 class Plan:
     def __init__(self, conv_impl: int = 0):
+        self._gn_scratch = None
         self.grid_gn = True  # single persistent launch with a grid barrier for the large GroupNorms (csrc/norm_grid.cu)
         self.fused_gn = True  # single-launch GroupNorm where the slab fits a cluster (csrc/norm_fused.cu)
         self.ops: list[PlanOp] = []
@@ -266,10 +267,11 @@ class Plan:
         bn = pick_bn(npad, m_tiles, kblocks)
         splits = pick_splits(m_tiles, npad // bn, kblocks, npad)
         ws = self.new(splits * ((m_tiles + 1) // 2 * 2) * 128 * npad, "f", "splitk_ws") if splits > 1 else None
+        skbar = self.new(2 * ((m_tiles + 1) // 2 * 2) * (npad // bn), "u32", "splitk_bar") if splits > 1 else None
         i = [NB, H, W, Cin, Cout, npad, taps, *x_strides, *out_strides, *(res_strides or (0, 0, 0)), bn, splits, self.conv_impl, out_sc,
              b_batch[0], b_batch[1], ldb]
         self.emit("CONV", flags=1 if out_f32 else 0, i=i,
-                  p=[x_ptr, b_ptr if b_ptr is not None else self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws)], tag=tag)
+                  p=[x_ptr, b_ptr if b_ptr is not None else self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws), self._bp(skbar)], tag=tag)
 
     @staticmethod
     def _strides(a: Act):
@@ -341,8 +343,11 @@ class Plan:
             elif gn_g:
                 bpart = self.new(N * gn_g * 64, "f", name + "_bpart")
                 bbar = self.new(2, "u32", name + "_bbar")
+                # one scratch tensor shared by every GroupNorm backward of the plan (they run one after the other)
+                if self._gn_scratch is None or self._gn_scratch.numel < N * HW * C:
+                    self._gn_scratch = self.new(N * HW * C, "h", "gn_bwd_dxhat")
                 self.emit("GN_BWD_GRID", flags=fl, i=[N, HW, C, dy.ld, x.ld, dx.ld, gn_g], f=[eps],
-                          p=common + [self._ap(dx), self._bp(bpart), self._bp(bbar)], tag="d_" + name)
+                          p=common + [self._ap(dx), self._bp(bpart), self._bp(bbar), self._bp(self._gn_scratch)], tag="d_" + name)
             else:
                 pp = max(1, 256 // (C // 8))
                 nchunk = int(min(max(1, -(-HW // (pp * 16))), max(1, 296 // N)))

@@ -63,7 +63,7 @@ class ViTB200:
     ``embeds`` (fp32 [n, D]) its output; ``d_embeds`` -> ``d_patches`` the backward."""
 
     def __init__(self, cfg: ViTConfig, state_dict: dict, n_images: int, device="cuda", conv_impl: int = 0, build_backward=True,
-                 plan: Plan = None, parts: int = 1):
+                 plan: Plan = None, parts: int = 1, suffix: str = "", share: "ViTB200" = None):
         """parts > 1 builds `parts` independent op lists over equal slices of the image batch (shared packed weights, shared
         patches / embeds buffers) so that the engine can run them on parallel streams: at 16 cutouts every ViT GEMM occupies a
         fraction of the SMs for a latency-bound ~8 us, two half-batches side by side hide each other's latency."""
@@ -72,7 +72,10 @@ class ViTB200:
         self.sd = state_dict
         self.own_plan = plan is None
         self.plan = plan or Plan(conv_impl=conv_impl)
-        self._wcache, self._ccache = {}, {}
+        # `share`: another tower on the same plan whose packed weights are reused (engines with several cutout counts:
+        # progressive_cutout, cgd/cgd.py:167-175); `suffix` keeps the range marks of the towers apart
+        self.suffix = suffix
+        self._wcache, self._ccache = (share._wcache, share._ccache) if share is not None else ({}, {})
         self._build(build_backward)
         if self.own_plan:
             self.plan.finalize(device)
@@ -96,8 +99,9 @@ class ViTB200:
 
     def part_ranges(self, which: str):
         """[(mark_a, mark_b)] of the forward ("fwd") or backward ("bwd") op range of every part"""
-        names = ["vit_" + which] + [f"vit_{which}_p{k}" for k in range(1, self.parts)]
-        ends = names[1:] + ["vit_bwd" if which == "fwd" else "vit_end"]
+        sfx = self.suffix
+        names = [f"vit_{which}{sfx}"] + [f"vit_{which}_p{k}{sfx}" for k in range(1, self.parts)]
+        ends = names[1:] + [("vit_bwd" if which == "fwd" else "vit_end") + sfx]
         return list(zip(names, ends))
 
     def _build(self, build_backward):
@@ -111,19 +115,19 @@ class ViTB200:
         saved_tape, p._tape = p._tape, []
         tapes, heads = [], []
         for k in range(self.parts):
-            p.mark("vit_fwd" if k == 0 else f"vit_fwd_p{k}")
+            p.mark(("vit_fwd" if k == 0 else f"vit_fwd_p{k}") + self.suffix)
             heads.append(self._build_forward(k, nk, build_backward))
             tapes.append(p._tape)
             p._tape = []
-        p.mark("vit_bwd")
+        p.mark("vit_bwd" + self.suffix)
         if build_backward:
             for k in range(self.parts):
                 if k:
-                    p.mark(f"vit_bwd_p{k}")
+                    p.mark(f"vit_bwd_p{k}" + self.suffix)
                 p._tape = tapes[k]
                 self._build_backward(k, nk, *heads[k])
         p._tape = saved_tape
-        p.mark("vit_end")
+        p.mark("vit_end" + self.suffix)
 
     def _build_forward(self, k, n, build_backward):
         p, cfg = self.plan, self.cfg
@@ -173,11 +177,11 @@ class ViTB200:
     def encode_patches(self, patches: th.Tensor = None) -> th.Tensor:
         if patches is not None:
             self.plan.view(self.patches, patches.shape).copy_(patches)
-        self.plan.run_range("vit_fwd", "vit_bwd")
+        self.plan.run_range("vit_fwd" + self.suffix, "vit_bwd" + self.suffix)
         return self.plan.view(self.embeds, (self.n, self.cfg.output_dim))
 
     def backward_patches(self, d_embeds: th.Tensor = None) -> th.Tensor:
         if d_embeds is not None:
             self.plan.view(self.d_embeds, d_embeds.shape).copy_(d_embeds)
-        self.plan.run_range("vit_bwd", "vit_end")
+        self.plan.run_range("vit_bwd" + self.suffix, "vit_end" + self.suffix)
         return self.plan.view(self.d_patches, (self.n, self.cfg.grid ** 2, self.cfg.kpad))

@@ -61,6 +61,8 @@ enum {
    *   with scalar stores, e.g. fp32 NCHW outputs of the UNet head / stem dgrad)
    *   i20, i21 batched-GEMM mode: element strides of the B operand per h / per n index (0, 0 = one shared weight matrix);
    *   i22 row stride of B (0 = taps*Cin).  Batched mode needs W % 256 == 0 (attention: A = Q/P/dS..., B = K/V^T/...)
+   *   p6 split-K barrier words (u32 [2 * row tiles * channel tiles], zero-initialised)|0: when given and the launch fits one wave,
+   *   the kernel reduces its own split-K partials (no second launch)
    *   flags: 1 = out is fp32 */
   CGD_OP_CONV = 1,
   /* GroupNorm(32) statistics: per (image, chunk, group) partial sum / sum of squares; the last block per image
@@ -179,6 +181,7 @@ enum {
    * i0 N i1 HW i2 C i3 ldx i4 ldy i5 Gn (CTAs per image) ; f0 eps ; flags 1 = SiLU.  C % 64 == 0 */
   CGD_OP_GN_FWD_GRID = 35,
   /* backward of the above: p0 dy p1 x p2 stats p3 gamma p4 beta p5 emb|0 p6 dx(h) p7 partials p8 barrier
+   * p9 scratch(h, dense [N,HW,C])|0: d xhat is stored once and streamed back instead of recomputing SiLU' in the apply pass
    * i0 N i1 HW i2 C i3 ld_dy i4 ldx i5 ld_dx i6 Gn ; flags 1 = SiLU, 2 = accumulate into dx */
   CGD_OP_GN_BWD_GRID = 36,
   CGD_OP__COUNT

@@ -66,7 +66,7 @@ def main():
         if kind == "CONV" and op.i[17] > 1:
             n = 2
         elif kind == "ATTN_BWD":
-            n = 1 if op.i[2] <= 64 else 3
+            n = 1 if op.i[2] <= 64 else 2
         elif kind == "FINAL_GRAD" and op.flags & 1:
             n = 2
         t = sum(v for _, v in launches[li:li + n])

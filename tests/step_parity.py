@@ -31,7 +31,7 @@ def prod_unet_cfg(ocfg):
 
 
 def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0, respacing="25", conv_impl=0, use_graph=False, P=1,
-               new_order=False, vit_streams=1):
+               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None):
     ocfg = tiny_config(image_size=image, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(image // 2,),
                        class_cond=True, use_new_attention_order=new_order)
     ounet = seeded_init_(UNetModel(ocfg)).eval()
@@ -47,10 +47,10 @@ def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0
     kw = dict(clip_guidance_scale=1000.0, tv_scale=150.0, range_scale=50.0, sat_scale=sat_scale)
     eng = pg.GuidedStepB200(prod_unet_cfg(ocfg), ounet.state_dict(), pv.ViTConfig(32, 16, 128, 2, 64), oclip.state_dict(), batch=B,
                             num_cutouts=cutn, max_prompts=P, use_magnitude=use_magnitude, device=device, conv_impl=conv_impl,
-                            use_graph=use_graph, vit_streams=vit_streams, **kw)
+                            use_graph=use_graph, vit_streams=vit_streams, cutn_variants=cutn_variants, **kw)
     eng.set_targets(targets, weights)
     return dict(ounet=ounet, oclip=oclip, odiff=odiff, pdiff=pdiff, eng=eng, targets=targets, weights=weights, kw=kw,
-                use_magnitude=use_magnitude, cutn=cutn, B=B, image=image)
+                use_magnitude=use_magnitude, cutn=run_cutn or cutn, B=B, image=image)
 
 
 def oracle_step(ctx, mode, x, t_index, y, noise_seed, coords, fac_index):
@@ -80,10 +80,11 @@ def engine_step(ctx, mode, x, t_index, y, noise, coords, fac_index, runner=None,
     eng.stage_step(sc, coords, pdiff.model_timestep(t_index), y)
     eng.img(eng.unet.x_in).copy_(x)
     eng.img(eng.noise).copy_(noise)
+    cutn = len(coords) if eng.cutn else None
     if fused:
-        eng.replay(mode)
+        eng.replay(mode, cutn)
     else:
-        eng._run_all(mode, runner)
+        eng._run_all(mode, runner, cutn)
     if eng.device.type == "cuda":
         th.cuda.synchronize()
     return dict(sample=eng.img(eng.sample).float().cpu().clone(), pred_xstart=eng.img(eng.x0).float().cpu().clone(),

@@ -45,3 +45,16 @@ def test_step_parity_vs_oracle(mode, fused, streams):
     res = compare(o, e)
     # tolerance: fp16 activations/weights vs the fp32 oracle, teacher-forced single step
     assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["eager", "graph"])
+def test_progressive_cutout_variant_vs_oracle(fused):
+    """An engine built for cutout counts (2, 4, 8) -- progressive_cutout, cgd/cgd.py:167-175 -- runs a step with 4 cutouts
+    (its own ViT activations / op ranges / CUDA graph, shared packed weights) and matches the oracle with the same 4 windows."""
+    ctx = build_tiny("cuda", conv_impl=IMPL, image=64, use_graph=True, B=1, cutn=8, cutn_variants=(2, 4, 8), run_cutn=4)
+    x, y, noise, nseed, coords = make_inputs(ctx)
+    assert len(coords) == 4
+    o = oracle_step(ctx, "ddim", x, 14, y, nseed, coords, fac_index=14)
+    e = engine_step(ctx, "ddim", x, 14, y, noise, coords, fac_index=14, fused=fused)
+    res = compare(o, e)
+    assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res

@@ -12,9 +12,42 @@ def _interp_runner(eng):
 
 
 @pytest.mark.parametrize("mode,kw", [("ancestral", {}), ("ddim", {}), ("ancestral", dict(use_magnitude=True, sat_scale=30.0)),
-                                     ("ddim", dict(B=1, P=2, cutn=2)), ("ddim", dict(B=2, cutn=4, vit_streams=2))])
+                                     ("ddim", dict(B=1, P=2, cutn=2)), ("ddim", dict(B=2, cutn=4, vit_streams=2)),
+                                     ("ancestral", dict(B=1, cutn=8, cutn_variants=(2, 4, 8), run_cutn=4))])
 def test_step_plan_matches_oracle(mode, kw):
     res = run_tiny_step_parity(device="cpu", mode=mode, runner_factory=_interp_runner, image=32, **kw)
     assert res["cos_g"] > 0.999, res
     assert res["rel_g"] < 5e-2 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res
     assert res["clip_loss_rel"] < 2e-2 and res["tv_loss_rel"] < 1e-3 and res["range_loss_rel"] < 1e-2, res
+
+
+def test_progressive_cutout_schedule():
+    """CondFnB200 follows the reference's cutout-count schedule (cgd/cgd.py:167-175) and the CPU-generator draw order."""
+    import torch as th
+    from clip_guided_diffusion_b200 import guidance as pg
+
+    class Eng:
+        cutn = 16
+        vits = {4: None, 8: None, 16: None}
+
+    class Diff:
+        num_timesteps = 100
+
+    mk = pg.MakeCutouts(224, 16)
+    cf = pg.CondFnB200(Eng(), Diff(), mk, progressive_cutout=True)
+    seen = []
+    for step in range(100):
+        seen.append(cf.current_cutn())
+        th.manual_seed(step)
+        coords = cf.next_coords(256, 256)
+        assert len(coords) == seen[-1]
+        th.manual_seed(step)
+        assert coords == mk._generate_coords(256, 256, seen[-1])  # same draws as the reference's MakeCutouts for that count
+        cf.step_done()
+    total = 100
+    want = [4 if (total - t) / total < 0.3 else (8 if (total - t) / total < 0.7 else 16) for t in range(99, -1, -1)]
+    assert seen == want
+    with pytest.raises(ValueError):
+        class Small(Eng):
+            vits = {16: None}
+        pg.CondFnB200(Small(), Diff(), mk, progressive_cutout=True)
