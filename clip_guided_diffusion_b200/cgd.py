@@ -77,6 +77,18 @@ def _encode_text(prompts, clip_model_name, device):
     return th.cat(embeds), th.tensor(weights)
 
 
+def _lpips_sd(given):
+    """LPIPS(net='vgg') weights in upstream key layout: passed in, or taken from the ``lpips`` package when it is installed"""
+    if given is not None:
+        return given
+    try:
+        import lpips  # noqa: WPS433 (optional dependency, like the reference's lazy construction at cgd/cgd.py:147-148)
+    except ImportError as e:
+        raise RuntimeError("init_scale != 0 needs the LPIPS-VGG weights: pass lpips_state_dict= (keys net.sliceK.N.*, linK.model.1.weight) "
+                           "or install the `lpips` package") from e
+    return lpips.LPIPS(net="vgg").state_dict()
+
+
 def clip_guided_diffusion(
     image_size: int = 128, num_cutouts: int = 16, prompts: "list[str]" = [], image_prompts: "list[str]" = [],
     clip_guidance_scale: int = 1000, tv_scale: float = 150, range_scale: float = 50, sat_scale: float = 0, init_scale: float = 0,
@@ -88,6 +100,7 @@ def clip_guided_diffusion(
     reduce_clip: bool = False, progressive_cutout: bool = False, cached_cutouts: bool = False,
     # --- additions of this framework (all optional)
     unet_state_dict: dict = None, clip_state_dict: dict = None, target_embeds: th.Tensor = None, weights: th.Tensor = None,
+    lpips_state_dict: dict = None,
     rank: int = 0, world_size: int = 1,
 ):
     if len(device) == 0:
@@ -96,8 +109,6 @@ def clip_guided_diffusion(
         raise RuntimeError("clip_guided_diffusion_b200 runs the sampling step on a CUDA (sm_100a) device only; there is no CPU path")
     if image_prompts:
         raise NotImplementedError("image prompts are unsupported (the reference's encode_image_prompt crashes, SURVEY quirk B5)")
-    if init_scale != 0:
-        raise NotImplementedError("LPIPS init loss (init_scale) is not part of this build (SURVEY 8f rank 3)")
     if wandb_project is not None:
         raise NotImplementedError("W&B logging is outside the hot path (SURVEY section 2)")
     th.manual_seed(seed)
@@ -128,7 +139,9 @@ def clip_guided_diffusion(
                             max_prompts=target_embeds.shape[0], clip_guidance_scale=clip_guidance_scale, tv_scale=tv_scale,
                             range_scale=range_scale, sat_scale=sat_scale, use_magnitude=use_magnitude, device=device, rank=rank,
                             world_size=world_size,
-                            cutn_variants=CondFnB200.progressive_counts(num_cutouts) if progressive_cutout else ())
+                            cutn_variants=CondFnB200.progressive_counts(num_cutouts) if progressive_cutout else (),
+                            lpips_sd=_lpips_sd(lpips_state_dict) if (init_image is not None and init_scale != 0) else None,
+                            init_scale=init_scale)
     engine.set_targets(target_embeds, weights)
     make_cutouts = MakeCutouts(cut_size=vit_cfg.input_resolution, num_cutouts=num_cutouts, cutout_size_power=cutout_power, use_augs=use_augs)
     if cached_cutouts:
@@ -142,6 +155,8 @@ def clip_guided_diffusion(
         import numpy as np
         pil = Image.open(init_image).convert("RGB").resize((image_size, image_size))
         init_tensor = th.from_numpy(np.asarray(pil)).float().div(255).permute(2, 0, 1).unsqueeze(0).mul(2).sub(1).to(device)
+        if engine.lpips is not None:  # cgd/cgd.py:147-148, 220-224
+            engine.set_init_image(init_tensor)
 
     model_kwargs = {}
     if class_cond:

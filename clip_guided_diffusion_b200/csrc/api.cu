@@ -58,6 +58,12 @@ static int dispatch(const CgdOp& op, const ConvTcLaunch* conv, cudaStream_t st) 
     case CGD_OP_GN_BWD_FUSED: return launch_gn_bwd_fused(op, st);
     case CGD_OP_GN_FWD_GRID: return launch_gn_fwd_grid(op, st);
     case CGD_OP_GN_BWD_GRID: return launch_gn_bwd_grid(op, st);
+    case CGD_OP_RELU_FWD: return launch_relu_fwd(op, st);
+    case CGD_OP_RELU_BWD: return launch_relu_bwd(op, st);
+    case CGD_OP_MAXPOOL2_FWD: return launch_maxpool2_fwd(op, st);
+    case CGD_OP_MAXPOOL2_BWD: return launch_maxpool2_bwd(op, st);
+    case CGD_OP_LPIPS_TAP: return launch_lpips_tap(op, st);
+    case CGD_OP_FILL: return launch_fill(op, st);
     case CGD_OP_LINEAR_SMALL: return launch_linear_small(op, st);
     case CGD_OP_TIMESTEP_EMB: return launch_timestep_emb(op, st);
     case CGD_OP_LABEL_ADD: return launch_label_add(op, st);

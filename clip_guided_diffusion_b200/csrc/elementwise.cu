@@ -128,7 +128,9 @@ int launch_copy(const CgdOp& op, cudaStream_t st) {
 
 // ---- layout conversion at the sampler boundary
 // fp32 NCHW [N,C,HW] -> fp16 pixel-major [N*HW, ld], channels >= C zero-filled
-__global__ void nchw_to_pm_kernel(const float* __restrict__ src, __half* __restrict__ dst, int N, int C, int64_t HW, int64_t ld, float scale) {
+// optional per-channel affine (C <= 3: the LPIPS ScalingLayer): value = (x - shift_c) * mul_c * scale
+__global__ void nchw_to_pm_kernel(const float* __restrict__ src, __half* __restrict__ dst, int N, int C, int64_t HW, int64_t ld, float scale,
+                                  float3 shift, float3 mul) {
   pdl_wait();
   pdl_launch_dependents();
   const int V = (int)(ld / 8);
@@ -141,7 +143,8 @@ __global__ void nchw_to_pm_kernel(const float* __restrict__ src, __half* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = v * 8 + j;
-      o[j] = c < C ? src[((int64_t)n * C + c) * HW + p] * scale : 0.f;
+      const float sh = c == 0 ? shift.x : (c == 1 ? shift.y : shift.z), mu = c == 0 ? mul.x : (c == 1 ? mul.y : mul.z);
+      o[j] = c < C ? (src[((int64_t)n * C + c) * HW + p] - sh) * mu * scale : 0.f;
     }
     st8(dst + pix * ld + v * 8, pack8(o));
   }
@@ -149,7 +152,7 @@ __global__ void nchw_to_pm_kernel(const float* __restrict__ src, __half* __restr
 // pixel-major (fp16 / fp32) -> fp32 NCHW, one thread per destination element (reads of a pixel's few channels hit one sector)
 template <typename T>
 __global__ void pm_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int64_t HW, int64_t ld, float scale,
-                                  int accumulate) {
+                                  int accumulate, float3 mul) {
   pdl_wait();
   pdl_launch_dependents();
   const int64_t total = (int64_t)N * C * HW;
@@ -158,14 +161,18 @@ __global__ void pm_to_nchw_kernel(const T* __restrict__ src, float* __restrict__
     const int64_t nc = idx / HW;
     const int c = (int)(nc % C);
     const int64_t n = nc / C;
-    const float v = (float)src[(n * HW + p) * ld + c] * scale;
+    const float v = (float)src[(n * HW + p) * ld + c] * scale * (c == 0 ? mul.x : (c == 1 ? mul.y : mul.z));
     dst[idx] = accumulate ? dst[idx] + v : v;
   }
 }
 int launch_nchw_to_pm(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], C = op.i[1], HW = op.i[2], ld = op.i[3];
   CGD_CHECK_ARG(N > 0 && C > 0 && HW > 0 && ld % 8 == 0 && C <= ld && op.p[0] && op.p[1], "nchw_to_pm: bad args");
-  CGD_CUDA(launch_pdl(nchw_to_pm_kernel, dim3(ew_blocks(N * HW * (ld / 8))), dim3(256), 0, st, (const float*)op.p[0], (__half*)op.p[1], (int)N, (int)C, HW, ld, op.f[0]));
+  const bool aff = (op.flags & 4) != 0;  // f1..3 shift, f4..6 multiplier per channel
+  CGD_CHECK_ARG(!aff || C <= 3, "nchw_to_pm: per-channel affine needs C <= 3");
+  CGD_CUDA(launch_pdl(nchw_to_pm_kernel, dim3(ew_blocks(N * HW * (ld / 8))), dim3(256), 0, st, (const float*)op.p[0], (__half*)op.p[1], (int)N, (int)C, HW, ld, op.f[0],
+                      aff ? make_float3(op.f[1], op.f[2], op.f[3]) : make_float3(0.f, 0.f, 0.f),
+                      aff ? make_float3(op.f[4], op.f[5], op.f[6]) : make_float3(1.f, 1.f, 1.f)));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -173,10 +180,12 @@ int launch_pm_to_nchw(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], C = op.i[1], HW = op.i[2], ld = op.i[3];
   CGD_CHECK_ARG(N > 0 && C > 0 && HW > 0 && C <= ld && op.p[0] && op.p[1], "pm_to_nchw: bad args");
   const int acc = (op.flags & 2) ? 1 : 0;
+  CGD_CHECK_ARG(!(op.flags & 4) || C <= 3, "pm_to_nchw: per-channel scale needs C <= 3");
+  const float3 mul = (op.flags & 4) ? make_float3(op.f[1], op.f[2], op.f[3]) : make_float3(1.f, 1.f, 1.f);  // per-channel multiplier
   if (op.flags & 1)
-    CGD_CUDA(launch_pdl(pm_to_nchw_kernel<float>, dim3(ew_blocks(N * C * HW)), dim3(256), 0, st, (const float*)op.p[0], (float*)op.p[1], (int)N, (int)C, HW, ld, op.f[0], acc));
+    CGD_CUDA(launch_pdl(pm_to_nchw_kernel<float>, dim3(ew_blocks(N * C * HW)), dim3(256), 0, st, (const float*)op.p[0], (float*)op.p[1], (int)N, (int)C, HW, ld, op.f[0], acc, mul));
   else
-    CGD_CUDA(launch_pdl(pm_to_nchw_kernel<__half>, dim3(ew_blocks(N * C * HW)), dim3(256), 0, st, (const __half*)op.p[0], (float*)op.p[1], (int)N, (int)C, HW, ld, op.f[0], acc));
+    CGD_CUDA(launch_pdl(pm_to_nchw_kernel<__half>, dim3(ew_blocks(N * C * HW)), dim3(256), 0, st, (const __half*)op.p[0], (float*)op.p[1], (int)N, (int)C, HW, ld, op.f[0], acc, mul));
   CGD_LAUNCH_CHECK();
   return 0;
 }

@@ -9,7 +9,7 @@
 // ring with cp.async.bulk (16 KB per stage, 128 KB in flight per SM = 19 MB over the chip, independent of the consumers'
 // registers); 512 consumer threads reduce each stage from shared memory, write per-group partial sums, meet the other CTAs
 // at a generation-counted grid barrier (every CTA is resident: grid <= SM count, one CTA per SM), fold the partials
-// themselves (fixed order, fp64: bit-identical in every CTA) and normalise the same pixel range from a second trip through
+// themselves (fixed order, compensated fp32: bit-identical in every CTA) and normalise the same pixel range from a second trip through
 // the ring, whose loads are L2 hits (the tensors are 8 - 67 MB, the L2 is 126 MB) and start while the barrier is still
 // being crossed.  HBM traffic: x once + y once (forward), dy + x once + dx (backward).
 //
@@ -70,16 +70,23 @@ __device__ __forceinline__ void gng_block_reduce(const float* s, const float* q,
   gng_sync();
 }
 
-// Fold the Gn per-CTA partials of image n (layout [Gn][32][2]) in a fixed order, fp64: thread (g, part) takes CTAs part,
-// part+16, ...; the 16 parts are folded by shuffles.  Results for all 32 groups land in shared memory.
-__device__ __forceinline__ void gng_fold(const float* part_n, int Gn, double* out_a, double* out_b) {
+// Fold the Gn per-CTA partials of image n (layout [Gn][32][2]) in a fixed order: thread (g, part) takes CTAs part, part+16, ...
+// with Neumaier-compensated fp32 sums (exact to ~1 ulp for <= 10 terms), the 16 parts are folded by shuffles.  No fp64: the
+// F2F.F64 / DADD sequence of the first version was 10 % of the kernel's stall samples (B200's fp64 pipe is narrow) for a
+// reduction of 148 numbers.  Results for all 32 groups land in shared memory.
+__device__ __forceinline__ void gng_fold(const float* part_n, int Gn, float* out_a, float* out_b) {
   const int g = threadIdx.x >> 4, part = threadIdx.x & 15;
-  double da = 0.0, db = 0.0;
+  float sa = 0.f, ca = 0.f, sb = 0.f, cb = 0.f;
   for (int j = part; j < Gn; j += 16) {
     const float2 v = __ldcg(reinterpret_cast<const float2*>(part_n + ((int64_t)j * 32 + g) * 2));
-    da += (double)v.x;
-    db += (double)v.y;
+    float t = sa + v.x;
+    ca += fabsf(sa) >= fabsf(v.x) ? (sa - t) + v.x : (v.x - t) + sa;
+    sa = t;
+    t = sb + v.y;
+    cb += fabsf(sb) >= fabsf(v.y) ? (sb - t) + v.y : (v.y - t) + sb;
+    sb = t;
   }
+  float da = sa + ca, db = sb + cb;
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) {
     da += __shfl_xor_sync(0xffffffffu, da, o);
@@ -179,7 +186,7 @@ gn_fwd_grid_kernel(const __half* __restrict__ x, const float* __restrict__ gamma
   extern __shared__ uint8_t gng_dyn[];
   __shared__ float red_s[kGngConsumers * 8], red_q[kGngConsumers * 8];
   __shared__ float gs[32], gq[32];
-  __shared__ double fa[32], fb[32];
+  __shared__ float fa[32], fb[32];
   __shared__ float s_mean[32], s_rstd[32];
   __shared__ __align__(8) uint64_t bars[2 * kGngStages];
   const int n = blockIdx.x / Gn, chunk = blockIdx.x % Gn;
@@ -224,11 +231,10 @@ gn_fwd_grid_kernel(const __half* __restrict__ x, const float* __restrict__ gamma
   grid_barrier(bar, gridDim.x);
   gng_fold(partials + (int64_t)n * Gn * 64, Gn, fa, fb);
   if (threadIdx.x < 32) {
-    const double m = (double)cpg * (double)HW;
-    const double mean = fa[threadIdx.x] / m;
-    double var = fb[threadIdx.x] / m - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float mu = (float)mean, rs = (float)(1.0 / sqrt(var + (double)eps));
+    const float inv_m = 1.f / ((float)cpg * (float)HW);
+    const float mu = fa[threadIdx.x] * inv_m;
+    const float var = fmaxf(fmaf(-mu, mu, fb[threadIdx.x] * inv_m), 0.f);  // E[x^2] - mean^2: relative error ~ 6e-8 * mean^2 / var
+    const float rs = 1.f / sqrtf(var + eps);
     s_mean[threadIdx.x] = mu;
     s_rstd[threadIdx.x] = rs;
     if (chunk == 0) {
@@ -278,7 +284,7 @@ gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
   extern __shared__ uint8_t gng_dyn[];
   __shared__ float red_s[kGngConsumers * 8], red_q[kGngConsumers * 8];
   __shared__ float gs[32], gq[32];
-  __shared__ double fa[32], fb[32];
+  __shared__ float fa[32], fb[32];
   __shared__ float s_m1[32], s_m2[32];
   __shared__ __align__(8) uint64_t bars[2 * kGngStages + 1];
   uint64_t* trip1_done = &bars[2 * kGngStages];
@@ -371,9 +377,9 @@ gn_bwd_grid_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
   grid_barrier(bar, gridDim.x);
   gng_fold(partials + (int64_t)n * Gn * 64, Gn, fa, fb);
   if (threadIdx.x < 32) {
-    const double m = (double)cpg * (double)HW;
-    s_m1[threadIdx.x] = (float)(fa[threadIdx.x] / m);  // mean(dxhat)
-    s_m2[threadIdx.x] = (float)(fb[threadIdx.x] / m);  // mean(dxhat * xhat)
+    const float inv_m = 1.f / ((float)cpg * (float)HW);
+    s_m1[threadIdx.x] = fa[threadIdx.x] * inv_m;  // mean(dxhat)
+    s_m2[threadIdx.x] = fb[threadIdx.x] * inv_m;  // mean(dxhat * xhat)
   }
   gng_sync();
   float m1[8], m2[8];

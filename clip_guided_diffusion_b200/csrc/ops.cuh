@@ -13,6 +13,12 @@ int launch_gn_fwd_fused(const CgdOp& op, cudaStream_t st);
 int launch_gn_bwd_fused(const CgdOp& op, cudaStream_t st);
 int launch_gn_fwd_grid(const CgdOp& op, cudaStream_t st);
 int launch_gn_bwd_grid(const CgdOp& op, cudaStream_t st);
+int launch_relu_fwd(const CgdOp& op, cudaStream_t st);
+int launch_relu_bwd(const CgdOp& op, cudaStream_t st);
+int launch_maxpool2_fwd(const CgdOp& op, cudaStream_t st);
+int launch_maxpool2_bwd(const CgdOp& op, cudaStream_t st);
+int launch_lpips_tap(const CgdOp& op, cudaStream_t st);
+int launch_fill(const CgdOp& op, cudaStream_t st);
 int launch_ln_fwd(const CgdOp& op, cudaStream_t st);
 int launch_ln_bwd(const CgdOp& op, cudaStream_t st);
 int launch_pool2(const CgdOp& op, cudaStream_t st);

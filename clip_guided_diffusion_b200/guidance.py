@@ -109,7 +109,7 @@ class GuidedStepB200:
                  height: int = None, width: int = None, num_cutouts: int = 16, max_prompts: int = 1, clip_guidance_scale=1000.0,
                  tv_scale=150.0, range_scale=50.0, sat_scale=0.0, use_magnitude=False, device="cuda", seed_scale=16.0,
                  vit_grad_scale=1.0, conv_impl=0, rank: int = 0, world_size: int = 1, use_graph: bool = True, vit_streams: int = 1,
-                 cutn_variants: tuple = ()):
+                 cutn_variants: tuple = (), lpips_sd: dict = None, init_scale: float = 0.0):
         self.device = th.device(device)
         self.B = batch
         self.rank, self.world = rank, world_size
@@ -142,6 +142,7 @@ class GuidedStepB200:
                                                  (self.var, 0), (self.logvar, 0), (self.x_inb, 0), (self.loss, B)], tag="p_mean_variance+blend")
         p.mark("cond")
         self.vit = None
+        self.lpips = None
         if vit_cfg is not None:
             cutn, cs, ps, kp, D = self.cutn, vit_cfg.input_resolution, vit_cfg.patch_size, vit_cfg.kpad, vit_cfg.output_dim
             self.vit_cfg = vit_cfg
@@ -171,6 +172,10 @@ class GuidedStepB200:
                 p.emit("CUTOUTS_BWD", i=[B, H, W, c, cs, ps, kp], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
                        p=[(vt.d_patches, 0), (self.coords, 0), (self.g_clip, 0)], tag="d_make_cutouts")
                 p.mark("cut_end" + sfx)
+            if lpips_sd is not None and init_scale != 0:
+                from .lpips import LpipsB200
+                # d (init_scale * lpips_vgg(x_in, init).sum()) / d x_in is added to the x_in gradient the cutout backward left in g_clip
+                self.lpips = LpipsB200(lpips_sd, B, H, W, p, self.x_inb, self.g_clip, init_scale)
             p.mark("guide")
             p.emit("GUIDE_GRAD", i=[B, H, W, IN_PAD], f=[self.scales["tv"], self.scales["rng"], self.scales["sat"], self.seed_scale],
                    p=[(self.x_inb, 0), (self.x0, 0), (self.g_clip, 0), (self.sc, 0), (self.unet.seed, 0), (self.dx_direct, 0), (self.loss, B)],
@@ -209,6 +214,12 @@ class GuidedStepB200:
 
     def img(self, buf):
         return self.plan.view(buf, self.shape)
+
+    def set_init_image(self, init: th.Tensor, runner=None):
+        """init image in [-1, 1] for the LPIPS init loss (cgd/cgd.py:116-120, 220-224); engines built with lpips_sd only"""
+        if self.lpips is None:
+            raise RuntimeError("engine built without the LPIPS loss (pass lpips_sd= and init_scale != 0)")
+        self.lpips.set_init_image(init, runner)
 
     def set_targets(self, target_embeds: th.Tensor, weights: th.Tensor):
         """target_embeds [P, D] (un-normalised is fine: the loss normalises, cgd/losses.py:12-13); weights already divided by
@@ -277,7 +288,8 @@ class GuidedStepB200:
         self._run_vit("fwd", None, cutn)
         self.plan.run_range("sph" + sfx, "cut_bwd" + sfx)
         self._run_vit("bwd", None, cutn)
-        for a, b in (("cut_bwd" + sfx, "cut_end" + sfx), ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g")):
+        for a, b in (("cut_bwd" + sfx, "cut_end" + sfx),) + ((("lpips", "lpips_end"),) if self.lpips is not None else ()) + (
+                ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g")):
             self.plan.run_range(a, b)
         return self.img(self.g)
 
@@ -316,6 +328,8 @@ class GuidedStepB200:
         pr("sph" + sfx, "cut_bwd" + sfx)
         self._run_vit("bwd", pr, cutn)
         pr("cut_bwd" + sfx, "cut_end" + sfx)
+        if self.lpips is not None:
+            pr("lpips", "lpips_end")
         pr("guide", "final")
         pr("unet_bwd", "unet_end")
         pr("final", "upd_anc_g")
@@ -344,7 +358,8 @@ class GuidedStepB200:
     def launches_per_step(self, mode="ddim") -> int:
         m = self.plan.marks
         segs = [("unet_emb", "unet_bwd"), ("pmv", "cond"), ("cut_fwd", "sph"), ("vit_fwd", "vit_bwd"), ("sph", "cut_bwd"), ("vit_bwd", "vit_end"),
-                ("cut_bwd", "guide"), ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g"),
+                ("cut_bwd", "cut_end")] + ([("lpips", "lpips_end")] if self.lpips is not None else []) + [
+                ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g"),
                 ("upd_anc_g", "upd_anc") if mode == "ancestral" else ("upd_ddim_g", "upd_ddim")]
         return sum(self.plan.num_launches(m[a], m[b] - m[a]) for a, b in segs)
 
@@ -408,7 +423,10 @@ class GuidedStepB200:
     def losses(self) -> dict:
         """per-image loss terms of the last step (device->host sync; logging only, like tqdm.write at cgd/cgd.py:234-236)"""
         l = self.v(self.loss, (4, self.B)).cpu()
-        return {"clip": l[0], "tv": l[1], "range": l[2], "sat": l[3]}
+        d = {"clip": l[0], "tv": l[1], "range": l[2], "sat": l[3]}
+        if self.lpips is not None:
+            d["init"] = self.lpips.loss_value().cpu() * self.lpips.init_scale
+        return d
 
 
 class CondFnB200:

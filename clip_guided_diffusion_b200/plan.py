@@ -414,6 +414,42 @@ class Plan:
         self._tape.append(bwd)
         return y
 
+    # ------------------------------------------------------------------ VGG pieces of the LPIPS loss (csrc/lpips.cu)
+    def relu(self, x: Act, name="relu") -> Act:
+        assert x.ld == x.C
+        y = self.act(x.N, x.H, x.W, x.C, name)
+        self.emit("RELU_FWD", i=[x.rows * x.C], p=[self._ap(x), self._ap(y)], tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            assert dy.ld == dy.C
+            cur, has = self.writable_grad(x)
+            dx = cur if has else self.act(x.N, x.H, x.W, x.C, "d_" + name)
+            self.emit("RELU_BWD", flags=2 if has else 0, i=[x.rows * x.C], p=[self._ap(dy), self._ap(y), self._ap(dx)], tag="d_" + name)
+            self._grads[x.key()] = dx
+
+        self._tape.append(bwd)
+        return y
+
+    def maxpool2(self, x: Act, name="maxpool") -> Act:
+        assert x.ld == x.C and x.H % 2 == 0 and x.W % 2 == 0
+        y = self.act(x.N, x.H // 2, x.W // 2, x.C, name)
+        self.emit("MAXPOOL2_FWD", i=[x.N, x.H, x.W, x.C], p=[self._ap(x), self._ap(y)], tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            assert dy.ld == dy.C
+            dx = self.act(x.N, x.H, x.W, x.C, "d_" + name)
+            self.emit("MAXPOOL2_BWD", i=[x.N, x.H, x.W, x.C], p=[self._ap(dy), self._ap(x), self._ap(dx)], tag="d_" + name)
+            self.add_grad(x, dx)
+
+        self._tape.append(bwd)
+        return y
+
     def concat_view(self, y: Act, a: Act, b: Act):
         """`y` = [a | b] where a and b are channel slices of y's own storage, already written there by their producers:
         no forward op; the backward hands the matching slices of dy to a and b."""

@@ -106,10 +106,11 @@ enum {
   CGD_OP_TIMESTEP_EMB = 12,
   /* emb[b,:] += table[y[b],:] : p0 emb(f) p1 table(f) p2 y(int64) ; i0 B i1 D */
   CGD_OP_LABEL_ADD = 13,
-  /* fp32 NCHW -> fp16 pixel-major zero-padded to ld channels: p0 src p1 dst ; i0 N i1 C i2 HW i3 ld ; f0 scale */
+  /* fp32 NCHW -> fp16 pixel-major zero-padded to ld channels: p0 src p1 dst ; i0 N i1 C i2 HW i3 ld ; f0 scale
+   * flags 4 (C <= 3): per-channel affine (x - f[1+c]) * f[4+c] * f0 (the LPIPS ScalingLayer) */
   CGD_OP_NCHW_TO_PM = 14,
   /* pixel-major (h, or f with flag 1) -> fp32 NCHW (first C channels): p0 src p1 dst ; i0 N i1 C i2 HW i3 ld ; f0 scale
-   * flags 1 = src fp32, 2 = accumulate */
+   * flags 1 = src fp32, 2 = accumulate, 4 (C <= 3) = per-channel multiplier f[1+c] */
   CGD_OP_PM_TO_NCHW = 15,
   /* LayerNorm rows: p0 x(h) p1 gamma(f) p2 beta(f) p3 y(h) p4 stats(f [rows,2]) ; i0 rows i1 w i2 ldx i3 ldy ; f0 eps */
   CGD_OP_LN_FWD = 16,
@@ -184,6 +185,20 @@ enum {
    * p9 scratch(h, dense [N,HW,C])|0: d xhat is stored once and streamed back instead of recomputing SiLU' in the apply pass
    * i0 N i1 HW i2 C i3 ld_dy i4 ldx i5 ld_dx i6 Gn ; flags 1 = SiLU, 2 = accumulate into dx */
   CGD_OP_GN_BWD_GRID = 36,
+  /* y = max(x, 0) on n fp16 elements (n % 8 == 0; in place allowed): p0 x p1 y ; i0 n.  [3P] VGG16 ReLU of lpips.LPIPS (K21) */
+  CGD_OP_RELU_FWD = 37,
+  /* dx (=|+=) dy where y > 0: p0 dy p1 y (ReLU output) p2 dx ; i0 n ; flags 2 = accumulate */
+  CGD_OP_RELU_BWD = 38,
+  /* 2x2 stride-2 max pool on pixel-major [N,H,W,C] (H, W even, C % 8 == 0): p0 x p1 y ; i0 N i1 H i2 W i3 C */
+  CGD_OP_MAXPOOL2_FWD = 39,
+  /* its input gradient (dy to the first window position holding the maximum, like ATen): p0 dy p1 x p2 dx ; i0 N i1 H i2 W i3 C */
+  CGD_OP_MAXPOOL2_BWD = 40,
+  /* one LPIPS tap: xh = f / (||f||_C + 1e-10); loss[b] += mean_p sum_c w_c (xh - tn)^2 ; df = f0 * d loss / d f.
+   * p0 f(h [B,HW,C]) p1 tn(h [Bt,HW,C], normalised init-image features) p2 w(f [C]) p3 df(h) p4 loss(f [B], accumulated)
+   * i0 B i1 HW i2 C (<= 512) i3 Bt (1 = broadcast) ; f0 gradient scale.  cgd/cgd.py:220-224, SURVEY A.4 */
+  CGD_OP_LPIPS_TAP = 41,
+  /* dst[0..n) = f0 (fp32): p0 dst ; i0 n */
+  CGD_OP_FILL = 42,
   CGD_OP__COUNT
 };
 

@@ -73,9 +73,11 @@ class MakeCutouts(th.nn.Module):
 
 
 def guidance_loss(x, pred_xstart, fac, coords, clip_model, target_embeds, weights, *, cut_size,
-                  clip_guidance_scale=1000.0, tv_scale=150.0, range_scale=50.0, sat_scale=0.0):
-    """The differentiable body of cond_fn (cgd/cgd.py:177-226, LPIPS excluded) with explicit cutout
-    coordinates.  Returns (total_loss, dict of per-term scalars)."""
+                  clip_guidance_scale=1000.0, tv_scale=150.0, range_scale=50.0, sat_scale=0.0,
+                  lpips_model=None, init_tensor=None, init_scale=0.0):
+    """The differentiable body of cond_fn (cgd/cgd.py:177-226) with explicit cutout coordinates; the LPIPS term
+    (cgd/cgd.py:220-224) when ``lpips_model`` (oracle/lpips.py) and ``init_tensor`` are given.
+    Returns (total_loss, dict of per-term scalars)."""
     n = x.shape[0]
     cutn = len(coords)
     x_in = pred_xstart * fac + x * (1 - fac)
@@ -92,6 +94,10 @@ def guidance_loss(x, pred_xstart, fac, coords, clip_model, target_embeds, weight
         sat_l = th.abs(x_in - x_in.clamp(min=-1, max=1)).mean() * sat_scale
         loss = loss + sat_l
         terms["sat"] = sat_l
+    if lpips_model is not None and init_tensor is not None and init_scale != 0:  # cgd/cgd.py:220-224
+        init_l = lpips_model(x_in, init_tensor).sum() * init_scale
+        loss = loss + init_l
+        terms["init"] = init_l
     return loss, terms
 
 
@@ -107,12 +113,13 @@ class OracleCondFn:
 
     def __init__(self, diffusion, clip_model, target_embeds, weights, *, cut_size, num_cutouts,
                  cutout_power=1.0, clip_guidance_scale=1000.0, tv_scale=150.0, range_scale=50.0,
-                 sat_scale=0.0, use_magnitude=False):
+                 sat_scale=0.0, use_magnitude=False, lpips_model=None, init_tensor=None, init_scale=0.0):
         self.diffusion, self.clip_model = diffusion, clip_model
         self.target_embeds, self.weights = target_embeds, weights
         self.mk = MakeCutouts(cut_size, num_cutouts, cutout_power)
         self.kw = dict(cut_size=cut_size, clip_guidance_scale=clip_guidance_scale, tv_scale=tv_scale,
-                       range_scale=range_scale, sat_scale=sat_scale)
+                       range_scale=range_scale, sat_scale=sat_scale, lpips_model=lpips_model, init_tensor=init_tensor,
+                       init_scale=init_scale)
         self.use_magnitude = use_magnitude
         self.current_timestep = diffusion.num_timesteps - 1
         self.last_coords = None

@@ -13,7 +13,8 @@ OUT_PTRS = {"CONV": [4], "GN_STATS": [2], "GN_APPLY": [5], "GN_BWD_STATS": [7], 
             "PM_TO_NCHW": [1], "LN_FWD": [3, 4], "LN_BWD": [4], "QGELU_FWD": [1], "QGELU_BWD": [2], "VIT_EMBED": [0], "CUTOUTS_FWD": [2],
             "CUTOUTS_BWD": [2], "SPHERICAL": [3, 4], "PMV_BLEND": [3, 4, 5, 6, 7], "GUIDE_GRAD": [4, 5, 6], "FINAL_GRAD": [2],
             "SAMPLE_ANCESTRAL": [6], "SAMPLE_DDIM": [5], "TRANSPOSE": [1, 3, 5], "SOFTMAX_FWD": [0, 1], "SOFTMAX_BWD": [1],
-            "GN_FWD_FUSED": [4, 5], "GN_BWD_FUSED": [6], "GN_FWD_GRID": [4, 5], "GN_BWD_GRID": [6]}
+            "GN_FWD_FUSED": [4, 5], "GN_BWD_FUSED": [6], "GN_FWD_GRID": [4, 5], "GN_BWD_GRID": [6],
+            "RELU_FWD": [1], "RELU_BWD": [2], "MAXPOOL2_FWD": [1], "MAXPOOL2_BWD": [2], "LPIPS_TAP": [3, 4], "FILL": [0]}
 
 
 def cpu_twin(plan):

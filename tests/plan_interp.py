@@ -176,6 +176,44 @@ class Interp:
         dx = self.V(op.p[6], (N, HW, C), (HW * ld_dx, ld_dx, 1))
         dx.copy_(dx.float() + r if op.flags & 2 else r)
 
+    def op_RELU_FWD(self, op):
+        n = op.i[0]
+        self.flat(op.p[1], n).copy_(self.flat(op.p[0], n).float().clamp_min(0))
+
+    def op_RELU_BWD(self, op):
+        n = op.i[0]
+        r = self.flat(op.p[0], n).float() * (self.flat(op.p[1], n).float() > 0)
+        dx = self.flat(op.p[2], n)
+        dx.copy_(dx.float() + r if op.flags & 2 else r)
+
+    def op_MAXPOOL2_FWD(self, op):
+        N, H, W, C = op.i[:4]
+        x = self.V(op.p[0], (N, H, W, C), (H * W * C, W * C, C, 1)).float()
+        y = F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+        self.V(op.p[1], (N, H // 2, W // 2, C), (H * W * C // 4, W * C // 2, C, 1)).copy_(y)
+
+    def op_MAXPOOL2_BWD(self, op):
+        N, H, W, C = op.i[:4]
+        x = self.V(op.p[1], (N, H, W, C), (H * W * C, W * C, C, 1)).float().permute(0, 3, 1, 2).contiguous().requires_grad_()
+        dy = self.V(op.p[0], (N, H // 2, W // 2, C), (H * W * C // 4, W * C // 2, C, 1)).float().permute(0, 3, 1, 2)
+        (g,) = th.autograd.grad(F.max_pool2d(x, 2, 2), x, dy)
+        self.V(op.p[2], (N, H, W, C), (H * W * C, W * C, C, 1)).copy_(g.permute(0, 2, 3, 1))
+
+    def op_LPIPS_TAP(self, op):
+        B, HW, C, Bt = op.i[:4]
+        f = self.V(op.p[0], (B, HW, C), (HW * C, C, 1)).float().requires_grad_()
+        tn = self.V(op.p[1], (Bt, HW, C), (HW * C, C, 1)).float()
+        w = self.flat(op.p[2], C)
+        xh = f / (f.pow(2).sum(-1, keepdim=True).sqrt() + 1e-10)
+        per = ((xh - tn) ** 2 * w).sum(-1).mean(-1)  # [B]
+        (g,) = th.autograd.grad(per.sum(), f)
+        self.V(op.p[3], (B, HW, C), (HW * C, C, 1)).copy_(g * op.f[0])
+        loss = self.flat(op.p[4], B)
+        loss.copy_(loss + per.detach())
+
+    def op_FILL(self, op):
+        self.flat(op.p[0], op.i[0]).fill_(op.f[0])
+
     def op_POOL2(self, op):
         N, H, W, C, ldx, ldy = op.i[:6]
         x = self.V(op.p[0], (N, H, W, C), (H * W * ldx, W * ldx, ldx, 1)).float()
@@ -292,7 +330,10 @@ class Interp:
 
     def op_NCHW_TO_PM(self, op):
         N, C, HW, ld = op.i[:4]
-        src = self.V(op.p[0], (N, C, HW), (C * HW, HW, 1)) * op.f[0]
+        src = self.V(op.p[0], (N, C, HW), (C * HW, HW, 1))
+        if op.flags & 4:
+            src = (src - th.tensor(op.f[1:4][:C]).view(1, C, 1)) * th.tensor(op.f[4:7][:C]).view(1, C, 1)
+        src = src * op.f[0]
         dst = self.V(op.p[1], (N, HW, ld), (HW * ld, ld, 1))
         dst.zero_()
         dst[:, :, :C] = src.permute(0, 2, 1)
@@ -300,6 +341,8 @@ class Interp:
     def op_PM_TO_NCHW(self, op):
         N, C, HW, ld = op.i[:4]
         src = self.V(op.p[0], (N, HW, C), (HW * ld, ld, 1)).float() * op.f[0]
+        if op.flags & 4:
+            src = src * th.tensor(op.f[1:4][:C]).view(1, 1, C)
         dst = self.V(op.p[1], (N, C, HW), (C * HW, HW, 1))
         dst.copy_(dst + src.permute(0, 2, 1) if op.flags & 2 else src.permute(0, 2, 1))
 

@@ -58,3 +58,16 @@ def test_progressive_cutout_variant_vs_oracle(fused):
     e = engine_step(ctx, "ddim", x, 14, y, noise, coords, fac_index=14, fused=fused)
     res = compare(o, e)
     assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res
+
+
+def test_step_with_lpips_init_loss_vs_oracle():
+    """Whole guided step with an init image: ``+ lpips_vgg(x_in, init).sum() * init_scale`` inside the differentiated loss
+    (cgd/cgd.py:220-224), CUDA-graph replay vs the oracle."""
+    ctx = build_tiny("cuda", conv_impl=IMPL, image=64, use_graph=True, B=1, cutn=2, init_scale=1000.0)
+    ctx["eng"].set_init_image(ctx["init"])
+    x, y, noise, nseed, coords = make_inputs(ctx)
+    o = oracle_step(ctx, "ddim", x, 14, y, nseed, coords, fac_index=14)
+    e = engine_step(ctx, "ddim", x, 14, y, noise, coords, fac_index=14, fused=True)
+    res = compare(o, e)
+    assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res
+    assert abs(float(e["losses"]["init"].sum()) - o["terms"]["init"]) / abs(o["terms"]["init"]) < 3e-2
