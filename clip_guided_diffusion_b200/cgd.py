@@ -100,7 +100,7 @@ def clip_guided_diffusion(
     reduce_clip: bool = False, progressive_cutout: bool = False, cached_cutouts: bool = False,
     # --- additions of this framework (all optional)
     unet_state_dict: dict = None, clip_state_dict: dict = None, target_embeds: th.Tensor = None, weights: th.Tensor = None,
-    lpips_state_dict: dict = None,
+    lpips_state_dict: dict = None, cutout_resize: str = "pool",
     rank: int = 0, world_size: int = 1,
 ):
     if len(device) == 0:
@@ -141,7 +141,7 @@ def clip_guided_diffusion(
                             world_size=world_size,
                             cutn_variants=CondFnB200.progressive_counts(num_cutouts) if progressive_cutout else (),
                             lpips_sd=_lpips_sd(lpips_state_dict) if (init_image is not None and init_scale != 0) else None,
-                            init_scale=init_scale)
+                            init_scale=init_scale, cutout_resize=cutout_resize)
     engine.set_targets(target_embeds, weights)
     make_cutouts = MakeCutouts(cut_size=vit_cfg.input_resolution, num_cutouts=num_cutouts, cutout_size_power=cutout_power, use_augs=use_augs)
     if cached_cutouts:

@@ -109,6 +109,113 @@ __global__ void cutouts_bwd_kernel(const __half* __restrict__ dpatch, const int*
   }
 }
 
+// ---------------------------------------------------------------- cutouts, ResizeRight (lanczos3, antialiased) mode
+// Same contract as cutouts_fwd / cutouts_bwd, but every square S x S crop is resampled to cs x cs with the separable tables the
+// host builds per crop size (clip_guided_diffusion_b200/resize_right.py, following cgd/ResizeRight/resize_right.py:31-122):
+// left[k][o] = first input index (relative to the crop) of output o, w[k][o][0..T) its normalised weights, samples outside
+// the crop are zero (pad_mode 'constant').  inv[k][r] = [lo, hi]: the outputs whose field of view contains input r.
+constexpr int RR_TMAX = 16;
+
+__global__ void cutouts_rr_fwd_kernel(const float* __restrict__ x, const int* __restrict__ coords, const int* __restrict__ left,
+                                      const float* __restrict__ wt, const int* __restrict__ taps, __half* __restrict__ out, int B, int H, int W,
+                                      int cutn, int cs, int P, int Kpad, float3 mean, float3 stdv) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int g = cs / P, G2 = g * g, PP = P * P;
+  const int64_t total = (int64_t)cutn * B * G2 * Kpad;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % Kpad);
+    int64_t r = idx / Kpad;
+    const int patch = (int)(r % G2);
+    r /= G2;
+    const int b = (int)(r % B), k = (int)(r / B);
+    if (kk >= 3 * PP) {
+      out[idx] = __float2half_rn(0.f);
+      continue;
+    }
+    const int c = kk / PP, ky = (kk % PP) / P, kx = kk % P;
+    const int oy = (patch / g) * P + ky, ox = (patch % g) * P + kx;
+    const int offx = coords[k * 3 + 0], offy = coords[k * 3 + 1], S = coords[k * 3 + 2], T = taps[k];
+    const int ly = left[k * cs + oy], lx = left[k * cs + ox];
+    const float* wy = wt + ((int64_t)k * cs + oy) * RR_TMAX;
+    const float* wx = wt + ((int64_t)k * cs + ox) * RR_TMAX;
+    const float* src = x + ((int64_t)b * 3 + c) * H * W;
+    float acc = 0.f;
+    for (int i = 0; i < T; ++i) {
+      const int yy = ly + i;
+      if (yy < 0 || yy >= S) continue;
+      const float* row = src + (int64_t)(offy + yy) * W + offx;
+      float rs = 0.f;
+      for (int j = 0; j < T; ++j) {
+        const int xx = lx + j;
+        if (xx >= 0 && xx < S) rs = fmaf(wx[j], row[xx], rs);
+      }
+      acc = fmaf(wy[i], rs, acc);
+    }
+    const float mu = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
+    const float sd = c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z);
+    out[idx] = __float2half_rn(((acc + 1.f) * 0.5f - mu) / sd);
+  }
+}
+
+__global__ void cutouts_rr_bwd_kernel(const __half* __restrict__ dpatch, const int* __restrict__ coords, const int* __restrict__ left,
+                                      const float* __restrict__ wt, const int* __restrict__ inv, float* __restrict__ dx, int B, int H, int W,
+                                      int cutn, int cs, int P, int Kpad, int Smax, float3 stdv, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int g = cs / P, G2 = g * g, PP = P * P;
+  const int64_t total = (int64_t)B * 3 * H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int xg = (int)(idx % W);
+    int64_t r = idx / W;
+    const int yg = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % 3), b = (int)(r / 3);
+    const float sd = c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z);
+    float acc = 0.f;
+    for (int k = 0; k < cutn; ++k) {
+      const int offx = coords[k * 3 + 0], offy = coords[k * 3 + 1], S = coords[k * 3 + 2];
+      const int ry = yg - offy, rx = xg - offx;
+      if (ry < 0 || ry >= S || rx < 0 || rx >= S) continue;
+      const int oy0 = inv[((int64_t)k * Smax + ry) * 2], oy1 = inv[((int64_t)k * Smax + ry) * 2 + 1];
+      const int ox0 = inv[((int64_t)k * Smax + rx) * 2], ox1 = inv[((int64_t)k * Smax + rx) * 2 + 1];
+      const __half* dp = dpatch + ((int64_t)k * B + b) * G2 * Kpad + (int64_t)c * PP;
+      for (int oy = oy0; oy <= oy1; ++oy) {
+        const float wyv = wt[((int64_t)k * cs + oy) * RR_TMAX + (ry - left[k * cs + oy])];
+        float rs = 0.f;
+        for (int ox = ox0; ox <= ox1; ++ox) {
+          const float wxv = wt[((int64_t)k * cs + ox) * RR_TMAX + (rx - left[k * cs + ox])];
+          const int patch = (oy / P) * g + (ox / P);
+          rs = fmaf(wxv, __half2float(dp[(int64_t)patch * Kpad + (oy % P) * P + (ox % P)]), rs);
+        }
+        acc = fmaf(wyv, rs, acc);
+      }
+    }
+    dx[idx] = acc * (0.5f / sd) * scale;
+  }
+}
+
+static int cutout_check(const CgdOp& op);
+int launch_cutouts_rr_fwd(const CgdOp& op, cudaStream_t st) {
+  if (int rc = cutout_check(op)) return rc;
+  const int64_t B = op.i[0], cutn = op.i[3], cs = op.i[4], P = op.i[5], Kpad = op.i[6];
+  CGD_CHECK_ARG(op.p[3] && op.p[4] && op.p[5], "cutouts_rr_fwd: null table pointer");
+  const int64_t total = cutn * B * (cs / P) * (cs / P) * Kpad;
+  CGD_CUDA(launch_pdl(cutouts_rr_fwd_kernel, dim3(gw_blocks(total)), dim3(256), 0, st, (const float*)op.p[0], (const int*)op.p[1], (const int*)op.p[3],
+                      (const float*)op.p[4], (const int*)op.p[5], (__half*)op.p[2], (int)B, (int)op.i[1], (int)op.i[2], (int)cutn, (int)cs, (int)P,
+                      (int)Kpad, make_float3(op.f[0], op.f[1], op.f[2]), make_float3(op.f[3], op.f[4], op.f[5])));
+  return 0;
+}
+int launch_cutouts_rr_bwd(const CgdOp& op, cudaStream_t st) {
+  if (int rc = cutout_check(op)) return rc;
+  const int64_t B = op.i[0], H = op.i[1], W = op.i[2], Smax = op.i[7];
+  CGD_CHECK_ARG(op.p[3] && op.p[4] && op.p[5] && Smax > 0, "cutouts_rr_bwd: null table pointer / Smax");
+  CGD_CUDA(launch_pdl(cutouts_rr_bwd_kernel, dim3(gw_blocks(B * 3 * H * W)), dim3(256), 0, st, (const __half*)op.p[0], (const int*)op.p[1],
+                      (const int*)op.p[3], (const float*)op.p[4], (const int*)op.p[5], (float*)op.p[2], (int)B, (int)H, (int)W, (int)op.i[3],
+                      (int)op.i[4], (int)op.i[5], (int)op.i[6], (int)Smax, make_float3(op.f[3], op.f[4], op.f[5]), op.f[6]));
+  return 0;
+}
+
 static int cutout_check(const CgdOp& op) {
   const int64_t B = op.i[0], H = op.i[1], W = op.i[2], cutn = op.i[3], cs = op.i[4], P = op.i[5], Kpad = op.i[6];
   CGD_CHECK_ARG(B > 0 && H > 0 && W > 0 && cutn > 0 && cs > 0 && P > 0 && cs % P == 0 && Kpad >= 3 * P * P, "cutouts: bad dims");

@@ -41,6 +41,8 @@ int launch_qgelu_bwd(const CgdOp& op, cudaStream_t st);
 int launch_vit_embed(const CgdOp& op, cudaStream_t st);
 int launch_cutouts_fwd(const CgdOp& op, cudaStream_t st);
 int launch_cutouts_bwd(const CgdOp& op, cudaStream_t st);
+int launch_cutouts_rr_fwd(const CgdOp& op, cudaStream_t st);
+int launch_cutouts_rr_bwd(const CgdOp& op, cudaStream_t st);
 int launch_spherical(const CgdOp& op, cudaStream_t st);
 int launch_pmv_blend(const CgdOp& op, cudaStream_t st);
 int launch_guide_grad(const CgdOp& op, cudaStream_t st);

@@ -109,7 +109,7 @@ class GuidedStepB200:
                  height: int = None, width: int = None, num_cutouts: int = 16, max_prompts: int = 1, clip_guidance_scale=1000.0,
                  tv_scale=150.0, range_scale=50.0, sat_scale=0.0, use_magnitude=False, device="cuda", seed_scale=16.0,
                  vit_grad_scale=1.0, conv_impl=0, rank: int = 0, world_size: int = 1, use_graph: bool = True, vit_streams: int = 1,
-                 cutn_variants: tuple = (), lpips_sd: dict = None, init_scale: float = 0.0):
+                 cutn_variants: tuple = (), lpips_sd: dict = None, init_scale: float = 0.0, cutout_resize: str = "pool"):
         self.device = th.device(device)
         self.B = batch
         self.rank, self.world = rank, world_size
@@ -156,6 +156,19 @@ class GuidedStepB200:
             # further cutout counts of the same engine (progressive_cutout, cgd/cgd.py:167-175): own activations and op ranges
             # ("...@c" marks), shared packed weights; the default count keeps the un-suffixed marks
             self.vits = {cutn: self.vit}
+            # cutout resampling: "pool" = adaptive_avg_pool2d like the reference's MakeCutouts (cgd/modules.py:63); "lanczos3" =
+            # the vendored ResizeRight resampler north_star names (cgd/ResizeRight/resize_right.py, host tables in resize_right.py)
+            if cutout_resize not in ("pool", "lanczos3"):
+                raise ValueError("cutout_resize must be 'pool' or 'lanczos3'")
+            self.cutout_resize = cutout_resize
+            if cutout_resize == "lanczos3":
+                if H != W or cutn_variants:
+                    raise NotImplementedError("ResizeRight cutouts: square images and a single cutout count only")
+                from .resize_right import T_MAX
+                self.rr_left = p.new(cutn * cs, "i32", "rr_left")
+                self.rr_w = p.new(cutn * cs * T_MAX, "f", "rr_weights")
+                self.rr_taps = p.new(cutn, "i32", "rr_taps")
+                self.rr_inv = p.new(cutn * H * 2, "i32", "rr_inverse")
             for c in sorted(set(int(v) for v in cutn_variants) - {cutn}):
                 if not 0 < c < cutn:
                     raise ValueError(f"cutn_variants must lie in (0, {cutn}), got {c}")
@@ -163,14 +176,24 @@ class GuidedStepB200:
             for c in sorted(self.vits, key=lambda v: v == cutn):  # the default count last: its ranges end at "guide"
                 sfx, vt = ("" if c == cutn else f"@{c}"), self.vits[c]
                 p.mark("cut_fwd" + sfx)
-                p.emit("CUTOUTS_FWD", i=[B, H, W, c, cs, ps, kp], f=[*CLIP_MEAN, *CLIP_STD], p=[(self.x_inb, 0), (self.coords, 0), (vt.patches, 0)],
-                       tag="make_cutouts+normalize")
+                if cutout_resize == "lanczos3":
+                    p.emit("CUTOUTS_RR_FWD", i=[B, H, W, c, cs, ps, kp], f=[*CLIP_MEAN, *CLIP_STD],
+                           p=[(self.x_inb, 0), (self.coords, 0), (vt.patches, 0), (self.rr_left, 0), (self.rr_w, 0), (self.rr_taps, 0)],
+                           tag="make_cutouts(resize_right lanczos3)+normalize")
+                else:
+                    p.emit("CUTOUTS_FWD", i=[B, H, W, c, cs, ps, kp], f=[*CLIP_MEAN, *CLIP_STD], p=[(self.x_inb, 0), (self.coords, 0), (vt.patches, 0)],
+                           tag="make_cutouts+normalize")
                 p.mark("sph" + sfx)
                 p.emit("SPHERICAL", i=[c, B, self.P, D], f=[self.scales["cgs"], self.vit_grad_scale],
                        p=[(vt.embeds, 0), (self.targets, 0), (self.weights, 0), (vt.d_embeds, 0), (self.loss, 0)], tag="spherical_dist_loss")
                 p.mark("cut_bwd" + sfx)
-                p.emit("CUTOUTS_BWD", i=[B, H, W, c, cs, ps, kp], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
-                       p=[(vt.d_patches, 0), (self.coords, 0), (self.g_clip, 0)], tag="d_make_cutouts")
+                if cutout_resize == "lanczos3":
+                    p.emit("CUTOUTS_RR_BWD", i=[B, H, W, c, cs, ps, kp, H], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
+                           p=[(vt.d_patches, 0), (self.coords, 0), (self.g_clip, 0), (self.rr_left, 0), (self.rr_w, 0), (self.rr_inv, 0)],
+                           tag="d_make_cutouts(resize_right)")
+                else:
+                    p.emit("CUTOUTS_BWD", i=[B, H, W, c, cs, ps, kp], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
+                           p=[(vt.d_patches, 0), (self.coords, 0), (self.g_clip, 0)], tag="d_make_cutouts")
                 p.mark("cut_end" + sfx)
             if lpips_sd is not None and init_scale != 0:
                 from .lpips import LpipsB200
@@ -284,6 +307,7 @@ class GuidedStepB200:
         cutn = len(coords)
         sfx = self._sfx(cutn)
         self.v(self.coords, (self.cutn, 3))[:cutn].copy_(th.tensor(coords, dtype=th.int32), non_blocking=True)
+        self._stage_resize_tables(coords)
         self.plan.run_range("cut_fwd" + sfx, "sph" + sfx)
         self._run_vit("fwd", None, cutn)
         self.plan.run_range("sph" + sfx, "cut_bwd" + sfx)
@@ -389,6 +413,30 @@ class GuidedStepB200:
             st[o:o + n].view(th.int32).copy_(th.tensor(coords, dtype=th.int32).view(-1))
             self.v(self.coords).view(th.uint8)[:n].copy_(st[o:o + n], non_blocking=True)
             self.h2d_bytes += n
+            self._stage_resize_tables(coords)
+
+    def _stage_resize_tables(self, coords):
+        """ResizeRight mode: per-cutout resampling tables of this step's crop sizes (cached per size on the host) -> device"""
+        if self.vit is None or self.cutout_resize != "lanczos3":
+            return
+        from . import resize_right as rr
+        cs, S_max = self.vit_cfg.input_resolution, self.H
+        if not hasattr(self, "_rr_pin"):
+            pin = self.device.type == "cuda"
+            self._rr_pin = (th.zeros(self.cutn, cs, dtype=th.int32, pin_memory=pin), th.zeros(self.cutn, cs, rr.T_MAX, pin_memory=pin),
+                            th.zeros(self.cutn, dtype=th.int32, pin_memory=pin), th.zeros(self.cutn, S_max, 2, dtype=th.int32, pin_memory=pin))
+        pl, pw, pt, pi_ = self._rr_pin
+        for k, (_, _, S) in enumerate(coords):
+            left, w, T = rr.tables(int(S), cs)
+            pl[k].copy_(left)
+            pw[k].copy_(w)
+            pt[k] = T
+            pi_[k, :S].copy_(rr.inverse_ranges(left, T, int(S)))
+        self.v(self.rr_left, (self.cutn, cs)).copy_(pl, non_blocking=True)
+        self.v(self.rr_w, (self.cutn, cs, rr.T_MAX)).copy_(pw, non_blocking=True)
+        self.v(self.rr_taps, (self.cutn,)).copy_(pt, non_blocking=True)
+        self.v(self.rr_inv, (self.cutn, S_max, 2)).copy_(pi_, non_blocking=True)
+        self.h2d_bytes += pl.numel() * 4 + pw.numel() * 4 + pt.numel() * 4 + pi_.numel() * 4
 
     def fused_step(self, diffusion, mode, t_index, img, y, cond_fn, eta=0.0) -> dict:
         fac_index = cond_fn.current_timestep

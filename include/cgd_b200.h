@@ -199,6 +199,11 @@ enum {
   CGD_OP_LPIPS_TAP = 41,
   /* dst[0..n) = f0 (fp32): p0 dst ; i0 n */
   CGD_OP_FILL = 42,
+  /* MakeCutouts in ResizeRight mode (lanczos3, antialiased; cgd/ResizeRight/resize_right.py:31-122): like CUTOUTS_FWD / _BWD with
+   * host-built separable tables per cutout: p3 left(i32 [cutn,cs]) p4 weights(f [cutn,cs,16]) p5 taps(i32 [cutn]) (fwd)
+   * / inverse ranges(i32 [cutn,Smax,2]) (bwd) ; i7 Smax (bwd).  Square crops only. */
+  CGD_OP_CUTOUTS_RR_FWD = 43,
+  CGD_OP_CUTOUTS_RR_BWD = 44,
   CGD_OP__COUNT
 };
 

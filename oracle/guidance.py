@@ -60,6 +60,8 @@ class MakeCutouts(th.nn.Module):
     def cache_coordinates(self, side_x, side_y):  # modules.py:26-36
         self.cached_coords = self._generate_coords(side_x, side_y, self.cutn)
 
+    resize = "pool"  # "lanczos3": the ResizeRight mode named by north_star (oracle/resize_right.py) instead of the reference's pooling
+
     def forward(self, x, use_cache=False, num_cutouts_override=None, coords=None):
         cutn = num_cutouts_override if num_cutouts_override is not None else self.cutn
         side_x, side_y = x.shape[2:4]  # sic: (H, W) named (x, y), modules.py:52 (quirk B3)
@@ -68,13 +70,16 @@ class MakeCutouts(th.nn.Module):
                 coords = self.cached_coords[:cutn]
             else:
                 coords = self._generate_coords(side_x, side_y, cutn)
+        if self.resize == "lanczos3":
+            from .resize_right import resize_lanczos3
+            return th.cat([resize_lanczos3(x[:, :, oy:oy + s, ox:ox + s], (self.cut_size, self.cut_size)) for ox, oy, s in coords])
         outs = [F.adaptive_avg_pool2d(x[:, :, oy:oy + s, ox:ox + s], self.cut_size) for ox, oy, s in coords]
         return th.cat(outs)
 
 
 def guidance_loss(x, pred_xstart, fac, coords, clip_model, target_embeds, weights, *, cut_size,
                   clip_guidance_scale=1000.0, tv_scale=150.0, range_scale=50.0, sat_scale=0.0,
-                  lpips_model=None, init_tensor=None, init_scale=0.0):
+                  lpips_model=None, init_tensor=None, init_scale=0.0, cutout_resize="pool"):
     """The differentiable body of cond_fn (cgd/cgd.py:177-226) with explicit cutout coordinates; the LPIPS term
     (cgd/cgd.py:220-224) when ``lpips_model`` (oracle/lpips.py) and ``init_tensor`` are given.
     Returns (total_loss, dict of per-term scalars)."""
@@ -82,6 +87,7 @@ def guidance_loss(x, pred_xstart, fac, coords, clip_model, target_embeds, weight
     cutn = len(coords)
     x_in = pred_xstart * fac + x * (1 - fac)
     mk = MakeCutouts(cut_size, cutn)
+    mk.resize = cutout_resize
     clip_in = clip_normalize(mk(x_in.add(1).div(2), coords=coords))
     embeds = clip_model.encode_image(clip_in).float().view([cutn, n, -1])
     dists = spherical_dist_loss(embeds.unsqueeze(0), target_embeds.unsqueeze(0)).view([cutn, n, -1])
@@ -113,13 +119,13 @@ class OracleCondFn:
 
     def __init__(self, diffusion, clip_model, target_embeds, weights, *, cut_size, num_cutouts,
                  cutout_power=1.0, clip_guidance_scale=1000.0, tv_scale=150.0, range_scale=50.0,
-                 sat_scale=0.0, use_magnitude=False, lpips_model=None, init_tensor=None, init_scale=0.0):
+                 sat_scale=0.0, use_magnitude=False, lpips_model=None, init_tensor=None, init_scale=0.0, cutout_resize="pool"):
         self.diffusion, self.clip_model = diffusion, clip_model
         self.target_embeds, self.weights = target_embeds, weights
         self.mk = MakeCutouts(cut_size, num_cutouts, cutout_power)
         self.kw = dict(cut_size=cut_size, clip_guidance_scale=clip_guidance_scale, tv_scale=tv_scale,
                        range_scale=range_scale, sat_scale=sat_scale, lpips_model=lpips_model, init_tensor=init_tensor,
-                       init_scale=init_scale)
+                       init_scale=init_scale, cutout_resize=cutout_resize)
         self.use_magnitude = use_magnitude
         self.current_timestep = diffusion.num_timesteps - 1
         self.last_coords = None

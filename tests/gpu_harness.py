@@ -14,7 +14,7 @@ OUT_PTRS = {"CONV": [4], "GN_STATS": [2], "GN_APPLY": [5], "GN_BWD_STATS": [7], 
             "CUTOUTS_BWD": [2], "SPHERICAL": [3, 4], "PMV_BLEND": [3, 4, 5, 6, 7], "GUIDE_GRAD": [4, 5, 6], "FINAL_GRAD": [2],
             "SAMPLE_ANCESTRAL": [6], "SAMPLE_DDIM": [5], "TRANSPOSE": [1, 3, 5], "SOFTMAX_FWD": [0, 1], "SOFTMAX_BWD": [1],
             "GN_FWD_FUSED": [4, 5], "GN_BWD_FUSED": [6], "GN_FWD_GRID": [4, 5], "GN_BWD_GRID": [6],
-            "RELU_FWD": [1], "RELU_BWD": [2], "MAXPOOL2_FWD": [1], "MAXPOOL2_BWD": [2], "LPIPS_TAP": [3, 4], "FILL": [0]}
+            "RELU_FWD": [1], "RELU_BWD": [2], "MAXPOOL2_FWD": [1], "MAXPOOL2_BWD": [2], "LPIPS_TAP": [3, 4], "FILL": [0], "CUTOUTS_RR_FWD": [2], "CUTOUTS_RR_BWD": [2]}
 
 
 def cpu_twin(plan):
@@ -54,7 +54,7 @@ def compare_ops(plan, ranges, tol_h=4e-3, tol_f=2e-4, verbose=False):
                 err = float((ref - got).abs().max()) / scale
                 bad = not th.isfinite(got).all()
                 tol = tol_h if buf.dt == "h" else tol_f
-                if name in ("ATTN_FWD", "ATTN_BWD", "SPHERICAL", "GN_BWD_APPLY", "GN_BWD_STATS", "GN_BWD_FUSED", "GN_BWD_GRID", "LN_BWD", "CUTOUTS_BWD", "SOFTMAX_FWD", "SOFTMAX_BWD"):
+                if name in ("ATTN_FWD", "ATTN_BWD", "SPHERICAL", "GN_BWD_APPLY", "GN_BWD_STATS", "GN_BWD_FUSED", "GN_BWD_GRID", "LN_BWD", "CUTOUTS_BWD", "CUTOUTS_RR_BWD", "SOFTMAX_FWD", "SOFTMAX_BWD"):
                     tol = max(tol, 4e-3)
                 if verbose or bad or err > tol:
                     rec = dict(op=k, code=name, tag=op.tag, slot=slot, buf=buf.name, err=err, ref_max=scale, got_max=float(got.abs().max()),

@@ -425,6 +425,39 @@ class Interp:
         (gx,) = th.autograd.grad(((cuts + 1) * 0.5 / std * dimg).sum(), x)
         self.V(op.p[2], (B, 3, H, W), (3 * H * W, H * W, W, 1)).copy_(gx * op.f[6])
 
+    def _rr_resize(self, op, crop, k):
+        """separable resample of crop [B,3,S,S] with cutout k's device tables (left, weights, taps): zero outside the crop"""
+        cs = op.i[4]
+        S = crop.shape[-1]
+        left = self.V(op.p[3], (op.i[3], cs), (cs, 1))[k].long()
+        w = self.V(op.p[4], (op.i[3], cs, 16), (cs * 16, 16, 1))[k]
+        idx = left[:, None] + th.arange(16)
+        wv = w * ((idx >= 0) & (idx < S))
+        idc = idx.clamp(0, S - 1)
+        rows = (crop[:, :, idc, :] * wv[None, None, :, :, None]).sum(3)      # [B,3,cs,S]
+        return (rows[:, :, :, idc] * wv[None, None, None, :, :]).sum(4)      # [B,3,cs,cs]
+
+    def op_CUTOUTS_RR_FWD(self, op):
+        B, H, W, cutn, cs, P, kpad = op.i[:7]
+        x = self.V(op.p[0], (B, 3, H, W), (3 * H * W, H * W, W, 1))
+        mean = th.tensor(op.f[0:3]).view(1, 3, 1, 1)
+        std = th.tensor(op.f[3:6]).view(1, 3, 1, 1)
+        cuts = [self._rr_resize(op, x[:, :, oy:oy + s, ox:ox + s], k) for k, (ox, oy, s) in enumerate(self._coords(op))]
+        img = ((th.cat(cuts) + 1) * 0.5 - mean) / std
+        g2 = (cs // P) ** 2
+        self.V(op.p[2], (cutn * B, g2, kpad), (g2 * kpad, kpad, 1)).copy_(self._patchify(img, P, kpad))
+
+    def op_CUTOUTS_RR_BWD(self, op):
+        B, H, W, cutn, cs, P, kpad = op.i[:7]
+        g2 = (cs // P) ** 2
+        dp = self.V(op.p[0], (cutn * B, g2, kpad), (g2 * kpad, kpad, 1)).float()
+        dimg = self._unpatchify(dp, P, cs)
+        std = th.tensor(op.f[3:6]).view(1, 3, 1, 1)
+        x = th.zeros(B, 3, H, W, requires_grad=True)
+        cuts = th.cat([self._rr_resize(op, x[:, :, oy:oy + s, ox:ox + s], k) for k, (ox, oy, s) in enumerate(self._coords(op))])
+        (gx,) = th.autograd.grad(((cuts + 1) * 0.5 / std * dimg).sum(), x)
+        self.V(op.p[2], (B, 3, H, W), (3 * H * W, H * W, W, 1)).copy_(gx * op.f[6])
+
     def op_SPHERICAL(self, op):
         cutn, B, P, D = op.i[:4]
         emb = self.V(op.p[0], (cutn, B, D), (B * D, D, 1)).clone().requires_grad_()

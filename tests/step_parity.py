@@ -31,7 +31,7 @@ def prod_unet_cfg(ocfg):
 
 
 def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0, respacing="25", conv_impl=0, use_graph=False, P=1,
-               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0):
+               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool"):
     ocfg = tiny_config(image_size=image, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(image // 2,),
                        class_cond=True, use_new_attention_order=new_order)
     ounet = seeded_init_(UNetModel(ocfg)).eval()
@@ -53,10 +53,10 @@ def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0
         init = th.rand(1, 3, image, image, generator=th.Generator().manual_seed(7)) * 2 - 1
     eng = pg.GuidedStepB200(prod_unet_cfg(ocfg), ounet.state_dict(), pv.ViTConfig(32, 16, 128, 2, 64), oclip.state_dict(), batch=B,
                             num_cutouts=cutn, max_prompts=P, use_magnitude=use_magnitude, device=device, conv_impl=conv_impl,
-                            use_graph=use_graph, vit_streams=vit_streams, cutn_variants=cutn_variants, lpips_sd=lp_sd, init_scale=init_scale, **kw)
+                            use_graph=use_graph, vit_streams=vit_streams, cutn_variants=cutn_variants, lpips_sd=lp_sd, init_scale=init_scale, cutout_resize=cutout_resize, **kw)
     eng.set_targets(targets, weights)
     return dict(ounet=ounet, oclip=oclip, odiff=odiff, pdiff=pdiff, eng=eng, targets=targets, weights=weights, kw=kw, olp=olp, init=init,
-                init_scale=init_scale,
+                init_scale=init_scale, cutout_resize=cutout_resize,
                 use_magnitude=use_magnitude, cutn=run_cutn or cutn, B=B, image=image)
 
 
@@ -64,7 +64,7 @@ def oracle_step(ctx, mode, x, t_index, y, noise_seed, coords, fac_index):
     odiff = ctx["odiff"]
     cond = og.OracleCondFn(odiff, ctx["oclip"], ctx["targets"], ctx["weights"], cut_size=32, num_cutouts=ctx["cutn"],
                            use_magnitude=ctx["use_magnitude"], lpips_model=ctx.get("olp"), init_tensor=ctx.get("init"),
-                           init_scale=ctx.get("init_scale", 0.0), **ctx["kw"])
+                           init_scale=ctx.get("init_scale", 0.0), cutout_resize=ctx.get("cutout_resize", "pool"), **ctx["kw"])
     cond.current_timestep = fac_index
     grabbed = {}
 

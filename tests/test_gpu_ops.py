@@ -16,8 +16,9 @@ SEGS = [("unet_emb", "unet_bwd"), ("pmv", "cond"), ("cut_fwd", "sph"), ("vit_fwd
         ("upd_ddim_g", "upd_ddim")]
 
 
-@pytest.mark.parametrize("kw", [dict(image=32), dict(image=64, B=1, cutn=2, use_magnitude=True, sat_scale=20.0, new_order=True)],
-                         ids=["b2_32px", "b1_64px_mag_sat_neworder"])
+@pytest.mark.parametrize("kw", [dict(image=32), dict(image=64, B=1, cutn=2, use_magnitude=True, sat_scale=20.0, new_order=True),
+                                dict(image=64, B=2, cutn=3, cutout_resize="lanczos3")],
+                         ids=["b2_32px", "b1_64px_mag_sat_neworder", "b2_64px_resize_right"])
 def test_every_op_matches_interpreter(kw):
     ctx = build_tiny("cuda", conv_impl=IMPL, **kw)
     eng = ctx["eng"]
@@ -71,3 +72,14 @@ def test_step_with_lpips_init_loss_vs_oracle():
     res = compare(o, e)
     assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res
     assert abs(float(e["losses"]["init"].sum()) - o["terms"]["init"]) / abs(o["terms"]["init"]) < 3e-2
+
+
+def test_step_with_resize_right_cutouts_vs_oracle():
+    """Cutouts resampled by the ResizeRight lanczos3 tables (the mode north_star names) instead of pooling: graph replay vs the
+    oracle whose MakeCutouts calls the pinned restatement of cgd/ResizeRight/resize_right.py."""
+    ctx = build_tiny("cuda", conv_impl=IMPL, image=64, use_graph=True, B=2, cutn=3, cutout_resize="lanczos3")
+    x, y, noise, nseed, coords = make_inputs(ctx)
+    o = oracle_step(ctx, "ancestral", x, 14, y, nseed, coords, fac_index=14)
+    e = engine_step(ctx, "ancestral", x, 14, y, noise, coords, fac_index=14, fused=True)
+    res = compare(o, e)
+    assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res

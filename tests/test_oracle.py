@@ -142,3 +142,45 @@ def test_tiny_unet_and_step_run():
                                              cond_fn=cond, randomize_class=True, cond_fn_with_grad=True)
     o = next(gen2)
     assert th.isfinite(o["sample"]).all()
+
+
+# ------------------------------------------------------------------ ResizeRight (cutout resize mode named by north_star)
+RR_CASES = ["down_237_224", "down_64_56", "down_60_32", "down_73_32", "same_32", "up_16_56", "up_20_32"]
+
+
+@pytest.mark.parametrize("name", RR_CASES)
+def test_resize_right_restatement_pinned_to_reference(name):
+    """oracle/resize_right.py against vectors produced by the reference's own cgd/ResizeRight (tests/golden/make_golden_resize.py):
+    forward bit-exact, autograd gradient to float rounding."""
+    import os
+    import numpy as np
+    from oracle.resize_right import resize_lanczos3
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "resize_right_golden.npz"))
+    S, O, C = (int(v) for v in d[name + "_shape"])
+    x = th.from_numpy(d[name + "_x"]).requires_grad_()
+    y = resize_lanczos3(x, (O, O))
+    assert th.equal(y.detach(), th.from_numpy(d[name + "_y"]))
+    (g,) = th.autograd.grad((y * th.from_numpy(d[name + "_w"])).sum(), x)
+    assert th.allclose(g, th.from_numpy(d[name + "_g"]), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", RR_CASES)
+def test_resize_tables_reproduce_reference(name):
+    """the product's host tables (clip_guided_diffusion_b200/resize_right.py) applied separably == the reference's output"""
+    import os
+    import numpy as np
+    from clip_guided_diffusion_b200 import resize_right as rr
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "resize_right_golden.npz"))
+    S, O, C = (int(v) for v in d[name + "_shape"])
+    left, w, T = rr.tables(S, O)
+    x = th.from_numpy(d[name + "_x"])[0]
+    idx = left[:, None].long() + th.arange(rr.T_MAX)
+    wv = w * ((idx >= 0) & (idx < S))
+    idc = idx.clamp(0, S - 1)
+    rows = (x[:, idc, :] * wv[None, :, :, None]).sum(2)
+    out = (rows[:, :, idc] * wv[None, None, :, :]).sum(3)
+    assert th.allclose(out, th.from_numpy(d[name + "_y"])[0], atol=1e-6)
+    inv = rr.inverse_ranges(left, T, S)
+    for r in (0, S // 3, S - 1):  # every output whose field of view holds r lies in [lo, hi], and none outside
+        touching = [o for o in range(O) if left[o] <= r <= left[o] + T - 1]
+        assert touching == list(range(int(inv[r, 0]), int(inv[r, 1]) + 1))

@@ -14,9 +14,10 @@ def _interp_runner(eng):
 @pytest.mark.parametrize("mode,kw", [("ancestral", {}), ("ddim", {}), ("ancestral", dict(use_magnitude=True, sat_scale=30.0)),
                                      ("ddim", dict(B=1, P=2, cutn=2)), ("ddim", dict(B=2, cutn=4, vit_streams=2)),
                                      ("ancestral", dict(B=1, cutn=8, cutn_variants=(2, 4, 8), run_cutn=4)),
-                                     ("ddim", dict(B=2, cutn=2, init_scale=1000.0))])
+                                     ("ddim", dict(B=2, cutn=2, init_scale=1000.0)),
+                                     ("ancestral", dict(B=2, cutn=3, image=64, cutout_resize="lanczos3"))])
 def test_step_plan_matches_oracle(mode, kw):
-    res = run_tiny_step_parity(device="cpu", mode=mode, runner_factory=_interp_runner, image=32, **kw)
+    res = run_tiny_step_parity(device="cpu", mode=mode, runner_factory=_interp_runner, **{"image": 32, **kw})
     assert res["cos_g"] > 0.999, res
     assert res["rel_g"] < 5e-2 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res
     assert res["clip_loss_rel"] < 2e-2 and res["tv_loss_rel"] < 1e-3 and res["range_loss_rel"] < 1e-2, res
