@@ -26,7 +26,20 @@ import torch as th
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(image_size=256, respacing="ddim250", per_gpu_batch=1, cutn=16, clip="ViT-B/32")
+# per-GPU shards of the BASELINE.json configurations; cfg2 is the metric's configuration (the default and the only one the driver
+# runs), the others are extra measurements (--workload).  tflop = algorithmic FLOPs per image-step (fwd + dgrad).
+WORKLOADS = {
+    "cfg2": dict(image_size=256, respacing="ddim250", per_gpu_batch=1, cutn=16, clip="ViT-B/32", lpips=False, tflop=4.775,
+                 name="BASELINE configs[1]: image_size=256, respace=ddim250, batch=1 per GPU, cutn=16, ViT-B/32"),
+    "cfg3": dict(image_size=256, respacing="1000", per_gpu_batch=1, cutn=32, clip="ViT-B/32", lpips=False, tflop=5.059,
+                 name="BASELINE configs[2] shard: image_size=256, respace=1000 (ancestral), batch=1 per GPU, cutn=32, ViT-B/32"),
+    "cfg4": dict(image_size=512, respacing="ddim250", per_gpu_batch=1, cutn=16, clip="ViT-B/16", lpips=False, tflop=9.09,
+                 name="BASELINE configs[3] shard: image_size=512, respace=ddim250, batch=1 per GPU, cutn=16, ViT-B/16"),
+    "cfg5": dict(image_size=512, respacing="1000", per_gpu_batch=1, cutn=64, clip="ViT-L/14", lpips=True, tflop=29.1,
+                 name="BASELINE configs[4] shard: image_size=512, respace=1000 (ancestral), batch=1 per GPU, cutn=64, ViT-L/14, "
+                      "init image + LPIPS init_scale=1000 (LPIPS FLOPs not counted)"),
+}
+CFG = WORKLOADS["cfg2"]
 FLOP_PER_IMAGE_STEP = 4.775e12  # UNet 2.240+2.252, CLIP 0.141+0.143 TFLOP (fwd + dgrad)
 DOMINANT = dict(M=65536, N=256, K=2304)  # 256^2 x 256ch conv3x3: 31 % of the UNet FLOPs
 
@@ -82,8 +95,11 @@ def build_engine(device, rank, world):
     vcfg = pv.VIT_CONFIGS[CFG["clip"]]
     usd = pw.seeded_state_dict(pw.unet_param_shapes(ucfg), seed=1234)
     vsd = pw.seeded_state_dict(pw.vit_param_shapes(vcfg), seed=1235)
+    extra = dict(lpips_sd=pw.seeded_lpips_state_dict(), init_scale=1000.0) if CFG["lpips"] else {}
     eng = pg.GuidedStepB200(ucfg, usd, vcfg, vsd, batch=CFG["per_gpu_batch"], num_cutouts=CFG["cutn"], device=device, rank=rank,
-                            world_size=world, vit_streams=int(os.environ.get("CGD_VIT_STREAMS", "1")))
+                            world_size=world, vit_streams=int(os.environ.get("CGD_VIT_STREAMS", "1")), **extra)
+    if CFG["lpips"]:
+        eng.set_init_image((th.rand(1, 3, CFG["image_size"], CFG["image_size"], generator=th.Generator().manual_seed(5)) * 2 - 1).to(device))
     del usd, vsd
     diff = gd.create_gaussian_diffusion(1000, "linear", CFG["respacing"])
     th.manual_seed(0)
@@ -135,6 +151,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     eng, diff, cond = build_engine(device, rank, world)
+    MODE = "ddim" if CFG["respacing"].startswith("ddim") else "ancestral"
     B = eng.B
     T = diff.num_timesteps
     y0 = th.zeros(eng.global_batch, dtype=th.long)
@@ -144,7 +161,7 @@ def run_ours(args):
         # few steps (pred_xstart ~ 1e3 and growing), which says nothing about throughput; timing is value-independent
         img = eng.draw_initial_noise()
         y = eng.draw_classes()
-        out = eng.fused_step(diff, "ddim", i, img, y, cond, 0.0)
+        out = eng.fused_step(diff, MODE, i, img, y, cond, 0.0)
         cond.current_timestep = max(cond.current_timestep - 1, 0)
         return out["sample"]
 
@@ -189,7 +206,7 @@ def run_ours(args):
     def step_host(i):
         y = th.randint(0, eng.unet.num_classes, (B,))  # host-side class draw, staged with the other per-step data
         eng.img(eng.unet.x_in).copy_(host_x, non_blocking=True)
-        out = eng.fused_step(diff, "ddim", i, eng.img(eng.unet.x_in), y, cond, 0.0)
+        out = eng.fused_step(diff, MODE, i, eng.img(eng.unet.x_in), y, cond, 0.0)
         host_out.copy_(out["sample"], non_blocking=True)
         th.cuda.current_stream().synchronize()
 
@@ -216,7 +233,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     pk = peaks()
-    launches = eng.launches_per_step("ddim")
+    launches = eng.launches_per_step(MODE)
     value = args.steps * eng.global_batch / (ms_total * 1e-3)
     e2e = args.steps * eng.global_batch / (ms_e2e * 1e-3)
     # roofline of the dominant kernel, timed alone right after the step loops
@@ -228,11 +245,11 @@ def run_ours(args):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     line = {
-        "metric": "diffusion-steps/sec", "value": value, "unit": "image-steps/s (1 step of one 256x256 image, 16 cutouts)",
+        "metric": "diffusion-steps/sec", "value": value,
+        "unit": f"image-steps/s (1 step of one {CFG['image_size']}x{CFG['image_size']} image, {CFG['cutn']} cutouts)",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate / norm / softmax / sampler)", "data": "synthetic (x_t ~ N(0,1) redrawn every step, seeded random weights)",
-        "config": {"workload": "BASELINE configs[1]: image_size=256, respace=ddim250, batch=1 per GPU, cutn=16, ViT-B/32, class-cond UNet, "
-                               "seeded random weights", "global_batch": eng.global_batch, "parallelism": f"dp{world} (batch shard, no data-path collective)",
+        "config": {"workload": CFG["name"] + ", class-cond UNet, seeded random weights", "global_batch": eng.global_batch, "parallelism": f"dp{world} (batch shard, no data-path collective)",
                    "l2": "per-step working set (2.3 GB of packed weights + activations) exceeds the 126 MB L2; no explicit flush",
                    "finite": finite},
         "e2e": {"value": e2e, "unit": "image-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
@@ -242,7 +259,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"], "traffic": traffic,
                      "kernel": "conv_tc2_kernel<256> 256x256x256->256 3x3 (M=65536,N=256,K=2304)", "peak_source": pk["src"] + " burst (kernel timed alone)",
                      "avg_launch_s": t_dom},
-        "step_tensor_frac": FLOP_PER_IMAGE_STEP * value / world / (pk["sustained"] * 1e12),
+        "step_tensor_frac": CFG["tflop"] * 1e12 * value / world / (pk["sustained"] * 1e12),
     }
     if world == 1 and args.torch_baseline:
         del eng
@@ -251,7 +268,7 @@ def run_ours(args):
             line["torch_cuda_baseline"] = torch_cuda_baseline(device, max(5, args.steps // 2))
         except Exception as e:  # context only: never lose the measured line
             line["torch_cuda_baseline"] = {"error": repr(e)[:300]}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2":
         line["cpu_baseline"] = cpu_baseline(sample_steps=1)
     print(json.dumps(line))
     if world > 1:
@@ -402,7 +419,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-baseline", action="store_true", help="also time the PyTorch-CUDA (cuDNN/cuBLAS eager autograd) oracle port")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="per-GPU shard of a BASELINE.json configuration (default: the metric's)")
     args = ap.parse_args()
+    global CFG
+    CFG = WORKLOADS[args.workload]
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)

@@ -94,6 +94,45 @@ __device__ __forceinline__ float silu_grad_f(float v) {
   return s * (1.f + v * (1.f - s));
 }
 
+// packed fp32 pairs (FFMA2 / FMUL2 / FADD2 in SASS, sm_100+): two lanes per issue slot for the issue-bound normalisation kernels
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; "
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// silu on a pair: t * 1 / (1 + 2^(-log2e * t))
+__device__ __forceinline__ float2 silu2(float2 t) {
+  const float2 u = mul2(t, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 d = add2(make_float2(ex2_ftz(u.x), ex2_ftz(u.y)), make_float2(1.f, 1.f));
+  return mul2(t, make_float2(rcp_ftz(d.x), rcp_ftz(d.y)));
+}
+// d silu / dt on a pair: s * (1 + t * (1 - s))
+__device__ __forceinline__ float2 silu_grad2(float2 t) {
+  const float2 u = mul2(t, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 d = add2(make_float2(ex2_ftz(u.x), ex2_ftz(u.y)), make_float2(1.f, 1.f));
+  const float2 s = make_float2(rcp_ftz(d.x), rcp_ftz(d.y));
+  const float2 one = make_float2(1.f, 1.f);
+  const float2 w = fma2(t, fma2(s, make_float2(-1.f, -1.f), one), one);  // 1 + t * (1 - s)
+  return mul2(s, w);
+}
+
 // ---------------------------------------------------------------- global-memory barrier among co-resident CTAs
 // bar[0] = arrival count (returns to 0), bar[1] = generation (only ever incremented): reusable across launches / graph replays
 // without a reset.  Called by ONE thread per CTA after a block-level barrier; acquire / release atomics instead of

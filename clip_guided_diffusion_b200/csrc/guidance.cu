@@ -356,11 +356,13 @@ int launch_pmv_blend(const CgdOp& op, cudaStream_t st) {
 // grid (chunks, B).  loss layout: [tv(B) | range(B) | sat(B)] accumulated with atomics (logging only).
 __global__ void guide_grad_kernel(const float* __restrict__ xin, const float* __restrict__ x0, const float* __restrict__ gclip,
                                   const float* __restrict__ sc, __half* __restrict__ seed, float* __restrict__ dxd, float* __restrict__ loss,
-                                  int B, int H, int W, int64_t ld, float tvs, float rs, float ss, float seed_scale) {
+                                  int B, int H, int W, int64_t ld, float tvs, float rs, float ss, float seed_scale,
+                                  float* __restrict__ seed_f32, float* __restrict__ dyn) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float red[32];
   const int b = blockIdx.y;
+  float amax = 0.f;
   const int64_t HW = (int64_t)H * W, per = 3 * HW;
   const float a = sc[CGD_SC_SQRT_RECIP_AC], bb = sc[CGD_SC_SQRT_RECIPM1_AC], fac = sc[CGD_SC_FAC], omf = sc[CGD_SC_ONE_MINUS_FAC];
   const float inv_n = 1.f / (float)per;
@@ -389,8 +391,18 @@ __global__ void guide_grad_kernel(const float* __restrict__ xin, const float* __
     const float d_x0 = fac * d_xin + rs * inv_n * 2.f * er;
     // pred_xstart = a*x - bb*eps  =>  d/d eps = -bb * d_x0 (UNet dgrad seed), direct d/dx = a * d_x0
     // saturate instead of overflowing to inf: a diverged chain (e.g. random weights) must not poison the fp16 backward with NaNs
-    seed[((int64_t)b * HW + p) * ld + c] = __float2half_rn(fminf(fmaxf(-bb * d_x0 * seed_scale, -60000.f), 60000.f));
+    if (seed_f32) {  // dynamic scaling: the fp16 seed is written by seed_quant_kernel once the per-image maximum is known
+      const float v = -bb * d_x0;
+      seed_f32[((int64_t)b * HW + p) * 3 + c] = v;
+      amax = fmaxf(amax, fminf(fabsf(v), 3.0e38f));  // fminf drops a NaN, an inf counts as the largest finite value
+    } else {
+      seed[((int64_t)b * HW + p) * ld + c] = __float2half_rn(fminf(fmaxf(-bb * d_x0 * seed_scale, -60000.f), 60000.f));
+    }
     dxd[((int64_t)b * 3 + c) * HW + p] = omf * d_xin + a * d_x0;
+  }
+  if (seed_f32) {
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<int*>(dyn) + b, __float_as_int(amax));  // non-negative floats order like ints
   }
   l_tv = block_sum(l_tv, red);
   l_r = block_sum(l_r, red);
@@ -401,13 +413,47 @@ __global__ void guide_grad_kernel(const float* __restrict__ xin, const float* __
     if (ss != 0.f) atomicAdd(&loss[2 * B + b], l_s * inv_n / (float)B * ss);
   }
 }
+// Dynamic seed scaling (flags & 1 of GUIDE_GRAD): d L / d eps = -sqrt(1/abar - 1) * d L / d pred_xstart spans many orders of
+// magnitude over a chain (the factor alone runs from 0.01 to 157) and is the seed of an fp16 backward.  Per image, the seed is
+// multiplied by the power of two that puts its largest element at [2048, 4096) (exact in fp16, 16x headroom for growth inside
+// the backward, 2^-24 / 4096 of dynamic range below), and FINAL_GRAD divides the input gradient by the same factor.
+// dyn layout: [B] max |seed| (float bits, reset to 0 by FINAL_GRAD) | [B] scale.
+__global__ void seed_quant_kernel(const float* __restrict__ seed_f32, float* __restrict__ dyn, __half* __restrict__ seed, int B, int64_t HW,
+                                  int64_t ld) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y;
+  const float m = dyn[b];
+  float scale = 1.f;
+  if (m > 0.f) scale = exp2f(fminf(fmaxf(floorf(log2f(4096.f / m)), -60.f), 60.f));
+  if (blockIdx.x == 0 && threadIdx.x == 0) dyn[B + b] = scale;
+  const int64_t per = 3 * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / 3;
+    const int c = (int)(i - p * 3);
+    seed[((int64_t)b * HW + p) * ld + c] = __float2half_rn(fminf(fmaxf(seed_f32[(int64_t)b * per + i] * scale, -60000.f), 60000.f));
+  }
+}
+int launch_seed_quant(const CgdOp& op, cudaStream_t st) {
+  const int64_t B = op.i[0], HW = op.i[1], ld = op.i[2];
+  CGD_CHECK_ARG(B > 0 && HW > 0 && ld >= 3 && op.p[0] && op.p[1] && op.p[2], "seed_quant: bad args");
+  const int chunks = (int)std::min<int64_t>(ceil_div(3 * HW, 256 * 4), std::max<int64_t>(1, 592 / B));
+  CGD_CUDA(launch_pdl(seed_quant_kernel, dim3(chunks, (unsigned)B), dim3(256), 0, st, (const float*)op.p[0], (float*)op.p[1], (__half*)op.p[2], (int)B,
+                      HW, ld));
+  CGD_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_guide_grad(const CgdOp& op, cudaStream_t st) {
   const int64_t B = op.i[0], H = op.i[1], W = op.i[2], ld = op.i[3];
   CGD_CHECK_ARG(B > 0 && H > 0 && W > 0 && ld >= 3 && op.p[0] && op.p[1] && op.p[3] && op.p[4] && op.p[5], "guide_grad: bad args");
+  const bool dynamic = op.flags & 1;
+  CGD_CHECK_ARG(!dynamic || (op.p[7] && op.p[8]), "guide_grad: dynamic seed scaling needs p7 (fp32 seed) and p8 (max / scale)");
   int chunks = (int)std::min<int64_t>(ceil_div(3 * H * W, 256 * 4), std::max<int64_t>(1, 592 / B));
   CGD_CUDA(launch_pdl(guide_grad_kernel, dim3(chunks, (unsigned)B), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2],
                                                               (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (float*)op.p[6], (int)B,
-                                                              (int)H, (int)W, ld, op.f[0], op.f[1], op.f[2], op.f[3]));
+                                                              (int)H, (int)W, ld, op.f[0], op.f[1], op.f[2], op.f[3],
+                                                              dynamic ? (float*)op.p[7] : (float*)nullptr, dynamic ? (float*)op.p[8] : (float*)nullptr));
   CGD_LAUNCH_CHECK();
   return 0;
 }
@@ -415,20 +461,22 @@ int launch_guide_grad(const CgdOp& op, cudaStream_t st) {
 // ---------------------------------------------------------------- final gradient (+ optional RMS clamp)
 constexpr int FG_BLOCKS = 128;
 __global__ void final_grad_kernel(const float* __restrict__ dxd, const float* __restrict__ dxu, float* __restrict__ g, int64_t n,
-                                  float inv_scale, float* __restrict__ ws) {
+                                  float inv_scale, float* __restrict__ ws, float* __restrict__ dyn, int B, int64_t per) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float red[32];
   float ssq = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = dxd[i];
-    if (dxu) v += dxu[i] * inv_scale;
+    if (dxu) v += dxu[i] * (dyn ? 1.f / dyn[B + i / per] : inv_scale);  // the scale is a power of two: the reciprocal is exact
     v = -v;
     g[i] = v;
     ssq = fmaf(v, v, ssq);
   }
   ssq = block_sum(ssq, red);
   if (threadIdx.x == 0 && ws) ws[blockIdx.x] = ssq;
+  if (dyn && blockIdx.x == 0)  // re-arm the running maximum for the next step (GUIDE_GRAD of step k+1 is a later launch)
+    for (int b = threadIdx.x; b < B; b += blockDim.x) dyn[b] = 0.f;
 }
 __global__ void magnitude_clamp_kernel(float* __restrict__ g, int64_t n, const float* __restrict__ ws, int nparts, float max_rms) {
   pdl_wait();
@@ -449,8 +497,10 @@ int launch_final_grad(const CgdOp& op, cudaStream_t st) {
   const int64_t n = B * 3 * HW;
   CGD_CHECK_ARG(n > 0 && op.p[0] && op.p[2], "final_grad: bad args");
   const bool mag = op.flags & 1;
+  CGD_CHECK_ARG(!(op.flags & 2) || op.p[4], "final_grad: dynamic seed scaling needs p4 (max / scale)");
   if (mag) CGD_CHECK_ARG(op.p[3] != nullptr, "final_grad: magnitude clamp needs a %d-float workspace", FG_BLOCKS);
-  CGD_CUDA(launch_pdl(final_grad_kernel, dim3(FG_BLOCKS), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (float*)op.p[2], n, op.f[0], (float*)op.p[3]));
+  CGD_CUDA(launch_pdl(final_grad_kernel, dim3(FG_BLOCKS), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (float*)op.p[2], n, op.f[0], (float*)op.p[3],
+                      (op.flags & 2) ? (float*)op.p[4] : (float*)nullptr, (int)B, 3 * HW));
   CGD_LAUNCH_CHECK();
   if (mag) {
     CGD_CUDA(launch_pdl(magnitude_clamp_kernel, dim3(FG_BLOCKS), dim3(256), 0, st, (float*)op.p[2], n, (const float*)op.p[3], FG_BLOCKS, op.f[1]));

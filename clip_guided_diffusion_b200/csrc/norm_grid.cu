@@ -14,6 +14,8 @@
 // being crossed.  HBM traffic: x once + y once (forward), dy + x once + dx (backward).
 //
 // Replaces [3P] guided-diffusion GroupNorm32 + SiLU + scale-shift and their autograd.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ops.cuh"
 #include "pdl.cuh"
@@ -428,6 +430,25 @@ static int gng_check(const char* what, int64_t N, int64_t HW, int64_t C, int64_t
                 what, (long long)N, (long long)Gn, kGngCtasPerSm, sms);
   return 0;
 }
+// norm_grid2.cu: the direct-load engine (C % 256 == 0)
+bool gn_grid2_supports(int64_t C);
+int launch_gn_fwd_grid2(const CgdOp& op, cudaStream_t st);
+int launch_gn_bwd_grid2(const CgdOp& op, cudaStream_t st);
+// Measured (profiles/r01_gn_microbench_v4.txt): the direct-load engine wins the backward of the 256x256 level (51 vs 57 us at
+// C = 256, 86 vs 104 us at C = 512: two input streams, SiLU' recomputed twice -- the ring's 16 consumer warps are issue-bound
+// there), ties at 128x128 x 512 and loses 3 - 5 us everywhere else (its 1024-thread CTAs start and synchronise more slowly).
+// CGD_GN_GRID_ENGINE = ring | direct forces one engine for A/B runs.
+static bool gng_use_direct(bool backward, int64_t HW, int64_t C) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("CGD_GN_GRID_ENGINE");
+    forced = !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'd' ? 2 : 0));
+  }
+  if (!gn_grid2_supports(C) || forced == 1) return false;
+  if (forced == 2) return true;
+  return backward && HW * C >= (int64_t(1) << 23);
+}
+
 template <typename K>
 static int gng_prepare(K kernel) {
   CGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGngDynSmem));
@@ -441,6 +462,7 @@ int launch_gn_fwd_grid(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], HW = op.i[1], C = op.i[2], ldx = op.i[3], ldy = op.i[4], Gn = op.i[5];
   if (int rc = gng_check("gn_fwd_grid", N, HW, C, Gn)) return rc;
   CGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[4] && op.p[5] && op.p[6] && op.p[7], "gn_fwd_grid: bad args");
+  if (gng_use_direct(false, HW, C)) return launch_gn_fwd_grid2(op, st);
   static bool set = false;
   if (!set) {
     if (int rc = gng_prepare(gn_fwd_grid_kernel)) return rc;
@@ -458,6 +480,7 @@ int launch_gn_bwd_grid(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(ld_dy % 8 == 0 && ldx % 8 == 0 && ld_dx % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[3] && op.p[4] && op.p[6] && op.p[7] &&
                     op.p[8],
                 "gn_bwd_grid: bad args");
+  if (gng_use_direct(true, HW, C)) return launch_gn_bwd_grid2(op, st);
   static bool set = false;
   if (!set) {
     if (int rc = gng_prepare(gn_bwd_grid_kernel)) return rc;

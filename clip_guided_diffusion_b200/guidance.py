@@ -107,7 +107,7 @@ class GuidedStepB200:
 
     def __init__(self, unet_cfg: UNetConfig, unet_sd: dict, vit_cfg: ViTConfig = None, vit_sd: dict = None, *, batch: int,
                  height: int = None, width: int = None, num_cutouts: int = 16, max_prompts: int = 1, clip_guidance_scale=1000.0,
-                 tv_scale=150.0, range_scale=50.0, sat_scale=0.0, use_magnitude=False, device="cuda", seed_scale=16.0,
+                 tv_scale=150.0, range_scale=50.0, sat_scale=0.0, use_magnitude=False, device="cuda", seed_scale=0.0,
                  vit_grad_scale=1.0, conv_impl=0, rank: int = 0, world_size: int = 1, use_graph: bool = True, vit_streams: int = 1,
                  cutn_variants: tuple = (), lpips_sd: dict = None, init_scale: float = 0.0, cutout_resize: str = "pool"):
         self.device = th.device(device)
@@ -124,7 +124,7 @@ class GuidedStepB200:
         self.use_graph = use_graph and self.device.type == "cuda"
         self.plan = p = Plan(conv_impl=conv_impl)
         B, H, W, HW = self.B, self.H, self.W, self.H * self.W
-        self.unet = UNetB200(unet_cfg, unet_sd, batch=B, height=H, width=W, device=device, seed_scale=seed_scale, plan=p,
+        self.unet = UNetB200(unet_cfg, unet_sd, batch=B, height=H, width=W, device=device, seed_scale=seed_scale or 1.0, plan=p,
                              build_backward=vit_cfg is not None)
         n3 = B * 3 * HW
         self.sc = p.new(SC["COUNT"], "f", "scalars")
@@ -200,12 +200,21 @@ class GuidedStepB200:
                 # d (init_scale * lpips_vgg(x_in, init).sum()) / d x_in is added to the x_in gradient the cutout backward left in g_clip
                 self.lpips = LpipsB200(lpips_sd, B, H, W, p, self.x_inb, self.g_clip, init_scale)
             p.mark("guide")
-            p.emit("GUIDE_GRAD", i=[B, H, W, IN_PAD], f=[self.scales["tv"], self.scales["rng"], self.scales["sat"], self.seed_scale],
-                   p=[(self.x_inb, 0), (self.x0, 0), (self.g_clip, 0), (self.sc, 0), (self.unet.seed, 0), (self.dx_direct, 0), (self.loss, B)],
-                   tag="tv+range+sat")
+            # seed_scale > 0: static loss scale; seed_scale = 0 (default): per-image power-of-two scale chosen on the device every step
+            dyn = self.seed_scale == 0.0
+            if dyn:
+                self.seed_f32 = p.new(n3, "f", "seed_f32")
+                self.seed_dyn = p.new(2 * B, "f", "seed_dyn")
+            p.emit("GUIDE_GRAD", flags=1 if dyn else 0, i=[B, H, W, IN_PAD],
+                   f=[self.scales["tv"], self.scales["rng"], self.scales["sat"], self.seed_scale],
+                   p=[(self.x_inb, 0), (self.x0, 0), (self.g_clip, 0), (self.sc, 0), (self.unet.seed, 0), (self.dx_direct, 0), (self.loss, B)]
+                   + ([(self.seed_f32, 0), (self.seed_dyn, 0)] if dyn else []), tag="tv+range+sat")
+            if dyn:
+                p.emit("SEED_QUANT", i=[B, HW, IN_PAD], p=[(self.seed_f32, 0), (self.seed_dyn, 0), (self.unet.seed, 0)], tag="seed scale")
             p.mark("final")
-            p.emit("FINAL_GRAD", flags=1 if self.use_magnitude else 0, i=[B, HW], f=[1.0 / self.seed_scale, 0.05],
-                   p=[(self.dx_direct, 0), (self.unet.dx, 0), (self.g, 0), (self.fg_ws, 0)], tag="-grad")
+            p.emit("FINAL_GRAD", flags=(1 if self.use_magnitude else 0) | (2 if dyn else 0), i=[B, HW],
+                   f=[1.0 / self.seed_scale if not dyn else 0.0, 0.05],
+                   p=[(self.dx_direct, 0), (self.unet.dx, 0), (self.g, 0), (self.fg_ws, 0)] + ([(self.seed_dyn, 0)] if dyn else []), tag="-grad")
         n = n3
         p.mark("upd_anc_g")
         p.emit("SAMPLE_ANCESTRAL", i=[n], p=[(self.mean, 0), (self.var, 0), (self.logvar, 0), (self.g, 0), (self.noise, 0), (self.sc, 0), (self.sample, 0)])

@@ -84,6 +84,33 @@ def vit_param_shapes(cfg: ViTConfig) -> dict:
     return sh
 
 
+def lpips_param_shapes() -> dict:
+    """lpips.LPIPS(net='vgg') v0.1: ``net.sliceK.<vgg16.features index>.{weight,bias}`` + ``linK.model.1.weight``"""
+    from .lpips import CHANNELS, SLICES
+    sh, cin = {}, 3
+    for k, idxs in enumerate(SLICES):
+        for i in idxs:
+            sh[f"net.slice{k + 1}.{i}.weight"] = (CHANNELS[k], cin, 3, 3)
+            sh[f"net.slice{k + 1}.{i}.bias"] = (CHANNELS[k],)
+            cin = CHANNELS[k]
+        sh[f"lin{k}.model.1.weight"] = (1, CHANNELS[k], 1, 1)
+    return sh
+
+
+def seeded_lpips_state_dict(seed: int = 77) -> dict:
+    """synthetic LPIPS weights: He-initialised convs (activations stay O(1) through 13 ReLU layers), non-negative lin weights"""
+    g = th.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in lpips_param_shapes().items():
+        if name.startswith("lin"):
+            sd[name] = th.rand(shape, generator=g) * 0.2
+        elif name.endswith("weight"):
+            sd[name] = th.randn(shape, generator=g) * (2.0 / (shape[1] * 9)) ** 0.5
+        else:
+            sd[name] = th.randn(shape, generator=g) * 0.05
+    return sd
+
+
 def seeded_state_dict(shapes: dict, seed: int = 1234) -> dict:
     """fp16-range-safe synthetic weights: conv/linear N(0, 1/fan_in), biases N(0, 0.02), norm gains 1 + N(0, 0.1),
     embeddings N(0, 0.5)."""

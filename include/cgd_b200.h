@@ -142,11 +142,13 @@ enum {
   /* tv_loss + range_loss (+ sat) forward and analytic backward, merged with the CLIP-path gradient
    * (cgd/losses.py:5-7,17-22, cgd/cgd.py:201-218).
    * p0 x_in(f) p1 pred_xstart(f) p2 g_clip(f, dL/dx_in from the CLIP path)|0 p3 sc p4 seed(h pixel-major [B*HW, ld], UNet dgrad seed)
-   * p5 dx_direct(f NCHW) p6 loss(f [3B] = tv[B], range[B], sat[B]) ; i0 B i1 H i2 W i3 ld ; f0 tv_scale f1 range_scale f2 sat_scale f3 seed scale */
+   * p5 dx_direct(f NCHW) p6 loss(f [3B] = tv[B], range[B], sat[B]) ; i0 B i1 H i2 W i3 ld ; f0 tv_scale f1 range_scale f2 sat_scale f3 seed scale
+   * flags 1 = dynamic seed scaling: p7 seed_f32(f [B,HW,3]) p8 dyn(f [2B]) are written instead of p4 (see CGD_OP_SEED_QUANT), f3 unused */
   CGD_OP_GUIDE_GRAD = 25,
   /* g = -(dx_direct + dx_unet / seed scale), optional RMS clamp (cgd/cgd.py:228-232).
    * p0 dx_direct(f NCHW) p1 dx_unet(f NCHW, still multiplied by the seed scale)|0 p2 g(f NCHW) p3 ws(f [128])|0
-   * i0 B i1 HW ; f0 1/seed scale f1 max rms ; flags 1 = use_magnitude (whole-batch RMS clamp, two launches) */
+   * i0 B i1 HW ; f0 1/seed scale f1 max rms ; flags 1 = use_magnitude (whole-batch RMS clamp, two launches),
+   * flags 2 = dynamic seed scaling: p4 dyn(f [2B]), per-image 1/scale instead of f0 */
   CGD_OP_FINAL_GRAD = 26,
   /* ancestral update ([3P] p_sample_with_grad / condition_mean_with_grad): sample = mean + var*g + nz*exp(.5 logvar)*noise
    * p0 mean p1 variance p2 log_variance p3 g|0 p4 noise p5 sc p6 sample ; i0 n elements */
@@ -204,6 +206,11 @@ enum {
    * / inverse ranges(i32 [cutn,Smax,2]) (bwd) ; i7 Smax (bwd).  Square crops only. */
   CGD_OP_CUTOUTS_RR_FWD = 43,
   CGD_OP_CUTOUTS_RR_BWD = 44,
+  /* dynamic scaling of the UNet-backward seed (GUIDE_GRAD flags 1 writes the fp32 seed p7 and the per-image max |.| into p8[0..B)):
+   * scale_b = 2^floor(log2(4096 / max_b)); seed(h, [B,HW,ld], channels 0..2) = seed_f32 * scale_b; p8[B + b] = scale_b.
+   * p0 seed_f32(f [B,HW,3]) p1 dyn(f [2B]) p2 seed(h) ; i0 B i1 HW i2 ld.  FINAL_GRAD flags 2 (p4 = dyn) divides dx_unet by
+   * scale_b and resets the maxima. */
+  CGD_OP_SEED_QUANT = 45,
   CGD_OP__COUNT
 };
 

@@ -13,6 +13,8 @@ if cs_override:
     P.gn_fused_cluster = lambda N, HW, C, maxv: (cs_override if orig(N, HW, C, maxv) and -(-HW // cs_override) <= maxv * (512 // max(2, C // 256)) else orig(N, HW, C, maxv))
 for HW, C in SHAPES:
     for mode in ('auto', 'grid', 'twopass'):
+        if os.environ.get('GN_ONLY') and mode != os.environ['GN_ONLY']:
+            continue
         plan = P.Plan()
         plan.fused_gn = mode == 'auto'
         plan.grid_gn = mode != 'twopass'

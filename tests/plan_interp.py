@@ -509,8 +509,14 @@ class Interp:
         if op.p[2] is not None:
             d_xin = d_xin + self.V(op.p[2], shp, st)
         d_x0 = fac * d_xin + (d_x0r if d_x0r is not None else 0)
-        seed = self.V(op.p[4], (B, H * W, 3), (H * W * ld, ld, 1))
-        seed.copy_((-bb * d_x0 * seed_scale).reshape(B, 3, H * W).permute(0, 2, 1))
+        if op.flags & 1:  # dynamic seed scaling: fp32 seed + per-image max, the fp16 seed is SEED_QUANT's
+            v = (-bb * d_x0).reshape(B, 3, H * W).permute(0, 2, 1)
+            self.V(op.p[7], (B, H * W, 3), (H * W * 3, 3, 1)).copy_(v)
+            dyn = self.flat(op.p[8], 2 * B)
+            dyn[:B] = th.maximum(dyn[:B], v.abs().reshape(B, -1).amax(1).clamp(max=3.0e38))
+        else:
+            seed = self.V(op.p[4], (B, H * W, 3), (H * W * ld, ld, 1))
+            seed.copy_((-bb * d_x0 * seed_scale).clamp(-60000, 60000).reshape(B, 3, H * W).permute(0, 2, 1))
         self.V(op.p[5], shp, st).copy_(omf * d_xin + a * d_x0)
         if op.p[6] is not None:
             lo = self.flat(op.p[6], 3 * B)
@@ -520,12 +526,26 @@ class Interp:
                 per = th.abs(xin - xin.clamp(-1, 1)).detach().mean([1, 2, 3]) / B * ss
                 lo[2 * B:3 * B] += per
 
+    def op_SEED_QUANT(self, op):
+        B, HW, ld = op.i[:3]
+        dyn = self.flat(op.p[1], 2 * B)
+        m = dyn[:B].clone()
+        scale = th.where(m > 0, th.exp2(th.floor(th.log2(4096.0 / m.clamp(min=1e-38))).clamp(-60, 60)), th.ones_like(m))
+        dyn[B:] = scale
+        v = self.V(op.p[0], (B, HW, 3), (HW * 3, 3, 1))
+        self.V(op.p[2], (B, HW, 3), (HW * ld, ld, 1)).copy_((v * scale.view(B, 1, 1)).clamp(-60000, 60000))
+
     def op_FINAL_GRAD(self, op):
         B, HW = op.i[:2]
         n = B * 3 * HW
         g = self.flat(op.p[0], n).clone()
         if op.p[1] is not None:
-            g = g + self.flat(op.p[1], n) * op.f[0]
+            if op.flags & 2:
+                dyn = self.flat(op.p[4], 2 * B)
+                g = g + (self.flat(op.p[1], n).view(B, -1) / dyn[B:].view(B, 1)).reshape(-1)
+                dyn[:B] = 0
+            else:
+                g = g + self.flat(op.p[1], n) * op.f[0]
         g = -g
         if op.flags & 1:
             mag = g.square().mean().sqrt()

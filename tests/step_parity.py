@@ -31,7 +31,7 @@ def prod_unet_cfg(ocfg):
 
 
 def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0, respacing="25", conv_impl=0, use_graph=False, P=1,
-               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool"):
+               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None):
     ocfg = tiny_config(image_size=image, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(image // 2,),
                        class_cond=True, use_new_attention_order=new_order)
     ounet = seeded_init_(UNetModel(ocfg)).eval()
@@ -45,6 +45,7 @@ def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0
     targets = th.randn(P, 64, generator=g)
     weights = th.ones(P) / P
     kw = dict(clip_guidance_scale=1000.0, tv_scale=150.0, range_scale=50.0, sat_scale=sat_scale)
+    kw.update(scales or {})
     lp_sd = init = olp = None
     if init_scale:
         from oracle import lpips as ol
@@ -129,3 +130,38 @@ def run_tiny_step_parity(device="cuda:0", mode="ancestral", t_index=14, runner_f
     res["tv_loss_rel"] = abs(float(e["losses"]["tv"].sum()) - o["terms"]["tv"]) / (abs(o["terms"]["tv"]) + 1e-9)
     res["range_loss_rel"] = abs(float(e["losses"]["range"].sum()) - o["terms"]["range"]) / (abs(o["terms"]["range"]) + 1e-9)
     return res
+
+
+def psnr(a, b, peak=None):
+    """peak = the reference image's own range (a trained model's samples live in [-1, 1]; seeded random weights do not)"""
+    peak = float(b.max() - b.min()) if peak is None else peak
+    mse = float(((a.float() - b.float()) ** 2).mean())
+    return float("inf") if mse == 0 else 10.0 * float(np.log10(peak * peak / mse))
+
+
+def run_tiny_chain(device="cuda:0", mode="ancestral", steps=None, runner_factory=None, fused=False, seed=11, **build_kw):
+    """Free-running chain (SURVEY.md 8c protocol item 3): both sides start from the same x_T and receive the same per-step
+    (class label, noise, cutout windows), but each side feeds ITS OWN sample back in -- nothing is teacher-forced after step 0.
+    Returns the per-step relative drift and the PSNR of the final sample / pred_xstart against the oracle's."""
+    ctx = build_tiny(device, **build_kw)
+    T = ctx["pdiff"].num_timesteps
+    steps = T if steps is None else steps
+    runner = runner_factory(ctx["eng"]) if runner_factory else None
+    g = th.Generator().manual_seed(seed)
+    xo = th.randn(ctx["B"], 3, ctx["image"], ctx["image"], generator=g)
+    xe = xo.clone()
+    drift = []
+    o = e = None
+    for k in range(steps):
+        t_index = T - 1 - k
+        y = th.randint(0, 10, (ctx["B"],), generator=g)
+        th.manual_seed(seed + 1000 + k)
+        noise = th.randn_like(xo)
+        th.manual_seed(seed + 5000 + k)
+        coords = og.MakeCutouts(32, ctx["cutn"])._generate_coords(ctx["image"], ctx["image"], ctx["cutn"])
+        o = oracle_step(ctx, mode, xo, t_index, y, seed + 1000 + k, coords, fac_index=t_index)
+        e = engine_step(ctx, mode, xe, t_index, y, noise, coords, fac_index=t_index, runner=runner, fused=fused)
+        xo, xe = o["sample"].detach(), e["sample"]
+        drift.append(rel(xe, xo))
+    return dict(drift=drift, psnr_sample=psnr(xe, xo), psnr_x0=psnr(e["pred_xstart"], o["pred_xstart"].detach()),
+                finite=bool(th.isfinite(xe).all()), steps=steps)

@@ -26,6 +26,7 @@ CASES = [
     (1, 16384, 768, False, True),   # backward slab too large -> two-pass backward, fused forward
     (1, 900, 256, True, True),      # ragged pixel count
     (1, 65536, 256, True, True),    # persistent grid kernel (or two-pass)
+    (1, 65536, 512, False, True),   # 33 M elements: the direct-load backward engine (norm_grid2.cu)
     (2, 4096, 192, True, True),     # C = 192: groups straddle the 8-channel vectors (64x64 checkpoint widths)
     (3, 1024, 64, False, True),
 ]
@@ -112,3 +113,15 @@ def test_all_paths_agree_on_statistics():
         outs.append(plan.view(st, (N, 32, 2)).clone())
     assert th.allclose(outs[0], outs[2], rtol=2e-5, atol=2e-6), float((outs[0] - outs[2]).abs().max())
     assert th.allclose(outs[1], outs[2], rtol=2e-5, atol=2e-6), float((outs[1] - outs[2]).abs().max())
+
+
+@pytest.mark.parametrize("engine", ["ring", "direct"])
+def test_grid_engines_forced(engine):
+    """The dispatch picks the ring or the direct-load engine by shape (norm_grid.cu: gng_use_direct); the choice is read from the
+    environment once per process, so every grid case is re-run with each engine forced in a child process."""
+    import os, subprocess, sys
+    env = dict(os.environ, CGD_GN_GRID_ENGINE=engine)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_norm.py", "-q", "-x", "-m", "gpu", "-k", "grid and not forced", "-p",
+                        "no:cacheprovider"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -53,3 +53,12 @@ def test_progressive_cutout_schedule():
         class Small(Eng):
             vits = {16: None}
         pg.CondFnB200(Small(), Diff(), mk, progressive_cutout=True)
+
+
+@pytest.mark.parametrize("mode", ["ancestral", "ddim"])
+def test_short_chain_matches_oracle(mode):
+    """free-running 6-step chain through the op-list interpreter: the host-side loop state (scalar tables, timestep map,
+    fac index, buffer reuse between steps) stays consistent with the oracle's loop"""
+    from tests.step_parity import run_tiny_chain
+    res = run_tiny_chain(device="cpu", mode=mode, steps=6, runner_factory=_interp_runner, image=32, B=1, cutn=2, use_magnitude=True)
+    assert res["finite"] and max(res["drift"]) < 2e-2 and res["psnr_sample"] > 40.0, res
