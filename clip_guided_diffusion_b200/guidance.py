@@ -418,6 +418,10 @@ class GuidedStepB200:
         o += n
         self.h2d_bytes += SC["COUNT"] * 4 + self.B * 4
         if self.cutn:
+            for ox, oy, size in coords:  # windows may be clipped at the border (quirk B3) but not empty
+                if not (0 <= ox < self.W and 0 <= oy < self.H and size > 0):
+                    raise RuntimeError(f"cutout window (x={ox}, y={oy}, size={size}) lies outside the {self.H}x{self.W} image: the reference's "
+                                       "adaptive_avg_pool2d raises on the empty crop (non-square images, cgd/modules.py:52,61)")
             n = len(coords) * 12
             st[o:o + n].view(th.int32).copy_(th.tensor(coords, dtype=th.int32).view(-1))
             self.v(self.coords).view(th.uint8)[:n].copy_(st[o:o + n], non_blocking=True)

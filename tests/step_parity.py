@@ -31,7 +31,7 @@ def prod_unet_cfg(ocfg):
 
 
 def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0, respacing="25", conv_impl=0, use_graph=False, P=1,
-               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None):
+               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None, hw=None):
     ocfg = tiny_config(image_size=image, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(image // 2,),
                        class_cond=True, use_new_attention_order=new_order)
     ounet = seeded_init_(UNetModel(ocfg)).eval()
@@ -54,11 +54,12 @@ def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0
         init = th.rand(1, 3, image, image, generator=th.Generator().manual_seed(7)) * 2 - 1
     eng = pg.GuidedStepB200(prod_unet_cfg(ocfg), ounet.state_dict(), pv.ViTConfig(32, 16, 128, 2, 64), oclip.state_dict(), batch=B,
                             num_cutouts=cutn, max_prompts=P, use_magnitude=use_magnitude, device=device, conv_impl=conv_impl,
+                            height=(hw or (image, image))[0], width=(hw or (image, image))[1],
                             use_graph=use_graph, vit_streams=vit_streams, cutn_variants=cutn_variants, lpips_sd=lp_sd, init_scale=init_scale, cutout_resize=cutout_resize, **kw)
     eng.set_targets(targets, weights)
     return dict(ounet=ounet, oclip=oclip, odiff=odiff, pdiff=pdiff, eng=eng, targets=targets, weights=weights, kw=kw, olp=olp, init=init,
                 init_scale=init_scale, cutout_resize=cutout_resize,
-                use_magnitude=use_magnitude, cutn=run_cutn or cutn, B=B, image=image)
+                use_magnitude=use_magnitude, cutn=run_cutn or cutn, B=B, image=image, hw=hw or (image, image))
 
 
 def oracle_step(ctx, mode, x, t_index, y, noise_seed, coords, fac_index):
@@ -101,14 +102,14 @@ def engine_step(ctx, mode, x, t_index, y, noise, coords, fac_index, runner=None,
 
 
 def make_inputs(ctx, seed=3):
-    B, image = ctx["B"], ctx["image"]
+    B, (H, W) = ctx["B"], ctx["hw"]
     g = th.Generator().manual_seed(seed)
-    x = th.randn(B, 3, image, image, generator=g)
+    x = th.randn(B, 3, H, W, generator=g)
     y = th.randint(0, 10, (B,), generator=g)
     th.manual_seed(seed + 100)
     noise = th.randn_like(x)  # == what the oracle draws right after manual_seed(seed + 100)
     th.manual_seed(seed + 200)
-    coords = og.MakeCutouts(32, ctx["cutn"])._generate_coords(image, image, ctx["cutn"])
+    coords = og.MakeCutouts(32, ctx["cutn"])._generate_coords(H, W, ctx["cutn"])  # sic: (H, W) as (side_x, side_y), quirk B3
     return x, y, noise, seed + 100, coords
 
 
@@ -148,7 +149,7 @@ def run_tiny_chain(device="cuda:0", mode="ancestral", steps=None, runner_factory
     steps = T if steps is None else steps
     runner = runner_factory(ctx["eng"]) if runner_factory else None
     g = th.Generator().manual_seed(seed)
-    xo = th.randn(ctx["B"], 3, ctx["image"], ctx["image"], generator=g)
+    xo = th.randn(ctx["B"], 3, *ctx["hw"], generator=g)
     xe = xo.clone()
     drift = []
     o = e = None
@@ -158,7 +159,7 @@ def run_tiny_chain(device="cuda:0", mode="ancestral", steps=None, runner_factory
         th.manual_seed(seed + 1000 + k)
         noise = th.randn_like(xo)
         th.manual_seed(seed + 5000 + k)
-        coords = og.MakeCutouts(32, ctx["cutn"])._generate_coords(ctx["image"], ctx["image"], ctx["cutn"])
+        coords = og.MakeCutouts(32, ctx["cutn"])._generate_coords(*ctx["hw"], ctx["cutn"])
         o = oracle_step(ctx, mode, xo, t_index, y, seed + 1000 + k, coords, fac_index=t_index)
         e = engine_step(ctx, mode, xe, t_index, y, noise, coords, fac_index=t_index, runner=runner, fused=fused)
         xo, xe = o["sample"].detach(), e["sample"]

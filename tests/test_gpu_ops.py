@@ -48,6 +48,20 @@ def test_step_parity_vs_oracle(mode, fused, streams):
     assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res
 
 
+@pytest.mark.parametrize("hw", [(64, 96), (96, 64)], ids=["64x96", "96x64"])
+def test_non_square_step_vs_oracle(hw):
+    """height_offset / width_offset (cgd/cgd.py:135): non-square x_t; cutout windows drawn with the reference's swapped sides are
+    clipped at the border and still pooled to a square (quirk B3)"""
+    ctx = build_tiny("cuda", conv_impl=IMPL, image=64, hw=hw, use_graph=True, B=2, cutn=5)
+    x, y, noise, nseed, coords = make_inputs(ctx)
+    o = oracle_step(ctx, "ddim", x, 14, y, nseed, coords, fac_index=14)
+    e = engine_step(ctx, "ddim", x, 14, y, noise, coords, fac_index=14, fused=True)
+    res = compare(o, e)
+    assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res
+    with pytest.raises(RuntimeError, match="outside"):
+        ctx["eng"].stage_step(ctx["pdiff"].scalar_table(14, 14, 0.0), [(0, hw[0], 32)] * 5, ctx["pdiff"].model_timestep(14), y)
+
+
 @pytest.mark.parametrize("fused", [False, True], ids=["eager", "graph"])
 def test_progressive_cutout_variant_vs_oracle(fused):
     """An engine built for cutout counts (2, 4, 8) -- progressive_cutout, cgd/cgd.py:167-175 -- runs a step with 4 cutouts

@@ -15,7 +15,11 @@ def _interp_runner(eng):
                                      ("ddim", dict(B=1, P=2, cutn=2)), ("ddim", dict(B=2, cutn=4, vit_streams=2)),
                                      ("ancestral", dict(B=1, cutn=8, cutn_variants=(2, 4, 8), run_cutn=4)),
                                      ("ddim", dict(B=2, cutn=2, init_scale=1000.0)),
-                                     ("ancestral", dict(B=2, cutn=3, image=64, cutout_resize="lanczos3"))])
+                                     ("ancestral", dict(B=2, cutn=3, image=64, cutout_resize="lanczos3")),
+                                     # non-square (height_offset / width_offset, cgd/cgd.py:135): windows drawn with the reference's
+                                     # swapped sides are clipped at the border (quirk B3) and still pooled to a square
+                                     ("ddim", dict(B=1, cutn=6, image=32, hw=(32, 64))),
+                                     ("ancestral", dict(B=2, cutn=4, image=32, hw=(48, 32)))])
 def test_step_plan_matches_oracle(mode, kw):
     res = run_tiny_step_parity(device="cpu", mode=mode, runner_factory=_interp_runner, **{"image": 32, **kw})
     assert res["cos_g"] > 0.999, res
