@@ -26,7 +26,7 @@ OP = dict(CONV=1, GN_STATS=2, GN_APPLY=3, GN_BWD_STATS=4, GN_BWD_APPLY=5, POOL2=
 SC = dict(SQRT_RECIP_AC=0, SQRT_RECIPM1_AC=1, POST_COEF1=2, POST_COEF2=3, MIN_LOG=4, MAX_LOG=5, FAC=6, NONZERO=7,
           SQRT_1M_AC=8, AC_PREV=9, AC=10, ETA=11, ONE_MINUS_FAC=12, COUNT=16)
 
-EXPORTS = ["cgd_abi_version", "cgd_last_error", "cgd_plan_create", "cgd_plan_run", "cgd_plan_num_launches",
+EXPORTS = ["cgd_abi_version", "cgd_last_error", "cgd_conv_cluster_capacity", "cgd_plan_create", "cgd_plan_run", "cgd_plan_num_launches",
            "cgd_plan_destroy", "cgd_run_op", "cgd_unet_create", "cgd_unet_fwd", "cgd_unet_bwd_input", "cgd_unet_destroy",
            "cgd_vit_create", "cgd_vit_fwd", "cgd_vit_bwd_input", "cgd_vit_destroy", "cgd_step_create", "cgd_step",
            "cgd_step_destroy", "cgd_cutouts_fwd", "cgd_cutouts_bwd", "cgd_spherical_fwd_bwd",
@@ -50,6 +50,7 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.cgd_last_error.restype = ctypes.c_char_p
     lib.cgd_abi_version.restype = ctypes.c_int
+    lib.cgd_conv_cluster_capacity.argtypes = [ctypes.c_int32, ctypes.c_int32]
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     lib.cgd_plan_create.argtypes = [ctypes.POINTER(CgdOp), i32, ctypes.POINTER(vp)]
     lib.cgd_plan_run.argtypes = [vp, i32, i32, vp]

@@ -381,7 +381,9 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   p.out_sc = op.i[19] > 0 ? op.i[19] : 1;
   if (!p.out_f32 && p.out_sc == 1) CGD_CHECK_ARG(op.i[10] % 8 == 0 && op.i[11] % 8 == 0 && op.i[12] % 8 == 0, "conv: fp16 out strides must be multiples of 8");
   if (p.res) CGD_CHECK_ARG(op.i[13] % 8 == 0 && op.i[14] % 8 == 0 && op.i[15] % 8 == 0 && ((uintptr_t)p.res % 16) == 0, "conv: residual must be 16-byte aligned with strides %% 8 == 0");
-  if (p.splits > 1) CGD_CHECK_ARG(p.ws != nullptr, "conv: split-K needs a workspace");
+  const bool want_cluster = op.i[23] == 1 && op.i[18] != 1 && op.i[18] != 2;  // plan flag; the SIMT twin / forced single-CTA kernel ignore it
+  if (p.splits > 1 && !want_cluster) CGD_CHECK_ARG(p.ws != nullptr, "conv: split-K needs a workspace");
+  L.cluster_split = 0;
   p.sk_bar = reinterpret_cast<unsigned int*>(op.p[6]);
   L.BN = (int)BN;
   L.impl = (int)op.i[18];
@@ -431,6 +433,11 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W half) failed with %d", (int)r);
   }
+  if (want_cluster) {
+    CGD_CHECK_ARG(conv_cluster_split_ok(L), "conv: layer flagged for cluster split-K is not eligible (BN=%d splits=%d Cout=%d f32=%d)", L.BN, p.splits,
+                  p.Cout, p.out_f32);
+    L.cluster_split = 1;
+  }
   // split-K reduction inside the conv kernel: needs the barrier buffer and every CTA of the launch resident at once
   {
     const int64_t units = conv_use_pair_kernel(L) ? (int64_t)((L.m_tiles + 1) / 2) * L.n_tiles * p.splits : (int64_t)L.m_tiles * L.n_tiles * p.splits;
@@ -440,7 +447,7 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   }
   // pair-kernel epilogue through shared memory + TMA tensor stores: same 4-D box geometry as the A operand, so rows outside
   // the image are clipped by the TMA unit; needs fp16 channel-contiguous output and whole 64-channel chunks
-  p.epi_tma = (conv_use_pair_kernel(L) && !p.out_f32 && p.out_sc == 1 && p.splits == 1 && BN >= 64 && Cout % 64 == 0) ? 1 : 0;
+  p.epi_tma = (!L.cluster_split && conv_use_pair_kernel(L) && !p.out_f32 && p.out_sc == 1 && p.splits == 1 && BN >= 64 && Cout % 64 == 0) ? 1 : 0;
   if (const char* e = getenv("CGD_CONV_EPI_TMA")) if (e[0] == '0') p.epi_tma = 0;
   if (p.epi_tma) {
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
@@ -491,6 +498,7 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
     CGD_CUDA(launch_pdl(conv_simt_kernel, dim3(blocks), dim3(256), 0, st, L.A, L.Wp, p, L.a_sn, L.a_sh, L.a_sw, L.ldb, L.b_sh, L.b_sn));
     return 0;
   }
+  if (L.cluster_split) return conv_tc3_launch(L, st);
   int rc = 0;
   if (conv_use_pair_kernel(L)) rc = conv_tc2_launch(L, st);
   else if (L.p.b_batched) { set_error("conv: batched-B GEMM reached the single-CTA kernel"); return -1; }
@@ -513,6 +521,6 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
   return 0;
 }
 
-int conv_tc_num_launches(const ConvTcLaunch& L) { return (L.impl != 1 && L.p.splits > 1 && !L.p.fuse_reduce) ? 2 : 1; }
+int conv_tc_num_launches(const ConvTcLaunch& L) { return (L.impl != 1 && L.p.splits > 1 && !L.p.fuse_reduce && !L.cluster_split) ? 2 : 1; }
 
 }  // namespace cgd

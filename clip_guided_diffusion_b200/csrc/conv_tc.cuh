@@ -37,6 +37,7 @@ struct ConvTcLaunch {
   CUtensorMap tmOut, tmRes;          // pair kernel epilogue: [64 ch x TW x TH x TN] boxes of the output / residual
   ConvTcParams p;
   int BN, impl, m_tiles, n_tiles;
+  int cluster_split;                 // split-K inside a 2*splits-CTA cluster, reduced through DSMEM (conv_tc3.cu): no workspace, one launch
   const __half* A;
   const __half* Wp;
   int64_t a_sn, a_sh, a_sw;
@@ -48,5 +49,8 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st);
 int conv_tc_num_launches(const ConvTcLaunch& L);
 int conv_tc2_launch(const ConvTcLaunch& L, cudaStream_t st);  // conv_tc2.cu
 bool conv_use_pair_kernel(const ConvTcLaunch& L);
+int conv_tc3_launch(const ConvTcLaunch& L, cudaStream_t st);  // conv_tc3.cu
+bool conv_cluster_split_ok(const ConvTcLaunch& L);
+int conv_tc3_max_clusters(int BN, int S);
 
 }  // namespace cgd

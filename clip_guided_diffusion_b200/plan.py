@@ -135,6 +135,64 @@ def pick_splits(m_tiles, n_tiles, kblocks, npad, ws_cap_bytes=16 << 20) -> int:
     return -(-kblocks // per)
 
 
+_T_KB = {64: 0.29, 128: 0.35, 192: 0.41, 256: 0.47}  # us per K-block per CTA of a pair (operand stream, profiles/r01_conv_sweep_v1.txt)
+
+
+_CLUSTER_CAP = {}
+
+
+def cluster_capacity(bn: int, S: int) -> int:
+    """co-resident clusters of 2*S CTAs for tile width bn: asked from the library on a CUDA box (cudaOccupancyMaxActiveClusters),
+    128 CTAs' worth (8 GPCs x 16 SMs) when there is no device (CPU plan builds for the interpreter tests)"""
+    key = (bn, S)
+    if key not in _CLUSTER_CAP:
+        cap = -1
+        try:
+            import torch as _th
+            if _th.cuda.is_available():
+                from . import _lib
+                cap = int(_lib.load().cgd_conv_cluster_capacity(bn, S))
+        except Exception:
+            cap = -1
+        _CLUSTER_CAP[key] = cap if cap >= 0 else 128 // (2 * S)
+    return _CLUSTER_CAP[key]
+
+
+# in-cluster split-K cost model, fitted to profiles/r01_cluster_sweep_v2.txt (in-graph times on B200): fixed us per (BN, S) -- launch,
+# two cluster barriers, the DSMEM exchange of a 128 x BN fp32 tile at ~20 B/clk per SM -- plus ~0.31 us per K-block per pair
+_CL_FIXED = {(64, 2): 7.2, (128, 2): 8.5, (192, 2): 9.6, (256, 2): 12.6, (64, 4): 7.0, (128, 4): 6.8, (192, 4): 8.5, (256, 4): 10.0,
+             (128, 8): 8.0, (256, 8): 9.6}
+
+
+def pick_cluster_split(m_tiles: int, npad: int, kblocks: int, cout: int):
+    """(BN, S, estimated us) for the in-cluster split-K kernel (csrc/conv_tc3.cu), or None.  One cluster of 2*S CTAs per output tile
+    of 256 pixels x BN channels; the whole launch must fit one wave of clusters (`cluster_capacity`: 33 / 15 / 7 clusters of
+    4 / 8 / 16 CTAs on B200); each pair gets >= 3 K-blocks and BN / S (the columns a pair reduces and stores) is a multiple of 16."""
+    if cout % 8:
+        return None
+    pair_tiles = (m_tiles + 1) // 2
+    best = None
+    for bn in (256, 192, 128, 64):
+        if npad % bn:
+            continue
+        tiles = pair_tiles * (npad // bn)
+        for S in (2, 4, 8):
+            if bn % S or (bn // S) % 16 or tiles > cluster_capacity(bn, S):
+                continue
+            kps = -(-kblocks // S)
+            if kps < 3 or (S - 1) * kps >= kblocks:
+                continue
+            est = _CL_FIXED[(bn, S)] + kps * (0.31 + (0.06 if tiles > 8 else 0.0))
+            if best is None or est < best[2] - 1e-9:
+                best = (bn, S, est)
+    return best
+
+
+def workspace_split_estimate(bn: int, splits: int, kblocks: int, rows: int, npad: int) -> float:
+    """us for the pair kernel writing `splits` fp32 partial tensors + the reduce launch (fit of the same sweep)"""
+    return 5.0 + -(-kblocks // splits) * _T_KB[bn] + 0.55 * splits * rows * npad * 4 / 1e6
+
+
 def gn_fused_cluster(N: int, HW: int, C: int, maxv: int) -> int:
     """Cluster size (CTAs along the pixel dimension) of the single-launch GroupNorm kernels (csrc/norm_fused.cu), or 0 when the
     two-pass kernels are the better choice.  512 threads, 16-byte vectors, at most `maxv` vectors per thread (16 forward,
@@ -183,6 +241,8 @@ class Plan:
         # long sequences (T % 256 == 0) as batched tcgen05 GEMMs + transposes + softmax kernels; superseded by the flash kernels of
         # csrc/attention_mma.cu (one launch forward, three backward, nothing T x T in HBM), kept for A/B measurements
         self.tc_attention = os.environ.get("CGD_TC_ATTENTION", "0") == "1"
+        # split-K reduced inside a thread-block cluster through DSMEM (csrc/conv_tc3.cu) instead of partials + a reduce launch
+        self.cluster_splitk = os.environ.get("CGD_CONV_CLUSTER", "1") == "1"
         self.arena: Optional[th.Tensor] = None
         self.handle = None
         self._c_ops = None
@@ -266,10 +326,20 @@ class Plan:
         kblocks = taps * Cin // 64
         bn = pick_bn(npad, m_tiles, kblocks)
         splits = pick_splits(m_tiles, npad // bn, kblocks, npad)
-        ws = self.new(splits * ((m_tiles + 1) // 2 * 2) * 128 * npad, "f", "splitk_ws") if splits > 1 else None
-        skbar = self.new(2 * ((m_tiles + 1) // 2 * 2) * (npad // bn), "u32", "splitk_bar") if splits > 1 else None
+        cluster = 0
+        if splits > 1 and self.cluster_splitk and self.conv_impl in (0, 3) and b_ptr is None and not out_f32 and out_sc == 1:
+            pick = pick_cluster_split(m_tiles, npad, kblocks, Cout)
+            if pick is not None and pick[2] + 1.0 < workspace_split_estimate(bn, splits, kblocks, NB * H * W, npad):
+                bn, splits = pick[:2]
+                cluster = 1
+        ws = skbar = None
+        if cluster:
+            pass
+        elif splits > 1:
+            ws = self.new(splits * ((m_tiles + 1) // 2 * 2) * 128 * npad, "f", "splitk_ws")
+            skbar = self.new(2 * ((m_tiles + 1) // 2 * 2) * (npad // bn), "u32", "splitk_bar")
         i = [NB, H, W, Cin, Cout, npad, taps, *x_strides, *out_strides, *(res_strides or (0, 0, 0)), bn, splits, self.conv_impl, out_sc,
-             b_batch[0], b_batch[1], ldb]
+             b_batch[0], b_batch[1], ldb, cluster]
         self.emit("CONV", flags=1 if out_f32 else 0, i=i,
                   p=[x_ptr, b_ptr if b_ptr is not None else self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws), self._bp(skbar)], tag=tag)
 

@@ -63,6 +63,8 @@ enum {
    *   i22 row stride of B (0 = taps*Cin).  Batched mode needs W % 256 == 0 (attention: A = Q/P/dS..., B = K/V^T/...)
    *   p6 split-K barrier words (u32 [2 * row tiles * channel tiles], zero-initialised)|0: when given and the launch fits one wave,
    *   the kernel reduces its own split-K partials (no second launch)
+   *   i23 = 1: split-K inside a thread-block cluster of 2 * splits CTAs, reduced through distributed shared memory (one launch, no
+   *   workspace; splits in 2..8, BN >= 64, BN / splits a multiple of 16, fp16 contiguous output, Cout % 8 == 0)
    *   flags: 1 = out is fp32 */
   CGD_OP_CONV = 1,
   /* GroupNorm(32) statistics: per (image, chunk, group) partial sum / sum of squares; the last block per image
@@ -235,6 +237,10 @@ enum {
 /* ------------------------------------------------------------------ entry points --------------- */
 int cgd_abi_version(void);
 const char* cgd_last_error(void);
+/* How many thread-block clusters of 2 * splits CTAs of the in-cluster split-K conv kernel (CONV i23 = 1, tile width bn in
+ * {64, 128, 192, 256}) the current device holds at once (cudaOccupancyMaxActiveClusters); -1 without a device.  Plans use it to
+ * keep such a layer within one wave of clusters. */
+int cgd_conv_cluster_capacity(int32_t bn, int32_t splits);
 
 /* Validate an op list, pre-encode TMA descriptors, return a handle.  The op array is copied. */
 int cgd_plan_create(const CgdOp* ops, int32_t n_ops, void** plan_out);

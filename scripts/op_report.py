@@ -40,7 +40,7 @@ def load_launches(path):
 def shape_of(kind, op):
     i = op.i
     if kind == "CONV":
-        return f"{i[0]}x{i[1]}x{i[2]} {i[3]}->{i[4]} t{i[6]} BN{i[16]} sp{i[17]}" + (" res" if op.p[3] is not None else "") + (" f32" if op.flags & 1 else "")
+        return f"{i[0]}x{i[1]}x{i[2]} {i[3]}->{i[4]} t{i[6]} BN{i[16]} {'cl' if len(i) > 23 and i[23] else 'sp'}{i[17]}" + (" res" if op.p[3] is not None else "") + (" f32" if op.flags & 1 else "")
     if kind.startswith("GN_"):
         return f"N{i[0]} HW{i[1]} C{i[2]} fl{op.flags}" + (f" CS{i[5] if kind == 'GN_FWD_FUSED' else i[6]}" if "FUSED" in kind else "")
     return " ".join(str(v) for v in i[:6])
@@ -63,7 +63,7 @@ def main():
     for op in ops:
         kind = inv[op.code]
         n = 1
-        if kind == "CONV" and op.i[17] > 1:
+        if kind == "CONV" and op.i[17] > 1 and not (len(op.i) > 23 and op.i[23]):
             n = 2
         elif kind == "ATTN_BWD":
             n = 1 if op.i[2] <= 64 else 2

@@ -26,6 +26,9 @@ CASES = [
     ("linear_m800_qkv", 1, 1, 800, 768, 2304, 1, True, False),
     ("linear_m50", 1, 1, 50, 768, 768, 1, True, True),
     ("linear_k3072", 1, 1, 800, 3072, 768, 1, True, True),
+    ("conv3x3_32x32_c512_cluster8", 1, 32, 32, 512, 512, 9, True, True),      # in-cluster split-K: 16 CTAs per tile (BN 256, S = 8)
+    ("conv1x1_16x16_k3072", 1, 16, 16, 3072, 1024, 1, True, False),
+    ("linear_k2304_m800", 1, 1, 800, 2304, 768, 1, False, True),              # BN 192, S = 4, ragged last pixel tile
 ]
 
 
@@ -36,10 +39,12 @@ def _ref_conv(x, w, b, res, taps):
     return y + res.float() if res is not None else y
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["auto", "simt", "tc1", "tc2pair"])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3, 13], ids=["auto", "simt", "tc1", "tc2pair", "tc2pair_ws_splitk"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_fwd_and_dgrad(case, impl):
     name, NB, H, W, Cin, Cout, taps, has_b, has_r = case
+    cluster = impl != 13  # 13: the pair kernel with the workspace split-K + reduce launch instead of the in-cluster reduction
+    impl = 3 if impl == 13 else impl
     if impl == 1 and NB * H * W * Cout * taps * Cin > 3e10:
         pytest.skip("SIMT twin only on small cases")
     th.manual_seed(0)
@@ -47,6 +52,7 @@ def test_conv_fwd_and_dgrad(case, impl):
     w = th.randn(Cout, Cin, k, k) * (taps * Cin) ** -0.5
     b = th.randn(Cout) * 0.1 if has_b else None
     plan = Plan(conv_impl=impl)
+    plan.cluster_splitk = cluster
     cw = pack_conv(plan, w, b, need_bwd=True, name=name)
     x = plan.act(NB, H, W, Cin, "x")
     res = plan.act(NB, H, W, Cout, "res") if has_r else None
