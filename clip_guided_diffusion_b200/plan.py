@@ -143,7 +143,7 @@ _CLUSTER_CAP = {}
 
 def cluster_capacity(bn: int, S: int) -> int:
     """co-resident clusters of 2*S CTAs for tile width bn: asked from the library on a CUDA box (cudaOccupancyMaxActiveClusters),
-    128 CTAs' worth (8 GPCs x 16 SMs) when there is no device (CPU plan builds for the interpreter tests)"""
+    B200's answers (33 / 15 / 7 clusters of 4 / 8 / 16 CTAs) when there is no device (CPU plan builds: interpreter tests, op_report)"""
     key = (bn, S)
     if key not in _CLUSTER_CAP:
         cap = -1
@@ -154,7 +154,7 @@ def cluster_capacity(bn: int, S: int) -> int:
                 cap = int(_lib.load().cgd_conv_cluster_capacity(bn, S))
         except Exception:
             cap = -1
-        _CLUSTER_CAP[key] = cap if cap >= 0 else 128 // (2 * S)
+        _CLUSTER_CAP[key] = cap if cap >= 0 else {1: 74, 2: 33, 4: 15, 8: 7}[S]  # the B200 answers
     return _CLUSTER_CAP[key]
 
 
