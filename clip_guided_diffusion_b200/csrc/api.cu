@@ -67,6 +67,7 @@ static int dispatch(const CgdOp& op, const ConvTcLaunch* conv, cudaStream_t st) 
     case CGD_OP_CUTOUTS_RR_FWD: return launch_cutouts_rr_fwd(op, st);
     case CGD_OP_CUTOUTS_RR_BWD: return launch_cutouts_rr_bwd(op, st);
     case CGD_OP_SEED_QUANT: return launch_seed_quant(op, st);
+    case CGD_OP_MAG_CLAMP: return launch_mag_clamp(op, st);
     case CGD_OP_LINEAR_SMALL: return launch_linear_small(op, st);
     case CGD_OP_TIMESTEP_EMB: return launch_timestep_emb(op, st);
     case CGD_OP_LABEL_ADD: return launch_label_add(op, st);
@@ -93,7 +94,7 @@ static int op_launches(const CgdOp& op, const ConvTcLaunch* conv) {
   switch (op.code) {
     case CGD_OP_CONV: return conv_tc_num_launches(*conv);
     case CGD_OP_ATTN_BWD: return attn_bwd_num_launches(op);
-    case CGD_OP_FINAL_GRAD: return (op.flags & 1) ? 2 : 1;
+    case CGD_OP_FINAL_GRAD: return ((op.flags & 1) && !(op.flags & 4)) ? 2 : 1;
     default: return 1;
   }
 }

@@ -478,14 +478,16 @@ __global__ void final_grad_kernel(const float* __restrict__ dxd, const float* __
   if (dyn && blockIdx.x == 0)  // re-arm the running maximum for the next step (GUIDE_GRAD of step k+1 is a later launch)
     for (int b = threadIdx.x; b < B; b += blockDim.x) dyn[b] = 0.f;
 }
-__global__ void magnitude_clamp_kernel(float* __restrict__ g, int64_t n, const float* __restrict__ ws, int nparts, float max_rms) {
+// n_rms: the element count the RMS is taken over -- the whole batch; larger than n when the batch is sharded over ranks and ws
+// holds the all-reduced partial sums (MAG_CLAMP)
+__global__ void magnitude_clamp_kernel(float* __restrict__ g, int64_t n, const float* __restrict__ ws, int nparts, float max_rms, int64_t n_rms) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float s_scale;
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int i = 0; i < nparts; ++i) tot += (double)ws[i];
-    const float mag = sqrtf((float)(tot / (double)n));
+    const float mag = sqrtf((float)(tot / (double)n_rms));
     s_scale = mag > 0.f ? fminf(mag, max_rms) / mag : 1.f;
   }
   __syncthreads();
@@ -502,10 +504,17 @@ int launch_final_grad(const CgdOp& op, cudaStream_t st) {
   CGD_CUDA(launch_pdl(final_grad_kernel, dim3(FG_BLOCKS), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (float*)op.p[2], n, op.f[0], (float*)op.p[3],
                       (op.flags & 2) ? (float*)op.p[4] : (float*)nullptr, (int)B, 3 * HW));
   CGD_LAUNCH_CHECK();
-  if (mag) {
-    CGD_CUDA(launch_pdl(magnitude_clamp_kernel, dim3(FG_BLOCKS), dim3(256), 0, st, (float*)op.p[2], n, (const float*)op.p[3], FG_BLOCKS, op.f[1]));
+  if (mag && !(op.flags & 4)) {  // flags 4: the clamp is a separate MAG_CLAMP op (the partial sums are all-reduced over ranks first)
+    CGD_CUDA(launch_pdl(magnitude_clamp_kernel, dim3(FG_BLOCKS), dim3(256), 0, st, (float*)op.p[2], n, (const float*)op.p[3], FG_BLOCKS, op.f[1], n));
     CGD_LAUNCH_CHECK();
   }
+  return 0;
+}
+int launch_mag_clamp(const CgdOp& op, cudaStream_t st) {
+  const int64_t n = op.i[0], n_rms = op.i[1];
+  CGD_CHECK_ARG(n > 0 && n_rms >= n && op.p[0] && op.p[1], "mag_clamp: bad args");
+  CGD_CUDA(launch_pdl(magnitude_clamp_kernel, dim3(FG_BLOCKS), dim3(256), 0, st, (float*)op.p[0], n, (const float*)op.p[1], FG_BLOCKS, op.f[0], n_rms));
+  CGD_LAUNCH_CHECK();
   return 0;
 }
 

@@ -120,6 +120,7 @@ class GuidedStepB200:
         self.P = max_prompts
         self.scales = dict(cgs=float(clip_guidance_scale), tv=float(tv_scale), rng=float(range_scale), sat=float(sat_scale))
         self.use_magnitude = bool(use_magnitude)
+        self.mag_sync = False
         self.seed_scale, self.vit_grad_scale = float(seed_scale), float(vit_grad_scale)
         self.use_graph = use_graph and self.device.type == "cuda"
         self.plan = p = Plan(conv_impl=conv_impl)
@@ -212,9 +213,16 @@ class GuidedStepB200:
             if dyn:
                 p.emit("SEED_QUANT", i=[B, HW, IN_PAD], p=[(self.seed_f32, 0), (self.seed_dyn, 0), (self.unet.seed, 0)], tag="seed scale")
             p.mark("final")
-            p.emit("FINAL_GRAD", flags=(1 if self.use_magnitude else 0) | (2 if dyn else 0), i=[B, HW],
+            # use_magnitude clamps by the RMS of the WHOLE batch (cgd/cgd.py:229-232).  With the batch sharded over ranks FINAL_GRAD
+            # only writes its partial sums, the host all-reduces the 128 floats (the step's one data-path collective, 512 bytes)
+            # and MAG_CLAMP applies the clamp; a single rank keeps the two-launch FINAL_GRAD.
+            self.mag_sync = self.use_magnitude and self.world > 1
+            p.emit("FINAL_GRAD", flags=(1 if self.use_magnitude else 0) | (2 if dyn else 0) | (4 if self.mag_sync else 0), i=[B, HW],
                    f=[1.0 / self.seed_scale if not dyn else 0.0, 0.05],
                    p=[(self.dx_direct, 0), (self.unet.dx, 0), (self.g, 0), (self.fg_ws, 0)] + ([(self.seed_dyn, 0)] if dyn else []), tag="-grad")
+            if self.mag_sync:
+                p.mark("mag")
+                p.emit("MAG_CLAMP", i=[n3, self.global_batch * 3 * HW], f=[0.05], p=[(self.g, 0), (self.fg_ws, 0)], tag="rms clamp")
         n = n3
         p.mark("upd_anc_g")
         p.emit("SAMPLE_ANCESTRAL", i=[n], p=[(self.mean, 0), (self.var, 0), (self.logvar, 0), (self.g, 0), (self.noise, 0), (self.sc, 0), (self.sample, 0)])
@@ -322,9 +330,20 @@ class GuidedStepB200:
         self.plan.run_range("sph" + sfx, "cut_bwd" + sfx)
         self._run_vit("bwd", None, cutn)
         for a, b in (("cut_bwd" + sfx, "cut_end" + sfx),) + ((("lpips", "lpips_end"),) if self.lpips is not None else ()) + (
-                ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g")):
+                ("guide", "final"), ("unet_bwd", "unet_end")):
             self.plan.run_range(a, b)
+        self._run_final(self.plan.run_range)
         return self.img(self.g)
+
+    def _run_final(self, pr):
+        """-grad (+ RMS clamp).  Sharded batch with use_magnitude: partial sums -> all-reduce over ranks -> clamp."""
+        if not self.mag_sync:
+            pr("final", "upd_anc_g")
+            return
+        import torch.distributed as dist
+        pr("final", "mag")
+        dist.all_reduce(self.v(self.fg_ws))
+        pr("mag", "upd_anc_g")
 
     def update(self, diffusion, mode, t_index, g, noise, eta=0.0) -> th.Tensor:
         if mode == "ddim" and eta != 0.0:
@@ -351,7 +370,7 @@ class GuidedStepB200:
             raise ValueError(f"engine built for cutout counts {sorted(self.vits)}, got {cutn}")
         return f"@{cutn}"
 
-    def _run_all(self, mode, runner=None, cutn=None):
+    def _run_all(self, mode, runner=None, cutn=None, part=None):
         pr = runner or self.plan.run_range
         sfx = self._sfx(cutn)
         pr("unet_emb", "unet_bwd")
@@ -365,7 +384,13 @@ class GuidedStepB200:
             pr("lpips", "lpips_end")
         pr("guide", "final")
         pr("unet_bwd", "unet_end")
-        pr("final", "upd_anc_g")
+        if part == "A":  # everything up to the partial sums of the sharded RMS clamp (see replay)
+            pr("final", "mag")
+            return
+        self._run_final(pr)
+        self._run_update(mode, pr)
+
+    def _run_update(self, mode, pr):
         if mode == "ancestral":
             pr("upd_anc_g", "upd_anc")
         else:
@@ -393,7 +418,7 @@ class GuidedStepB200:
         segs = [("unet_emb", "unet_bwd"), ("pmv", "cond"), ("cut_fwd", "sph"), ("vit_fwd", "vit_bwd"), ("sph", "cut_bwd"), ("vit_bwd", "vit_end"),
                 ("cut_bwd", "cut_end")] + ([("lpips", "lpips_end")] if self.lpips is not None else []) + [
                 ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g"),
-                ("upd_anc_g", "upd_anc") if mode == "ancestral" else ("upd_ddim_g", "upd_ddim")]
+                ("upd_anc_g", "upd_anc") if mode == "ancestral" else ("upd_ddim_g", "upd_ddim")]  # "mag" lies inside (final, upd_anc_g)
         return sum(self.plan.num_launches(m[a], m[b] - m[a]) for a, b in segs)
 
     def stage_step(self, sc: np.ndarray, coords, t_model: float, y=None):
@@ -470,6 +495,23 @@ class GuidedStepB200:
             cutn = None
         if not self.use_graph:
             self._run_all(mode, None, cutn)
+            return
+        if self.mag_sync:  # two graphs around the all-reduce of the RMS partial sums
+            import torch.distributed as dist
+            gs = self._graphs.get((mode, cutn))
+            if gs is None:
+                self._run_all(mode, None, cutn)
+                th.cuda.synchronize()
+                ga, gb = th.cuda.CUDAGraph(), th.cuda.CUDAGraph()
+                with th.cuda.graph(ga):
+                    self._run_all(mode, None, cutn, part="A")
+                with th.cuda.graph(gb):
+                    self.plan.run_range("mag", "upd_anc_g")
+                    self._run_update(mode, self.plan.run_range)
+                gs = self._graphs[(mode, cutn)] = (ga, gb)
+            gs[0].replay()
+            dist.all_reduce(self.v(self.fg_ws))
+            gs[1].replay()
             return
         g = self._graphs.get((mode, cutn))
         if g is None:

@@ -150,7 +150,9 @@ enum {
   /* g = -(dx_direct + dx_unet / seed scale), optional RMS clamp (cgd/cgd.py:228-232).
    * p0 dx_direct(f NCHW) p1 dx_unet(f NCHW, still multiplied by the seed scale)|0 p2 g(f NCHW) p3 ws(f [128])|0
    * i0 B i1 HW ; f0 1/seed scale f1 max rms ; flags 1 = use_magnitude (whole-batch RMS clamp, two launches),
-   * flags 2 = dynamic seed scaling: p4 dyn(f [2B]), per-image 1/scale instead of f0 */
+   * flags 2 = dynamic seed scaling: p4 dyn(f [2B]), per-image 1/scale instead of f0
+   * flags 4 (with 1) = only the partial sums of squares are written to ws; the clamp is a separate CGD_OP_MAG_CLAMP (batch sharded
+   * over ranks: the caller all-reduces ws in between) */
   CGD_OP_FINAL_GRAD = 26,
   /* ancestral update ([3P] p_sample_with_grad / condition_mean_with_grad): sample = mean + var*g + nz*exp(.5 logvar)*noise
    * p0 mean p1 variance p2 log_variance p3 g|0 p4 noise p5 sc p6 sample ; i0 n elements */
@@ -213,6 +215,9 @@ enum {
    * p0 seed_f32(f [B,HW,3]) p1 dyn(f [2B]) p2 seed(h) ; i0 B i1 HW i2 ld.  FINAL_GRAD flags 2 (p4 = dyn) divides dx_unet by
    * scale_b and resets the maxima. */
   CGD_OP_SEED_QUANT = 45,
+  /* whole-batch RMS clamp of cgd/cgd.py:229-232 from (all-reduced) partial sums: g *= min(rms, f0) / rms, rms = sqrt(sum(ws) / i1).
+   * p0 g(f, i0 local elements) p1 ws(f [128]) ; i0 n local i1 n of the whole batch ; f0 max rms */
+  CGD_OP_MAG_CLAMP = 46,
   CGD_OP__COUNT
 };
 

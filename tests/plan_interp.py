@@ -547,10 +547,21 @@ class Interp:
             else:
                 g = g + self.flat(op.p[1], n) * op.f[0]
         g = -g
-        if op.flags & 1:
+        if op.flags & 1 and op.flags & 4:  # partial sums only: MAG_CLAMP follows (after the caller's all-reduce)
+            ws = self.flat(op.p[3], 128)
+            ws.zero_()
+            ws[0] = g.double().square().sum().float()
+        elif op.flags & 1:
             mag = g.square().mean().sqrt()
             g = g * mag.clamp(max=op.f[1]) / mag
         self.flat(op.p[2], n).copy_(g)
+
+    def op_MAG_CLAMP(self, op):
+        n, n_rms = op.i[:2]
+        g = self.flat(op.p[0], n)
+        mag = (self.flat(op.p[1], 128).double().sum() / n_rms).sqrt().float()
+        if mag > 0:
+            g.mul_(mag.clamp(max=op.f[0]) / mag)
 
     def op_SAMPLE_ANCESTRAL(self, op):
         n = op.i[0]

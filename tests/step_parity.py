@@ -31,7 +31,7 @@ def prod_unet_cfg(ocfg):
 
 
 def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0, respacing="25", conv_impl=0, use_graph=False, P=1,
-               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None, hw=None):
+               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None, hw=None, rank=0, world_size=1):
     ocfg = tiny_config(image_size=image, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(image // 2,),
                        class_cond=True, use_new_attention_order=new_order)
     ounet = seeded_init_(UNetModel(ocfg)).eval()
@@ -55,7 +55,7 @@ def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0
     eng = pg.GuidedStepB200(prod_unet_cfg(ocfg), ounet.state_dict(), pv.ViTConfig(32, 16, 128, 2, 64), oclip.state_dict(), batch=B,
                             num_cutouts=cutn, max_prompts=P, use_magnitude=use_magnitude, device=device, conv_impl=conv_impl,
                             height=(hw or (image, image))[0], width=(hw or (image, image))[1],
-                            use_graph=use_graph, vit_streams=vit_streams, cutn_variants=cutn_variants, lpips_sd=lp_sd, init_scale=init_scale, cutout_resize=cutout_resize, **kw)
+                            rank=rank, world_size=world_size, use_graph=use_graph, vit_streams=vit_streams, cutn_variants=cutn_variants, lpips_sd=lp_sd, init_scale=init_scale, cutout_resize=cutout_resize, **kw)
     eng.set_targets(targets, weights)
     return dict(ounet=ounet, oclip=oclip, odiff=odiff, pdiff=pdiff, eng=eng, targets=targets, weights=weights, kw=kw, olp=olp, init=init,
                 init_scale=init_scale, cutout_resize=cutout_resize,

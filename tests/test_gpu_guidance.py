@@ -69,3 +69,29 @@ def test_cutouts_backward_golden(golden):
                                      ctypes.c_void_p(th.cuda.current_stream().cuda_stream))
     _lib.check(rc)
     assert np.allclose(dx.cpu().numpy(), g["cut_grad"], atol=2e-3, rtol=2e-3)
+
+
+def test_sharded_rms_clamp_ops_equal_fused():
+    """FINAL_GRAD(partial sums only) + MAG_CLAMP -- the sharded-batch form of the whole-batch RMS clamp (cgd/cgd.py:229-232) --
+    equals the two-launch FINAL_GRAD when the 'whole batch' is the local one, and scales with the global element count."""
+    from clip_guided_diffusion_b200.plan import Plan
+    B, HW = 2, 48 * 48
+    n = B * 3 * HW
+    outs = {}
+    for name in ("fused", "split", "split_2x"):
+        plan = Plan()
+        dxd, dxu, g, ws = plan.new(n, "f", "dxd"), plan.new(n, "f", "dxu"), plan.new(n, "f", "g"), plan.new(128, "f", "ws")
+        plan.emit("FINAL_GRAD", flags=1 if name == "fused" else 5, i=[B, HW], f=[0.5, 0.05], p=[(dxd, 0), (dxu, 0), (g, 0), (ws, 0)])
+        if name != "fused":
+            plan.emit("MAG_CLAMP", i=[n, n if name == "split" else 2 * n], f=[0.05], p=[(g, 0), (ws, 0)])
+        plan.finalize("cuda")
+        gen = th.Generator().manual_seed(1)
+        plan.view(dxd).copy_(th.randn(n, generator=gen))
+        plan.view(dxu).copy_(th.randn(n, generator=gen))
+        plan.run()
+        th.cuda.synchronize()
+        outs[name] = plan.view(g).float().cpu().clone()
+    assert abs(float(outs["fused"].square().mean().sqrt()) - 0.05) < 1e-5
+    assert th.allclose(outs["split"], outs["fused"], rtol=1e-6, atol=1e-9)
+    # twice the element count with the same sum of squares: the RMS halves by sqrt(2) but still exceeds the cap -> 0.05 * sqrt(2) locally
+    assert abs(float(outs["split_2x"].square().mean().sqrt()) - 0.05 * 2 ** 0.5) < 1e-5
