@@ -91,3 +91,30 @@ def test_param_inventories_match_oracle():
             m = CLIPVisualOnly(OV[name])
         ref = {k: tuple(v.shape) for k, v in m.state_dict().items()}
         assert pw.vit_param_shapes(pv.VIT_CONFIGS[name]) == ref
+
+
+def test_cluster_split_picks_are_eligible():
+    """plan.pick_cluster_split only returns configurations the C side accepts (csrc/conv_tc3.cu: conv_cluster_split_ok) and that fit
+    one wave of clusters; every K split is non-empty."""
+    from clip_guided_diffusion_b200 import plan as P
+    seen = 0
+    for (NB, H, W) in [(1, 8, 8), (2, 8, 8), (1, 16, 16), (1, 32, 32), (1, 64, 64), (1, 1, 800), (1, 1, 3152), (4, 16, 16)]:
+        m_tiles = P.conv_tile_count(NB, H, W)
+        for cin in (256, 512, 768, 1024, 1536, 2048, 2304, 3072):
+            for cout in (256, 512, 768, 1024, 1536, 2048, 3072):
+                for taps in (1, 9):
+                    kb = taps * cin // 64
+                    npad = P._npad(cout)
+                    pick = P.pick_cluster_split(m_tiles, npad, kb, cout)
+                    if pick is None:
+                        continue
+                    bn, S, est = pick
+                    seen += 1
+                    assert bn in (64, 128, 192, 256) and npad % bn == 0 and 2 <= S <= 8
+                    assert bn % S == 0 and (bn // S) % 16 == 0 and cout % 8 == 0
+                    kps = -(-kb // S)
+                    assert (S - 1) * kps < kb and kps >= 3            # no empty split, a pipeline worth filling
+                    assert (m_tiles + 1) // 2 * (npad // bn) <= P.cluster_capacity(bn, S)
+                    assert est > 0
+    assert seen > 50
+    assert P.pick_cluster_split(2, 1024, 144, 1023) is None  # Cout % 8 != 0: the vector epilogue cannot store it
