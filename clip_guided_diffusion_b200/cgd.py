@@ -2,8 +2,9 @@
 
 Same keyword arguments and the same generator contract (yields ``(batch_idx, png_path)``); set-up stays Python and
 runs once (seed, prompt encoding, weight loading, cutout cache), the per-timestep work is the engine's fused step.
-Out of scope here, exactly as SURVEY.md section 2 marks them: checkpoint download, W&B, GIF/MP4, LPIPS init loss
-(``init_scale``), torchvision augmentations, image prompts (the reference's ``encode_image_prompt`` crashes, quirk B5).
+Out of scope here, exactly as SURVEY.md section 2 marks them: checkpoint download, W&B, GIF/MP4, torchvision augmentations,
+image prompts (the reference's ``encode_image_prompt`` crashes, quirk B5).  The LPIPS init loss (``init_image`` + ``init_scale``)
+runs on the engine when the VGG weights are given (``lpips_state_dict=``) or the ``lpips`` package is installed.
 
 Weights: pass ``unet_state_dict`` / ``clip_state_dict`` (upstream key layout), or have the reference's checkpoints on
 disk under ``checkpoints_dir`` (``256x256_diffusion.pt`` ..., ``clip/ViT-B-32.pt``).  Text prompts need a text tower:

@@ -477,16 +477,20 @@ class GuidedStepB200:
         self.h2d_bytes += pl.numel() * 4 + pw.numel() * 4 + pt.numel() * 4 + pi_.numel() * 4
 
     def fused_step(self, diffusion, mode, t_index, img, y, cond_fn, eta=0.0) -> dict:
+        # RNG order of the reference: the ancestral sampler draws its noise BEFORE cond_fn (whose MakeCutouts draws the windows
+        # from the CPU generator), DDIM AFTER it.  On a GPU the two come from different generators and the order is immaterial;
+        # it is kept anyway so a CPU run (tests/test_loops_cpu.py) consumes the default generator exactly like the reference.
         fac_index = cond_fn.current_timestep
+        if mode == "ancestral":
+            self.draw_noise()
         coords = cond_fn.next_coords(self.H, self.W)
+        if mode != "ancestral":
+            self.draw_noise()
         sc = diffusion.scalar_table(t_index, fac_index, eta)
         self.stage_step(sc, coords, diffusion.model_timestep(t_index), y)
         xin = self.img(self.unet.x_in)
         if img.data_ptr() != xin.data_ptr():
             xin.copy_(img, non_blocking=True)
-        # RNG order: ancestral draws before cond_fn, DDIM after (values are identical either way: the generator is only
-        # consumed by this draw within a step; cutout windows come from the CPU generator)
-        self.draw_noise()
         self.replay(mode, len(coords) if self.cutn else None)
         return {"sample": self.img(self.sample).clone(), "pred_xstart": self.img(self.x0).clone()}
 
