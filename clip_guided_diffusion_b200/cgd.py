@@ -136,11 +136,13 @@ def clip_guided_diffusion(
     H, W = image_size + height_offset, image_size + width_offset
     local_b = batch_size // world_size
     assert local_b * world_size == batch_size, "batch_size must divide evenly over the ranks"
-    engine = GuidedStepB200(unet_cfg, unet_sd, vit_cfg, clip_sd, batch=local_b, height=H, width=W, num_cutouts=num_cutouts,
+    # progressive_cutout runs max(4, n // 4), max(8, n // 2), n cutouts (cgd/cgd.py:167-175): the middle count exceeds n when n < 16
+    counts = CondFnB200.progressive_counts(num_cutouts) if progressive_cutout else (num_cutouts,)
+    engine = GuidedStepB200(unet_cfg, unet_sd, vit_cfg, clip_sd, batch=local_b, height=H, width=W, num_cutouts=max(counts),
                             max_prompts=target_embeds.shape[0], clip_guidance_scale=clip_guidance_scale, tv_scale=tv_scale,
                             range_scale=range_scale, sat_scale=sat_scale, use_magnitude=use_magnitude, device=device, rank=rank,
                             world_size=world_size,
-                            cutn_variants=CondFnB200.progressive_counts(num_cutouts) if progressive_cutout else (),
+                            cutn_variants=tuple(c for c in counts if c != max(counts)),
                             lpips_sd=_lpips_sd(lpips_state_dict) if (init_image is not None and init_scale != 0) else None,
                             init_scale=init_scale, cutout_resize=cutout_resize)
     engine.set_targets(target_embeds, weights)

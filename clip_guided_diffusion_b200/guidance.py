@@ -52,6 +52,9 @@ class MakeCutouts(th.nn.Module):
     def coords_for(self, side_x, side_y, use_cache=False, num_cutouts_override=None):
         cutn = num_cutouts_override if num_cutouts_override is not None else self.cutn
         if use_cache and self.cached_coords is not None:
+            if len(self.cached_coords) < cutn:  # the reference fails one line later, at .view([current_cutn, n, -1]) (cgd/cgd.py:194-195)
+                raise RuntimeError(f"{cutn} cutouts requested but only {len(self.cached_coords)} cached: cached_cutouts with "
+                                   "progressive_cutout needs num_cutouts >= 16 (the schedule's middle count is max(8, n // 2))")
             return self.cached_coords[:cutn]
         return self._generate_coords(side_x, side_y, cutn)
 
@@ -547,10 +550,13 @@ class CondFnB200:
         self.engine, self.diffusion, self.make_cutouts = engine, diffusion, make_cutouts
         self.cached_cutouts, self.reduce_clip, self.progressive_cutout = cached_cutouts, reduce_clip, progressive_cutout
         self.current_timestep = diffusion.num_timesteps - 1  # cgd/cgd.py:265
-        if progressive_cutout:
-            missing = set(self.progressive_counts(engine.cutn)) - set(engine.vits)
-            if missing:
-                raise ValueError(f"progressive_cutout needs an engine built with cutn_variants={self.progressive_counts(engine.cutn)}")
+        # the schedule follows the user's num_cutouts (make_cutouts.cutn); for num_cutouts < 16 its middle count max(8, n // 2)
+        # EXCEEDS num_cutouts, so the engine is built for the largest count of the schedule (cgd.py does that)
+        counts = self.progressive_counts(make_cutouts.cutn) if progressive_cutout else (make_cutouts.cutn,)
+        missing = set(counts) - set(engine.vits)
+        if missing and engine.cutn:
+            raise ValueError(f"engine built for cutout counts {sorted(engine.vits)}; this cond_fn needs {sorted(set(counts))} "
+                             "(GuidedStepB200(num_cutouts=max, cutn_variants=the others))")
 
     @staticmethod
     def progressive_counts(num_cutouts: int) -> tuple:
@@ -558,7 +564,7 @@ class CondFnB200:
         return (max(4, num_cutouts // 4), max(8, num_cutouts // 2), num_cutouts)
 
     def current_cutn(self) -> int:
-        n = self.engine.cutn
+        n = self.make_cutouts.cutn
         if not self.progressive_cutout:
             return n
         total = self.diffusion.num_timesteps

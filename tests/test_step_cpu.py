@@ -58,6 +58,26 @@ def test_progressive_cutout_schedule():
             vits = {16: None}
         pg.CondFnB200(Small(), Diff(), mk, progressive_cutout=True)
 
+    # num_cutouts < 16: the middle phase runs max(8, n // 2) = 8 cutouts, MORE than num_cutouts (the reference does the same);
+    # the engine is then built for 8 with a 4-cutout variant (cgd.py)
+    class Eng8:
+        cutn = 8
+        vits = {4: None, 8: None}
+    mk4 = pg.MakeCutouts(224, 4)
+    cf = pg.CondFnB200(Eng8(), Diff(), mk4, progressive_cutout=True)
+    seen = []
+    for step in range(100):
+        seen.append(cf.current_cutn())
+        assert len(cf.next_coords(256, 256)) == seen[-1]
+        cf.step_done()
+    assert seen == [4 if (100 - t) / 100 < 0.3 else (8 if (100 - t) / 100 < 0.7 else 4) for t in range(99, -1, -1)]
+    # with cached_cutouts only num_cutouts windows exist: the reference crashes at .view([8, n, -1]); here a clear error
+    mk4.cache_coordinates(256, 256)
+    cf = pg.CondFnB200(Eng8(), Diff(), mk4, progressive_cutout=True, cached_cutouts=True)
+    cf.current_timestep = 50
+    with pytest.raises(RuntimeError, match="cached"):
+        cf.next_coords(256, 256)
+
 
 @pytest.mark.parametrize("mode", ["ancestral", "ddim"])
 def test_short_chain_matches_oracle(mode):
