@@ -63,3 +63,44 @@ def test_sampling_loops_follow_the_reference_draw_order(mode, fused, skip):
     assert cond.current_timestep == ocond.current_timestep == T - 1 - steps  # quirk B2: not advanced by skip_timesteps
     for k, ((so, xo), (se, xe)) in enumerate(zip(outs_o, outs_e)):
         assert rel(se, so) < 2e-2 and rel(xe, xo) < 2e-2, (k, rel(se, so), rel(xe, xo))
+
+
+def test_reduce_clip_schedule_matches_the_reference_rule():
+    """reduce_clip (cgd/cgd.py:141-144, 157-164): the first 20 % of the steps are skipped through skip_timesteps, up to 70 % CLIP
+    guidance runs on every 4th step and cond_fn returns zeros otherwise (the sampler then takes an unguided step)."""
+    B, cutn, image = 1, 2, 32
+    ctx = build_tiny("cpu", B=B, cutn=cutn, image=image, use_magnitude=True)
+    eng = _interpreted(ctx)
+    pdiff, odiff = ctx["pdiff"], ctx["odiff"]
+    T = pdiff.num_timesteps
+    skip = int(T * 0.2)
+    cond = pg.CondFnB200(eng, pdiff, pg.MakeCutouts(32, cutn), reduce_clip=True)
+    inner = og.OracleCondFn(odiff, ctx["oclip"], ctx["targets"], ctx["weights"], cut_size=32, num_cutouts=cutn, use_magnitude=True, **ctx["kw"])
+    guided = []
+
+    def ocond(x, t, out, y=None):  # the reference's rule, restated around the oracle's cond_fn
+        pct = (T - inner.current_timestep) / T
+        if pct < 0.7 and int((pct - 0.2) * T) % 4 != 0:
+            guided.append(False)
+            return th.zeros_like(x)
+        guided.append(True)
+        return inner(x, t, out, y=y)
+
+    shape = (B, 3, image, image)
+    kw = dict(clip_denoised=False, model_kwargs={"y": th.zeros(B, dtype=th.long)}, randomize_class=True, cond_fn_with_grad=True,
+              skip_timesteps=skip, progress=False)
+    th.manual_seed(1)
+    outs_o = []
+    for o in odiff.p_sample_loop_progressive(ctx["ounet"], shape, cond_fn=ocond, **kw):
+        outs_o.append(o["sample"].detach().clone())
+        inner.step_done()
+    state = th.get_rng_state()
+    th.manual_seed(1)
+    outs_e = []
+    for e in pdiff.p_sample_loop_progressive(eng.model, shape, cond_fn=cond, **kw):
+        outs_e.append(e["sample"].float().clone())
+        cond.step_done()
+    assert th.equal(th.get_rng_state(), state)  # skipped steps draw no cutout windows on either side
+    assert len(outs_e) == len(outs_o) == T - skip and 0 < sum(guided) < len(guided)
+    worst = max(rel(a, b) for a, b in zip(outs_e, outs_o))
+    assert worst < 3e-2, worst
