@@ -90,6 +90,11 @@ def _lpips_sd(given):
     return lpips.LPIPS(net="vgg").state_dict()
 
 
+def _require_cuda(device):
+    if not str(device).startswith("cuda") or not th.cuda.is_available():
+        raise RuntimeError("clip_guided_diffusion_b200 runs the sampling step on a CUDA (sm_100a) device only; there is no CPU path")
+
+
 def clip_guided_diffusion(
     image_size: int = 128, num_cutouts: int = 16, prompts: "list[str]" = [], image_prompts: "list[str]" = [],
     clip_guidance_scale: int = 1000, tv_scale: float = 150, range_scale: float = 50, sat_scale: float = 0, init_scale: float = 0,
@@ -106,8 +111,7 @@ def clip_guided_diffusion(
 ):
     if len(device) == 0:
         device = "cuda"
-    if not str(device).startswith("cuda") or not th.cuda.is_available():
-        raise RuntimeError("clip_guided_diffusion_b200 runs the sampling step on a CUDA (sm_100a) device only; there is no CPU path")
+    _require_cuda(device)
     if image_prompts:
         raise NotImplementedError("image prompts are unsupported (the reference's encode_image_prompt crashes, SURVEY quirk B5)")
     if wandb_project is not None:

@@ -1,0 +1,52 @@
+"""CPU: the orchestration of `clip_guided_diffusion(...)` (a generator of (batch_idx, png_path), cgd/cgd.py:19-55,
+265-271) with the engine's kernels interpreted: the 64x64 checkpoint architecture, three steps.  The device check and the engine
+class are patched (test seams only); the same call runs on the device in tests/test_gpu_entry.py."""
+import os
+
+import pytest
+import torch as th
+
+from clip_guided_diffusion_b200 import cgd
+from clip_guided_diffusion_b200 import guidance as pg
+from clip_guided_diffusion_b200 import unet as pu
+from clip_guided_diffusion_b200 import vit as pv
+from clip_guided_diffusion_b200 import weights as pw
+from tests.plan_interp import Interp
+
+
+class _InterpretedEngine(pg.GuidedStepB200):
+    def __init__(self, *a, **k):
+        k["device"] = "cpu"
+        super().__init__(*a, **k)
+        it = Interp(self.plan)
+        self.plan.run_range = lambda a, b, stream=None: it.run_range(a, b)
+        self.plan.run = lambda first=0, count=None, stream=None: it.run(first, len(self.plan.ops) - first if count is None else count)
+
+
+def test_clip_guided_diffusion_generator_on_the_interpreter(tmp_path, monkeypatch):
+    from PIL import Image
+    with pytest.raises(RuntimeError, match="CUDA"):
+        next(cgd.clip_guided_diffusion(image_size=64, device="cpu"))
+    monkeypatch.setattr(cgd, "_require_cuda", lambda device: None)
+    monkeypatch.setattr(cgd, "GuidedStepB200", _InterpretedEngine)
+    monkeypatch.chdir(tmp_path)  # log_image also writes ./current.png like the reference
+    ucfg, vcfg = pu.config_for(64, True), pv.ViTConfig(32, 16, 64, 1, 32)  # the real 64x64 UNet, a one-layer CLIP tower
+    usd = pw.seeded_state_dict(pw.unet_param_shapes(ucfg), 1234)
+    vsd = pw.seeded_state_dict(pw.vit_param_shapes(vcfg), 1235)
+    tgt = th.randn(2, 32, generator=th.Generator().manual_seed(0))
+    got = list(cgd.clip_guided_diffusion(image_size=64, num_cutouts=4, prompts=["a test prompt"], batch_size=1, timestep_respacing="25",
+                                         skip_timesteps=22, save_frequency=2, prefix_path=tmp_path / "out", progress=False, seed=0,
+                                         device="cpu", unet_state_dict=usd, clip_state_dict=vsd, target_embeds=tgt, weights=[2.0, 1.0],
+                                         progressive_cutout=True))
+    # 25 - 22 = 3 steps; frames at steps 0 and 2 (current_timestep never reaches -1 with skip_timesteps: quirk B2)
+    assert [b for b, _ in got] == [0, 0]
+    for (b, path), step in zip(got, (0, 2)):
+        assert path.endswith(os.path.join("a_test_prompt", "00", f"{step:04d}.png")) and os.path.exists(path), path
+        im = Image.open(path)
+        assert im.size == (64, 64) and im.mode == "RGB"
+    assert os.path.exists(tmp_path / "current.png")
+    with pytest.raises(RuntimeError, match="sum to 0"):
+        next(cgd.clip_guided_diffusion(image_size=64, device="cpu", unet_state_dict=usd, clip_state_dict=vsd, target_embeds=tgt, weights=[1.0, -1.0]))
+    with pytest.raises(NotImplementedError):
+        next(cgd.clip_guided_diffusion(image_size=64, device="cpu", image_prompts=["x.png"], unet_state_dict=usd, clip_state_dict=vsd,
+                                       target_embeds=tgt, weights=[1.0, 1.0]))
