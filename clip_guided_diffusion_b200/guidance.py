@@ -34,6 +34,7 @@ class MakeCutouts(th.nn.Module):
                                       "them, cgd/cgd.py:402)")
         self.cut_size, self.cutn, self.cut_pow = cut_size, num_cutouts, cutout_size_power
         self.cached_coords = None
+        self.augs = th.nn.Identity()  # the reference's empty tvt.Compose([]) when use_augs is off (cgd/modules.py:24)
 
     def _generate_coords(self, side_x: int, side_y: int, cutn: int):
         max_size = min(side_y, side_x)
@@ -103,6 +104,17 @@ class EngineModel:
 
     def convert_to_fp16(self):
         return self
+
+    def to(self, device=None, *a, **k):  # cgd/script_util.py:318 chains .requires_grad_(False).eval().to(device)
+        if device is not None and th.device(device).type != self.engine.device.type:
+            raise RuntimeError(f"the engine lives on {self.engine.device}; build a GuidedStepB200 per device")
+        return self
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Weights are packed into kernel layouts (K-major fp16 tiles, tap-flipped dgrad copies, fused emb matrix) when the engine is
+        built: pass the checkpoint's state_dict to ``GuidedStepB200(unet_cfg, state_dict, ...)`` (cgd/script_util.py:316-317
+        becomes that constructor call)."""
+        raise NotImplementedError("pass the state_dict to GuidedStepB200(...) -- weights are packed once at construction")
 
 
 class GuidedStepB200:

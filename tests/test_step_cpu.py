@@ -86,3 +86,27 @@ def test_short_chain_matches_oracle(mode):
     from tests.step_parity import run_tiny_chain
     res = run_tiny_chain(device="cpu", mode=mode, steps=6, runner_factory=_interp_runner, image=32, B=1, cutn=2, use_magnitude=True)
     assert res["finite"] and max(res["drift"]) < 2e-2 and res["psnr_sample"] > 40.0, res
+
+
+def test_make_cutouts_surface():
+    """cgd/modules.py:5-66: constructor, attributes, nn.Module-ness, coordinate cache, CPU-generator draw order; re-exported like the
+    reference does (cgd/modules.py, cgd/clip_util.py:13)"""
+    import torch as th
+    from clip_guided_diffusion_b200 import clip_util, modules
+    from clip_guided_diffusion_b200.guidance import MakeCutouts
+    from oracle import guidance as og
+    assert modules.MakeCutouts is MakeCutouts and clip_util.MakeCutouts is MakeCutouts
+    mk = MakeCutouts(224, 16, cutout_size_power=0.5)
+    assert isinstance(mk, th.nn.Module) and mk.to("cpu") is mk
+    assert (mk.cut_size, mk.cutn, mk.cut_pow, mk.cached_coords) == (224, 16, 0.5, None) and hasattr(mk, "augs")
+    th.manual_seed(0)
+    mk.cache_coordinates(256, 320)
+    th.manual_seed(0)
+    ref = og.MakeCutouts(224, 16, 0.5)
+    ref.cache_coordinates(256, 320)
+    assert mk.cached_coords == ref.cached_coords and len(mk.cached_coords) == 16
+    assert mk.coords_for(256, 320, use_cache=True, num_cutouts_override=4) == ref.cached_coords[:4]
+    with pytest.raises(NotImplementedError):
+        MakeCutouts(224, 16, use_augs=True)
+    with pytest.raises(Exception):
+        mk(th.zeros(1, 3, 256, 256))  # forward is the CUDA kernel: no CPU fallback
