@@ -58,3 +58,21 @@ def test_no_cpu_fallback():
     p.finalize("cpu")
     with pytest.raises(_lib.CgdError):
         p.run()
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/cgd_b200.h is the FFI contract: it must compile as C (no C++ or torch types) and link against the built library"""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "probe.c"
+    src.write_text('#include "cgd_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { CgdOp op; (void)op; printf("%d %d\\n", cgd_abi_version(), (int)sizeof(CgdOp)); return 0; }\n')
+    exe = tmp_path / "probe"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir,
+                        "-l:libcgd_b200.so", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["1", str(8 + 24 * 8 + 8 * 4 + 12 * 8)], out.stdout + out.stderr
