@@ -21,6 +21,7 @@ import torch as th
 from . import gaussian_diffusion as gd
 from .guidance import CondFnB200, GuidedStepB200, MakeCutouts
 from .unet import config_for
+from .rn import RN_CONFIGS, rn_config_from_state_dict
 from .vit import VIT_CONFIGS, vit_config_from_state_dict
 
 CACHE_PATH = os.path.expanduser("~/.cache/clip-guided-diffusion")  # cgd/script_util.py:18
@@ -90,6 +91,16 @@ def _lpips_sd(given):
     return lpips.LPIPS(net="vgg").state_dict()
 
 
+def _tower_config(clip_sd: dict):
+    """ViT-B/32, ViT-B/16, ViT-L/14 (vit.py) or a ModifiedResNet tower -- RN50, RN101 (rn.py) -- recognised from the state_dict keys"""
+    if "visual.layer1.0.conv1.weight" in clip_sd:
+        cfg = rn_config_from_state_dict(clip_sd)
+        if cfg.width % 64:
+            raise NotImplementedError(f"ModifiedResNet width {cfg.width} (RN50x4 / x16 / x64) is not a multiple of the 64-channel K-slice")
+        return cfg
+    return vit_config_from_state_dict(clip_sd)
+
+
 def _require_cuda(device):
     if not str(device).startswith("cuda") or not th.cuda.is_available():
         raise RuntimeError("clip_guided_diffusion_b200 runs the sampling step on a CUDA (sm_100a) device only; there is no CPU path")
@@ -122,7 +133,7 @@ def clip_guided_diffusion(
     Path(prefix_path).mkdir(parents=True, exist_ok=True)
 
     clip_sd = clip_state_dict if clip_state_dict is not None else _load_clip_sd(clip_model_name, checkpoints_dir)
-    vit_cfg = vit_config_from_state_dict(clip_sd) if clip_state_dict is not None else VIT_CONFIGS[clip_model_name]
+    vit_cfg = _tower_config(clip_sd) if clip_state_dict is not None else {**VIT_CONFIGS, **RN_CONFIGS}[clip_model_name]
     if target_embeds is None:
         target_embeds, weights = _encode_text(prompts, clip_model_name, device)
     weights = th.as_tensor(weights, dtype=th.float32)

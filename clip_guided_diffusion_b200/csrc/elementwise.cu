@@ -303,4 +303,86 @@ int launch_vit_embed(const CgdOp& op, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------- CLIP ModifiedResNet AttentionPool2d token assembly
+// y[n,0,:] = mean_t x[n,t,:] + pos[0,:] ; y[n,1+t,:] = x[n,t,:] + pos[1+t,:]  ([3P] clip/model.py AttentionPool2d.forward: cat of the mean
+// token, then the positional embedding; the mean is rounded to fp16 before the add like the reference's fp16 tensors)
+__global__ void attnpool_embed_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ pos, __half* __restrict__ y, int n, int HW,
+                                          int C, int64_t ldx) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int V = C / 8;
+  const int64_t total = (int64_t)n * (HW + 1) * V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % V);
+    const int64_t row = idx / V;
+    const int t = (int)(row % (HW + 1));
+    const int64_t img = row / (HW + 1);
+    const __half* xi = x + img * HW * ldx + v * 8;
+    float a[8];
+    if (t == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = 0.f;
+      for (int u = 0; u < HW; ++u) {
+        float f[8];
+        unpack8(ld8(xi + (int64_t)u * ldx), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += f[j];
+      }
+      const float inv = 1.f / (float)HW;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] *= inv;
+      const half8 h = pack8(a);
+      unpack8(h, a);
+    } else {
+      unpack8(ld8(xi + (int64_t)(t - 1) * ldx), a);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += pos[(int64_t)t * C + v * 8 + j];
+    st8(y + row * C + v * 8, pack8(a));
+  }
+}
+// dx[n,t,:] (=|+=) dy[n,1+t,:] + dy[n,0,:] / HW
+__global__ void attnpool_embed_bwd_kernel(const __half* __restrict__ dy, __half* __restrict__ dx, int n, int HW, int C, int64_t ld_dx, int accumulate) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int V = C / 8;
+  const int64_t total = (int64_t)n * HW * V;
+  const float inv = 1.f / (float)HW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % V);
+    const int64_t row = idx / V;
+    const int t = (int)(row % HW);
+    const int64_t img = row / HW;
+    float a[8], m[8];
+    unpack8(ld8(dy + (img * (HW + 1) + 1 + t) * C + v * 8), a);
+    unpack8(ld8(dy + (img * (HW + 1)) * C + v * 8), m);
+    __half* o = dx + (img * HW + t) * ld_dx + v * 8;
+    if (accumulate) {
+      float c[8];
+      unpack8(ld8(o), c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += c[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fmaf(m[j], inv, a[j]);
+    st8(o, pack8(a));
+  }
+}
+int launch_attnpool_embed_fwd(const CgdOp& op, cudaStream_t st) {
+  const int64_t n = op.i[0], HW = op.i[1], C = op.i[2], ldx = op.i[3];
+  CGD_CHECK_ARG(n > 0 && HW > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C && op.p[0] && op.p[1] && op.p[2], "attnpool_embed_fwd: bad args");
+  CGD_CUDA(launch_pdl(attnpool_embed_fwd_kernel, dim3(ew_blocks(n * (HW + 1) * (C / 8))), dim3(256), 0, st, (const __half*)op.p[0],
+                      (const float*)op.p[1], (__half*)op.p[2], (int)n, (int)HW, (int)C, ldx));
+  CGD_LAUNCH_CHECK();
+  return 0;
+}
+int launch_attnpool_embed_bwd(const CgdOp& op, cudaStream_t st) {
+  const int64_t n = op.i[0], HW = op.i[1], C = op.i[2], ld_dx = op.i[3];
+  CGD_CHECK_ARG(n > 0 && HW > 0 && C % 8 == 0 && ld_dx % 8 == 0 && ld_dx >= C && op.p[0] && op.p[1], "attnpool_embed_bwd: bad args");
+  CGD_CUDA(launch_pdl(attnpool_embed_bwd_kernel, dim3(ew_blocks(n * HW * (C / 8))), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], (int)n,
+                      (int)HW, (int)C, ld_dx, (int)((op.flags & 2) ? 1 : 0)));
+  CGD_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace cgd

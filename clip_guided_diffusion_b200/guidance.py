@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import SC
 from .plan import Plan
 from .unet import IN_PAD, UNetB200, UNetConfig
+from .rn import RNB200, RNConfig
 from .vit import ViTB200, ViTConfig
 
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)  # cgd/clip_util.py:45
@@ -168,7 +169,9 @@ class GuidedStepB200:
             self.g_clip = p.new(n3, "f", "g_clip")
             self.dx_direct = p.new(n3, "f", "dx_direct")
             self.fg_ws = p.new(128, "f", "final_grad_ws")
-            self.vit = ViTB200(vit_cfg, vit_sd, n_images=cutn * B, device=device, plan=p, parts=vit_streams)
+            # CLIP visual tower: ViT (vit.py) or ModifiedResNet (rn.py); both expose patches / embeds / d_embeds / d_patches
+            Tower = RNB200 if isinstance(vit_cfg, RNConfig) else ViTB200
+            self.vit = Tower(vit_cfg, vit_sd, n_images=cutn * B, device=device, plan=p, parts=vit_streams)
             # further cutout counts of the same engine (progressive_cutout, cgd/cgd.py:167-175): own activations and op ranges
             # ("...@c" marks), shared packed weights; the default count keeps the un-suffixed marks
             self.vits = {cutn: self.vit}
@@ -188,7 +191,7 @@ class GuidedStepB200:
             for c in sorted(set(int(v) for v in cutn_variants) - {cutn}):
                 if not 0 < c < cutn:
                     raise ValueError(f"cutn_variants must lie in (0, {cutn}), got {c}")
-                self.vits[c] = ViTB200(vit_cfg, vit_sd, n_images=c * B, device=device, plan=p, parts=vit_streams, suffix=f"@{c}", share=self.vit)
+                self.vits[c] = Tower(vit_cfg, vit_sd, n_images=c * B, device=device, plan=p, parts=vit_streams, suffix=f"@{c}", share=self.vit)
             for c in sorted(self.vits, key=lambda v: v == cutn):  # the default count last: its ranges end at "guide"
                 sfx, vt = ("" if c == cutn else f"@{c}"), self.vits[c]
                 p.mark("cut_fwd" + sfx)

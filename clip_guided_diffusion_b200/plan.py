@@ -661,6 +661,45 @@ class Plan:
         self._tape.append(bwd)
         return y
 
+    def attnpool_embed(self, x: Act, pos: Buf, name="attnpool.embed") -> Act:
+        """[3P] CLIP AttentionPool2d token assembly: [n, HW, C] -> [n*(HW+1) rows, C] = [mean; x] + positional_embedding"""
+        n, HW, C = x.N, x.HW, x.C
+        y = Act(self.new(n * (HW + 1) * C, "h", name), 0, 1, 1, n * (HW + 1), C, C)
+        self.emit("ATTNPOOL_EMBED_FWD", i=[n, HW, C, x.ld], p=[self._ap(x), self._bp(pos), self._ap(y)], tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            assert dy.ld == C
+            cur, has = self.writable_grad(x)
+            dx = cur if has else self.act(x.N, x.H, x.W, x.C, "d_" + name)
+            self.emit("ATTNPOOL_EMBED_BWD", flags=2 if has else 0, i=[n, HW, C, dx.ld], p=[self._ap(dy), self._ap(dx)], tag="d_" + name)
+            self._grads[x.key()] = dx
+
+        self._tape.append(bwd)
+        return y
+
+    def gather_rows(self, x: Act, rows: int, ldx: int, name="rows") -> Act:
+        """y[r, :] = x[row r * (ldx / x.ld), :]: every (ldx / x.ld)-th row of x as a dense [rows, C] matrix (first token of every image).
+        Backward scatters into a zero gradient of the full tensor: the arena is zero-initialised and only these rows are ever
+        written, so the others stay zero across replays (same scheme as the strided layer_norm)."""
+        y = Act(self.new(rows * x.C, "h", name), 0, 1, 1, rows, x.C, x.C)
+        self.emit("COPY", i=[rows, x.C, ldx, y.ld], p=[self._ap(x), self._ap(y)], tag=name)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            assert self.grad_of(x) is None
+            dx = self.act(x.N, x.H, x.W, x.C, "d_" + name)
+            dx.frozen = True
+            self.emit("COPY", i=[rows, x.C, dy.ld, ldx], p=[self._ap(dy), self._ap(dx)], tag="d_" + name)
+            self._grads[x.key()] = dx
+
+        self._tape.append(bwd)
+        return y
+
     def quick_gelu(self, u: Act, name="gelu") -> Act:
         assert u.ld == u.C
         a = self.act(u.N, u.H, u.W, u.C, name)

@@ -84,6 +84,63 @@ def vit_param_shapes(cfg: ViTConfig) -> dict:
     return sh
 
 
+def rn_param_shapes(cfg) -> dict:
+    """CLIP ModifiedResNet visual tower ([3P] clip/model.py) in upstream key layout, BatchNorm buffers included"""
+    w = cfg.width
+    sh = {}
+
+    def conv_bn(conv, bn, cout, cin, k):
+        sh[conv + ".weight"] = (cout, cin, k, k)
+        for suffix in ("weight", "bias", "running_mean", "running_var"):
+            sh[f"{bn}.{suffix}"] = (cout,)
+
+    conv_bn("visual.conv1", "visual.bn1", w // 2, 3, 3)
+    conv_bn("visual.conv2", "visual.bn2", w // 2, w // 2, 3)
+    conv_bn("visual.conv3", "visual.bn3", w, w // 2, 3)
+    inplanes = w
+    for li, (blocks, planes, stride) in enumerate(zip(cfg.layers, (w, 2 * w, 4 * w, 8 * w), (1, 2, 2, 2)), start=1):
+        for bi in range(blocks):
+            pre = f"visual.layer{li}.{bi}"
+            st = stride if bi == 0 else 1
+            conv_bn(pre + ".conv1", pre + ".bn1", planes, inplanes, 1)
+            conv_bn(pre + ".conv2", pre + ".bn2", planes, planes, 3)
+            conv_bn(pre + ".conv3", pre + ".bn3", planes * 4, planes, 1)
+            if st > 1 or inplanes != planes * 4:
+                conv_bn(pre + ".downsample.0", pre + ".downsample.1", planes * 4, inplanes, 1)
+            inplanes = planes * 4
+    C = cfg.embed_dim
+    sh["visual.attnpool.positional_embedding"] = (cfg.tokens, C)
+    for k in "kqv":
+        sh[f"visual.attnpool.{k}_proj.weight"] = (C, C)
+        sh[f"visual.attnpool.{k}_proj.bias"] = (C,)
+    sh["visual.attnpool.c_proj.weight"] = (cfg.output_dim, C)
+    sh["visual.attnpool.c_proj.bias"] = (cfg.output_dim,)
+    return sh
+
+
+def seeded_rn_state_dict(cfg, seed: int = 77) -> dict:
+    """He-initialised convs (the last conv of every block damped so that 16 residual additions keep O(1) activations), BatchNorm with
+    non-trivial running statistics"""
+    g = th.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in rn_param_shapes(cfg).items():
+        if name.endswith("running_mean"):
+            t = th.randn(shape, generator=g) * 0.1
+        elif name.endswith("running_var"):
+            t = 1.0 + 0.2 * th.rand(shape, generator=g)
+        elif name.endswith("positional_embedding"):
+            t = th.randn(shape, generator=g) * shape[1] ** -0.5
+        elif len(shape) >= 2:
+            gain = 0.25 if name.endswith("conv3.weight") else 1.0
+            t = th.randn(shape, generator=g) * gain * (2.0 / math.prod(shape[1:])) ** 0.5
+        elif name.endswith("bias"):
+            t = th.randn(shape, generator=g) * 0.05
+        else:
+            t = 1.0 + 0.1 * th.randn(shape, generator=g)
+        sd[name] = t
+    return sd
+
+
 def lpips_param_shapes() -> dict:
     """lpips.LPIPS(net='vgg') v0.1: ``net.sliceK.<vgg16.features index>.{weight,bias}`` + ``linK.model.1.weight``"""
     from .lpips import CHANNELS, SLICES

@@ -218,6 +218,11 @@ enum {
   /* whole-batch RMS clamp of cgd/cgd.py:229-232 from (all-reduced) partial sums: g *= min(rms, f0) / rms, rms = sqrt(sum(ws) / i1).
    * p0 g(f, i0 local elements) p1 ws(f [128]) ; i0 n local i1 n of the whole batch ; f0 max rms */
   CGD_OP_MAG_CLAMP = 46,
+  /* CLIP ModifiedResNet AttentionPool2d token assembly ([3P] clip/model.py): y[n,0,:] = mean_t x[n,t,:] + pos[0,:] ;
+   * y[n,1+t,:] = x[n,t,:] + pos[1+t,:].  p0 x(h [n,HW,C], row stride i3) p1 pos(f [HW+1,C]) p2 y(h [n,HW+1,C]) ; i0 n i1 HW i2 C i3 ldx */
+  CGD_OP_ATTNPOOL_EMBED_FWD = 47,
+  /* dx[n,t,:] (=|+=) dy[n,1+t,:] + dy[n,0,:] / HW : p0 dy(h [n,HW+1,C]) p1 dx(h, row stride i3) ; i0 n i1 HW i2 C i3 ld_dx ; flags 2 = accumulate */
+  CGD_OP_ATTNPOOL_EMBED_BWD = 48,
   CGD_OP__COUNT
 };
 

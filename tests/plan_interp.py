@@ -386,6 +386,20 @@ class Interp:
         t[:, 0] = self.flat(op.p[1], w).half().float()
         tok.copy_(t + self.V(op.p[2], (T, w), (w, 1)))
 
+    def op_ATTNPOOL_EMBED_FWD(self, op):
+        n, HW, C, ldx = op.i[:4]
+        x = self.V(op.p[0], (n, HW, C), (HW * ldx, ldx, 1)).float()
+        pos = self.V(op.p[1], (HW + 1, C), (C, 1))
+        mean = x.mean(dim=1, keepdim=True).half().float()  # the reference's fp16 mean token
+        self.V(op.p[2], (n, HW + 1, C), ((HW + 1) * C, C, 1)).copy_(th.cat([mean, x], dim=1) + pos)
+
+    def op_ATTNPOOL_EMBED_BWD(self, op):
+        n, HW, C, ld = op.i[:4]
+        dy = self.V(op.p[0], (n, HW + 1, C), ((HW + 1) * C, C, 1)).float()
+        dx = self.V(op.p[1], (n, HW, C), (HW * ld, ld, 1))
+        g = dy[:, 1:] + dy[:, :1] / HW
+        dx.copy_(dx.float() + g if op.flags & 2 else g)
+
     @staticmethod
     def _patchify(img, P, kpad):  # [n,3,cs,cs] -> [n, g*g, kpad] with k = (c, ky, kx)
         n, c, cs, _ = img.shape

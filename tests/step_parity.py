@@ -31,12 +31,21 @@ def prod_unet_cfg(ocfg):
 
 
 def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0, respacing="25", conv_impl=0, use_graph=False, P=1,
-               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None, hw=None, rank=0, world_size=1):
+               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None, hw=None, rank=0, world_size=1, tower="vit"):
     ocfg = tiny_config(image_size=image, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(image // 2,),
                        class_cond=True, use_new_attention_order=new_order)
     ounet = seeded_init_(UNetModel(ocfg)).eval()
-    ovit_cfg = OViTConfig(32, 16, 128, 2, 64)
-    oclip = seeded_init_(CLIPVisualOnly(ovit_cfg), seed=5).eval()
+    if tower == "rn":  # CLIP ModifiedResNet tower (rn.py / oracle/clip_rn.py): one bottleneck per stage, 32 x 32 cutouts
+        from clip_guided_diffusion_b200 import rn as prn
+        from clip_guided_diffusion_b200 import weights as pw
+        from oracle import clip_rn as orn
+        pvit_cfg = prn.RNConfig(layers=(1, 1, 1, 1), output_dim=64, input_resolution=32, width=64)
+        rn_sd = pw.seeded_rn_state_dict(pvit_cfg, seed=5)
+        oclip = orn.CLIPVisualRN(orn.RNConfig(layers=(1, 1, 1, 1), output_dim=64, input_resolution=32, width=64)).eval()
+        oclip.visual.load_state_dict({k[len("visual."):]: v for k, v in rn_sd.items()}, strict=False)
+    else:
+        pvit_cfg = pv.ViTConfig(32, 16, 128, 2, 64)
+        oclip = seeded_init_(CLIPVisualOnly(OViTConfig(32, 16, 128, 2, 64)), seed=5).eval()
     for prm in list(ounet.parameters()) + list(oclip.parameters()):
         prm.requires_grad_(False)
     odiff = od.create_gaussian_diffusion(1000, "linear", respacing)
@@ -52,7 +61,7 @@ def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0
         lp_sd = ol.seeded_state_dict()
         olp = ol.LPIPSVgg(lp_sd)
         init = th.rand(1, 3, image, image, generator=th.Generator().manual_seed(7)) * 2 - 1
-    eng = pg.GuidedStepB200(prod_unet_cfg(ocfg), ounet.state_dict(), pv.ViTConfig(32, 16, 128, 2, 64), oclip.state_dict(), batch=B,
+    eng = pg.GuidedStepB200(prod_unet_cfg(ocfg), ounet.state_dict(), pvit_cfg, oclip.state_dict(), batch=B,
                             num_cutouts=cutn, max_prompts=P, use_magnitude=use_magnitude, device=device, conv_impl=conv_impl,
                             height=(hw or (image, image))[0], width=(hw or (image, image))[1],
                             rank=rank, world_size=world_size, use_graph=use_graph, vit_streams=vit_streams, cutn_variants=cutn_variants, lpips_sd=lp_sd, init_scale=init_scale, cutout_resize=cutout_resize, **kw)

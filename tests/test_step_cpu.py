@@ -19,6 +19,7 @@ def _interp_runner(eng):
                                      # non-square (height_offset / width_offset, cgd/cgd.py:135): windows drawn with the reference's
                                      # swapped sides are clipped at the border (quirk B3) and still pooled to a square
                                      ("ddim", dict(B=1, cutn=6, image=32, hw=(32, 64))),
+                                     ("ddim", dict(B=2, cutn=3, tower="rn")),  # CLIP ModifiedResNet tower instead of the ViT
                                      ("ancestral", dict(B=2, cutn=4, image=32, hw=(48, 32)))])
 def test_step_plan_matches_oracle(mode, kw):
     res = run_tiny_step_parity(device="cpu", mode=mode, runner_factory=_interp_runner, **{"image": 32, **kw})
