@@ -70,6 +70,7 @@ static int dispatch(const CgdOp& op, const ConvTcLaunch* conv, cudaStream_t st) 
     case CGD_OP_MAG_CLAMP: return launch_mag_clamp(op, st);
     case CGD_OP_ATTNPOOL_EMBED_FWD: return launch_attnpool_embed_fwd(op, st);
     case CGD_OP_ATTNPOOL_EMBED_BWD: return launch_attnpool_embed_bwd(op, st);
+    case CGD_OP_GN_APPLY_EPI: return launch_gn_apply_epi(op, st);
     case CGD_OP_LINEAR_SMALL: return launch_linear_small(op, st);
     case CGD_OP_TIMESTEP_EMB: return launch_timestep_emb(op, st);
     case CGD_OP_LABEL_ADD: return launch_label_add(op, st);

@@ -449,6 +449,15 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   // the image are clipped by the TMA unit; needs fp16 channel-contiguous output and whole 64-channel chunks
   p.epi_tma = (!L.cluster_split && conv_use_pair_kernel(L) && !p.out_f32 && p.out_sc == 1 && p.splits == 1 && BN >= 64 && Cout % 64 == 0) ? 1 : 0;
   if (const char* e = getenv("CGD_CONV_EPI_TMA")) if (e[0] == '0') p.epi_tma = 0;
+  // flags 2: the epilogue also reduces its output tile to per-octet sums for the GroupNorm that follows (GN_APPLY_EPI): needs the
+  // TMA-store epilogue and tiles that are full and are 128 consecutive pixels of one image
+  p.epi_stats = nullptr;
+  if (op.flags & 2) {
+    CGD_CHECK_ARG(p.epi_tma && op.p[7] != nullptr && W % p.TW == 0 && H % p.TH == 0 && p.TN == 1 && (p.TW == W || p.TH == 1) && L.m_tiles % 2 == 0,
+                  "conv: epilogue statistics need the TMA-store epilogue and full 128-pixel tiles inside one image (W=%lld H=%lld tile %dx%dx%d)",
+                  (long long)W, (long long)H, p.TW, p.TH, p.TN);
+    p.epi_stats = reinterpret_cast<float*>(op.p[7]);
+  }
   if (p.epi_tma) {
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
     cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};

@@ -29,6 +29,7 @@ struct ConvTcParams {
   const __half* res;
   void* out;
   float* ws;                         // split-K partials [splits][m_tiles*128][Npad]
+  float* epi_stats;                  // flags 2: per (128-pixel tile, 8-channel octet) sum / sum of squares of the fp16 OUTPUT, [m_tiles][Npad/8][2]
 };
 
 struct ConvTcLaunch {

@@ -37,11 +37,13 @@ struct Tc2Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   // epilogue staging: 2 output tiles (TMA store sources); residual tiles are TMA-loaded INTO them and updated in place
   static constexpr int kEpiBytes = BN >= 64 ? 2 * kEpiChunkBytes : 0;
+  static constexpr int kStatBytes = 512;  // STATS instantiation only: epilogue statistics exchange, 2 buffers x 4 warps x 16 floats
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - kEpiBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
+  static_assert(kSmemBytes + kStatBytes <= 227 * 1024, "the STATS instantiation appends kStatBytes");
 };
 
 struct Tile2 {
@@ -60,7 +62,9 @@ __device__ __forceinline__ Tile2 decode_tile(const ConvTcParams& p, int t, int n
   return r;
 }
 
-template <int BN>
+// STATS: the epilogue additionally reduces every output chunk to per-octet sums for the GroupNorm that follows (CONV flags 2); a
+// separate instantiation so that the default kernel's code and shared-memory layout are untouched
+template <int BN, bool STATS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                 const __grid_constant__ CUtensorMap tmRes, const ConvTcParams p, int n_tiles, int pair_tiles, int total_tiles) {
@@ -76,6 +80,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
   uint64_t* res_full_bar = tmem_empty_bar + Cfg::kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 2);
+  float* stat_red = reinterpret_cast<float*>(smem_epi + Cfg::kEpiBytes + 512);  // STATS: [2][4 warps][8 octets][2], past the barriers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -254,6 +259,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             uint8_t* orow = st_out + buf * kEpiChunkBytes + r * 128;
             const uint8_t* rrow = orow;
+            float st_s[8], st_q[8];  // flags 2: per-octet sum / sum of squares of this row's fp16 outputs
 #pragma unroll
             for (int j = 0; j < 8; ++j) {  // 8 channels = one 16-byte unit of the 128-byte row, unit index XOR (row & 7)
               float a[8];
@@ -272,10 +278,44 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int e = 0; e < 8; ++e) a[e] += rr[e];
               }
-              *reinterpret_cast<half8*>(orow + unit) = pack8(a);
+              const half8 hv = pack8(a);
+              *reinterpret_cast<half8*>(orow + unit) = hv;
+              if constexpr (STATS) {  // statistics of the ROUNDED values: what the GroupNorm after this conv reads
+                float f[8];
+                unpack8(hv, f);
+                float s0 = 0.f, q0 = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  s0 += f[e];
+                  q0 = fmaf(f[e], f[e], q0);
+                }
+                st_s[j] = s0;
+                st_q[j] = q0;
+              }
+            }
+            if constexpr (STATS) {  // 128 rows -> one value per octet: warp shuffles, then the four warps through shared memory
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                st_s[j] = warp_sum(st_s[j]);
+                st_q[j] = warp_sum(st_q[j]);
+              }
+              if (lane == 0) {
+                float* dst = stat_red + ((buf * 4 + quad) * 8) * 2;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  dst[2 * j] = st_s[j];
+                  dst[2 * j + 1] = st_q[j];
+                }
+              }
             }
             fence_proxy_async_smem();
             named_bar_sync(1, kEpiThreads2);
+            if (STATS && r < 16) {  // thread (octet j = r / 2, kind = r % 2): fixed-order sum over the four warps
+              const float* src = stat_red + (buf * 4 * 8) * 2 + r;
+              const float v = (src[0] + src[16]) + (src[32] + src[48]);
+              const Tile2 tl2 = decode_tile(p, t, n_tiles, pair_tiles, rank);
+              p.epi_stats[((size_t)tl2.mt * (p.Npad / 8) + (size_t)(col / 8 + (r >> 1))) * 2 + (r & 1)] = v;
+            }
             if (issuer) {
               if (!(p.dbg & 4)) tma_store_4d(st_out + buf * kEpiChunkBytes, &tmOut, col, w0, h0, n0);
               bulk_commit_group();
@@ -391,12 +431,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BN>
+template <int BN, bool STATS>
 static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   using Cfg = Tc2Cfg<BN>;
+  constexpr int kSmem = Cfg::kSmemBytes + (STATS ? Cfg::kStatBytes : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    CGD_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    CGD_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
   const int pair_tiles = (L.m_tiles + 1) / 2;
@@ -409,18 +450,27 @@ static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   ConvTcParams prm = L.p;
   prm.dbg = dbg;
   const int clusters = std::min(total, 74);  // 148 SMs = 74 TPC pairs
-  CGD_CUDA(launch_pdl(conv_tc2_kernel<BN>, dim3(2 * clusters), dim3(kThreads2), Cfg::kSmemBytes, st, L.tmA, L.tmB2, L.tmOut, L.tmRes, prm, L.n_tiles, pair_tiles, total));
+  CGD_CUDA(launch_pdl(conv_tc2_kernel<BN, STATS>, dim3(2 * clusters), dim3(kThreads2), kSmem, st, L.tmA, L.tmB2, L.tmOut, L.tmRes, prm, L.n_tiles, pair_tiles, total));
   return 0;
 }
 
 int conv_tc2_launch(const ConvTcLaunch& L, cudaStream_t st) {
+  if (L.p.epi_stats) {  // prepare() has checked the TMA-store epilogue (BN >= 64) and full tiles
+    switch (L.BN) {
+      case 64: return launch_tc2<64, true>(L, st);
+      case 128: return launch_tc2<128, true>(L, st);
+      case 192: return launch_tc2<192, true>(L, st);
+      case 256: return launch_tc2<256, true>(L, st);
+      default: set_error("conv: epilogue statistics need BN >= 64, got %d", L.BN); return -1;
+    }
+  }
   switch (L.BN) {
-    case 16: return launch_tc2<16>(L, st);
-    case 32: return launch_tc2<32>(L, st);
-    case 64: return launch_tc2<64>(L, st);
-    case 128: return launch_tc2<128>(L, st);
-    case 192: return launch_tc2<192>(L, st);
-    case 256: return launch_tc2<256>(L, st);
+    case 16: return launch_tc2<16, false>(L, st);
+    case 32: return launch_tc2<32, false>(L, st);
+    case 64: return launch_tc2<64, false>(L, st);
+    case 128: return launch_tc2<128, false>(L, st);
+    case 192: return launch_tc2<192, false>(L, st);
+    case 256: return launch_tc2<256, false>(L, st);
     default: set_error("conv: unsupported BN %d", L.BN); return -1;
   }
 }

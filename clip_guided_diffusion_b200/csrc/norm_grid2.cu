@@ -212,6 +212,98 @@ gn_fwd_grid2_kernel(const __half* __restrict__ x, const float* __restrict__ gamm
       });
 }
 
+// ------------------------------------------------------------------------------------------------ forward from conv-epilogue statistics
+// GN_APPLY_EPI: the conv that produced x already reduced it to per (128-pixel tile, 8-channel octet) sums (CONV flags 2,
+// conv_tc2.cu STATS), so the forward is ONE streaming trip: every CTA folds the partial sums of its image (warp g = group g, fixed
+// order, compensated fp32 -- bit-identical in every CTA, no grid barrier), then applies.  partials: [N * tpi][octs][2], tpi = HW / 128.
+template <int U>
+__global__ void __launch_bounds__(kG2Threads, 1)
+gn_apply_epi_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ emb,
+                    __half* __restrict__ y, float* __restrict__ stats, const float* __restrict__ partials, int HW, int C, int64_t ldx, int64_t ldy,
+                    int Gn, int octs, int oct0, float eps, int silu) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int n = blockIdx.x / Gn, chunk = blockIdx.x % Gn;
+  const int V = C / 8, PP = kG2Threads / V, cpg = C / 32, vpg = cpg / 8;
+  const int ppc = (HW + Gn - 1) / Gn;
+  const int p0 = min(HW, chunk * ppc), p1 = min(HW, p0 + ppc);
+  const int col = threadIdx.x % V, pl = threadIdx.x / V;
+  const bool active = pl < PP;
+  const int pend = active ? p1 : p0;
+  pdl_wait();
+  pdl_launch_dependents();
+  {
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tpi = HW / 128, cnt = tpi * vpg;  // group g: octets [oct0 + g * vpg, + vpg) of every tile of image n
+    float sa = 0.f, ca = 0.f, sb = 0.f, cb = 0.f;
+    for (int m = lane; m < cnt; m += 32) {
+      const int tile = m / vpg, o = m - tile * vpg;
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(partials + (((int64_t)n * tpi + tile) * octs + oct0 + g * vpg + o) * 2));
+      float t = sa + v.x;
+      ca += fabsf(sa) >= fabsf(v.x) ? (sa - t) + v.x : (v.x - t) + sa;
+      sa = t;
+      t = sb + v.y;
+      cb += fabsf(sb) >= fabsf(v.y) ? (sb - t) + v.y : (v.y - t) + sb;
+      sb = t;
+    }
+    float da = sa + ca, db = sb + cb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      da += __shfl_xor_sync(0xffffffffu, da, o);
+      db += __shfl_xor_sync(0xffffffffu, db, o);
+    }
+    if (lane == 0) {
+      const float inv_m = 1.f / ((float)cpg * (float)HW);
+      const float mu = da * inv_m;
+      const float var = fmaxf(fmaf(-mu, mu, db * inv_m), 0.f);
+      const float rs = 1.f / sqrtf(var + eps);
+      s_mean[g] = mu;
+      s_rstd[g] = rs;
+      if (chunk == 0) {
+        stats[((int64_t)n * 32 + g) * 2 + 0] = mu;
+        stats[((int64_t)n * 32 + g) * 2 + 1] = rs;
+      }
+    }
+  }
+  __syncthreads();
+  float2 A[4], Bc[4];
+  {
+    const int g = min(col / vpg, 31);
+    const float mu = s_mean[g], rs = s_rstd[g];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a[2], b[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = col * 8 + 2 * j + h;
+        const float ga = gamma[c], be = beta[c];
+        const float sc1 = emb ? 1.f + emb[(int64_t)n * 2 * C + c] : 1.f, sh = emb ? emb[(int64_t)n * 2 * C + C + c] : 0.f;
+        a[h] = rs * ga * sc1;
+        b[h] = (be - mu * rs * ga) * sc1 + sh;
+      }
+      A[j] = make_float2(a[0], a[1]);
+      Bc[j] = make_float2(b[0], b[1]);
+    }
+  }
+  const __half* xb = x + (int64_t)n * HW * ldx + col * 8;
+  __half* yb = y + (int64_t)n * HW * ldy + col * 8;
+  uint4 v[U];
+  g2_sweep<U>(
+      p0, pend, pl, PP, [&](int p, int u) { v[u] = g2_ld(xb + (int64_t)p * ldx); },
+      [&](int p, int u) {
+        float2 f[4];
+        g2_unpack(v[u], f);
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 t = fma2(f[j], A[j], Bc[j]);
+          if (silu) t = silu2(t);
+          ow[j] = g2_f2h(t);
+        }
+        *reinterpret_cast<uint4*>(yb + (int64_t)p * ldy) = o;
+      });
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 template <int U>
 __global__ void __launch_bounds__(kG2Threads, 1)
@@ -317,6 +409,17 @@ gn_bwd_grid2_kernel(const __half* __restrict__ dy, const __half* __restrict__ x,
 constexpr int kG2FwdU = 4, kG2BwdU = 2;
 
 bool gn_grid2_supports(int64_t C) { return C % 256 == 0 && C <= 2048; }
+
+int launch_gn_apply_epi(const CgdOp& op, cudaStream_t st) {
+  const int64_t N = op.i[0], HW = op.i[1], C = op.i[2], ldx = op.i[3], ldy = op.i[4], Gn = op.i[5], octs = op.i[6], oct0 = op.i[7];
+  CGD_CHECK_ARG(N > 0 && HW > 0 && HW % 128 == 0 && gn_grid2_supports(C) && Gn >= 1 && ldx % 8 == 0 && ldy % 8 == 0 && octs >= oct0 + C / 8 && oct0 >= 0,
+                "gn_apply_epi: bad dims (HW %% 128, C %% 256, octets)");
+  CGD_CHECK_ARG(op.p[0] && op.p[1] && op.p[2] && op.p[4] && op.p[5] && op.p[6], "gn_apply_epi: null pointer");
+  CGD_CUDA(launch_pdl(gn_apply_epi_kernel<kG2FwdU>, dim3((unsigned)(N * Gn)), dim3(kG2Threads), 0, st, (const __half*)op.p[0], (const float*)op.p[1],
+                      (const float*)op.p[2], (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (const float*)op.p[6], (int)HW, (int)C, ldx, ldy,
+                      (int)Gn, (int)octs, (int)oct0, op.f[0], (int)(op.flags & 1)));
+  return 0;
+}
 
 int launch_gn_fwd_grid2(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], HW = op.i[1], C = op.i[2], ldx = op.i[3], ldy = op.i[4], Gn = op.i[5];

@@ -243,6 +243,10 @@ class Plan:
         self.tc_attention = os.environ.get("CGD_TC_ATTENTION", "0") == "1"
         # split-K reduced inside a thread-block cluster through DSMEM (csrc/conv_tc3.cu) instead of partials + a reduce launch
         self.cluster_splitk = os.environ.get("CGD_CONV_CLUSTER", "1") == "1"
+        # GroupNorm forward from statistics reduced in the producing conv's epilogue (CONV flags 2 + GN_APPLY_EPI): one streaming trip
+        # instead of two.  Interpreter-verified, NOT yet run on the device: opt-in until it is (DESIGN.md "Next")
+        self.gn_epi_stats = os.environ.get("CGD_GN_EPI_STATS", "0") == "1"
+        self._epi_stats = {}  # output Act key -> (partials Buf, octets per tile row)
         self.arena: Optional[th.Tensor] = None
         self.handle = None
         self._c_ops = None
@@ -319,7 +323,7 @@ class Plan:
 
     # ------------------------------------------------------------------ conv / GEMM
     def _emit_conv(self, x_ptr, x_strides, NB, H, W, Cin, wbuf, npad, Cout, taps, bias, res_ptr, res_strides, out_ptr, out_strides,
-                   out_f32=False, out_sc=1, tag="", b_ptr=None, b_batch=(0, 0), ldb=0):
+                   out_f32=False, out_sc=1, tag="", b_ptr=None, b_batch=(0, 0), ldb=0, want_stats=False):
         """b_ptr / b_batch / ldb: batched-GEMM mode (attention): the B operand is a strided activation matrix selected by the
         tile's (h, n) instead of a packed weight."""
         m_tiles = conv_tile_count(NB, H, W)
@@ -340,8 +344,29 @@ class Plan:
             skbar = self.new(2 * ((m_tiles + 1) // 2 * 2) * (npad // bn), "u32", "splitk_bar")
         i = [NB, H, W, Cin, Cout, npad, taps, *x_strides, *out_strides, *(res_strides or (0, 0, 0)), bn, splits, self.conv_impl, out_sc,
              b_batch[0], b_batch[1], ldb, cluster]
-        self.emit("CONV", flags=1 if out_f32 else 0, i=i,
-                  p=[x_ptr, b_ptr if b_ptr is not None else self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws), self._bp(skbar)], tag=tag)
+        # epilogue statistics for a following GroupNorm: pair kernel with the TMA-store epilogue, full 128-pixel tiles inside an image
+        stats = None
+        tw = 1
+        while tw < W and tw < 128:
+            tw <<= 1
+        t_h = min(128 // tw, 1 << max(0, (H - 1).bit_length()))
+        if (want_stats and self.gn_epi_stats and self.conv_impl in (0, 3) and splits == 1 and not cluster and not out_f32 and out_sc == 1 and b_ptr is None
+                and bn >= 64 and Cout % 64 == 0 and m_tiles >= 2 and m_tiles % 2 == 0 and tw * t_h == 128 and W % tw == 0 and H % t_h == 0
+                and (tw == W or t_h == 1)):
+            stats = self.new(m_tiles * (npad // 8) * 2, "f", "epi_stats")
+        self.emit("CONV", flags=(1 if out_f32 else 0) | (2 if stats is not None else 0), i=i,
+                  p=[x_ptr, b_ptr if b_ptr is not None else self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws), self._bp(skbar)]
+                  + ([self._bp(stats)] if stats is not None else []), tag=tag)
+        return stats
+
+    def _gn_would_use_epi(self, y: Act) -> bool:
+        """would a GroupNorm over y take the statistics of the producing conv's epilogue?  (the large activations of the persistent
+        grid kernels; the small ones keep the one-launch cluster kernel)"""
+        if not self.gn_epi_stats or y.HW % 128 or y.C % 256:
+            return False
+        if self.fused_gn and gn_fused_cluster(y.N, y.HW, y.C, 16):
+            return False
+        return bool(self.grid_gn and gn_grid_ctas(y.N, y.HW, y.C))
 
     @staticmethod
     def _strides(a: Act):
@@ -352,8 +377,11 @@ class Plan:
         assert x.C == w.cin_pad, (x.C, w.cin_pad, name)
         y = out if out is not None else self.act(x.N, x.H, x.W, w.cout, name)
         assert y.C == w.cout and (y.N, y.H, y.W) == (x.N, x.H, x.W)
-        self._emit_conv(self._ap(x), self._strides(x), x.N, x.H, x.W, x.C, w.fwd, w.fwd_npad, w.cout, w.taps, w.bias,
-                        self._ap(res), self._strides(res) if res is not None else None, self._ap(y), self._strides(y), tag=name)
+        stats = self._emit_conv(self._ap(x), self._strides(x), x.N, x.H, x.W, x.C, w.fwd, w.fwd_npad, w.cout, w.taps, w.bias,
+                                self._ap(res), self._strides(res) if res is not None else None, self._ap(y), self._strides(y), tag=name,
+                                want_stats=self._gn_would_use_epi(y))
+        if stats is not None:
+            self._epi_stats[y.key()] = (stats, w.fwd_npad // 8)
 
         def bwd():
             dy = self.grad_of(y)
@@ -382,7 +410,11 @@ class Plan:
         embp = self._bp(emb[0], emb[1]) if emb is not None else None
         cs_f = gn_fused_cluster(N, HW, C, 16) if self.fused_gn else 0
         gn_g = gn_grid_ctas(N, HW, C) if self.grid_gn else 0
-        if cs_f:
+        epi = self._epi_stats.get(x.key()) if self.gn_epi_stats else None
+        if epi is not None and not cs_f and gn_g and HW % 128 == 0 and C % 256 == 0:
+            self.emit("GN_APPLY_EPI", flags=1 if silu else 0, i=[N, HW, C, x.ld, y.ld, gn_g, epi[1], 0], f=[eps],
+                      p=[self._ap(x), self._bp(gamma), self._bp(beta), embp, self._ap(y), self._bp(stats), self._bp(epi[0])], tag=name)
+        elif cs_f:
             self.emit("GN_FWD_FUSED", flags=1 if silu else 0, i=[N, HW, C, x.ld, y.ld, cs_f], f=[eps],
                       p=[self._ap(x), self._bp(gamma), self._bp(beta), embp, self._ap(y), self._bp(stats)], tag=name)
         elif gn_g:

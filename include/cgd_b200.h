@@ -65,7 +65,8 @@ enum {
    *   the kernel reduces its own split-K partials (no second launch)
    *   i23 = 1: split-K inside a thread-block cluster of 2 * splits CTAs, reduced through distributed shared memory (one launch, no
    *   workspace; splits in 2..8, BN >= 64, BN / splits a multiple of 16, fp16 contiguous output, Cout % 8 == 0)
-   *   flags: 1 = out is fp32 */
+   *   flags: 1 = out is fp32 ; 2 = epilogue statistics for CGD_OP_GN_APPLY_EPI into p7 (pair kernel with the TMA-store epilogue, full
+   *   128-pixel tiles inside one image) */
   CGD_OP_CONV = 1,
   /* GroupNorm(32) statistics: per (image, chunk, group) partial sum / sum of squares; the last block per image
    * folds the chunks (fixed order, fp64) into (mean, rstd).  [3P] GroupNorm32.
@@ -223,6 +224,12 @@ enum {
   CGD_OP_ATTNPOOL_EMBED_FWD = 47,
   /* dx[n,t,:] (=|+=) dy[n,1+t,:] + dy[n,0,:] / HW : p0 dy(h [n,HW+1,C]) p1 dx(h, row stride i3) ; i0 n i1 HW i2 C i3 ld_dx ; flags 2 = accumulate */
   CGD_OP_ATTNPOOL_EMBED_BWD = 48,
+  /* GroupNorm(32) (+scale-shift, +SiLU) forward in ONE streaming trip from statistics the producing conv already reduced (CONV flags 2:
+   * p7 = partials(f [m_tiles][Npad/8][2]): sum / sum of squares of the fp16 output per 128-pixel tile and 8-channel octet).
+   * p0 x(h) p1 gamma p2 beta p3 emb|0 p4 y(h) p5 stats(f [N,32,2] = mean, rstd, for the backward) p6 partials
+   * i0 N i1 HW (% 128 == 0) i2 C (% 256 == 0) i3 ldx i4 ldy i5 CTAs per image i6 octets per tile row of the partials (producer Npad / 8)
+   * i7 first octet of x's channels in the producer's output ; f0 eps ; flags 1 = SiLU */
+  CGD_OP_GN_APPLY_EPI = 49,
   CGD_OP__COUNT
 };
 

@@ -8,10 +8,10 @@ from clip_guided_diffusion_b200.plan import _DT
 from tests.plan_interp import CODE, Interp
 
 # output pointer slots per op code (whole owning buffers are compared)
-OUT_PTRS = {"CONV": [4], "GN_STATS": [2], "GN_APPLY": [5], "GN_BWD_STATS": [7], "GN_BWD_APPLY": [7], "POOL2": [1], "UP2": [1], "ADD": [2],
+OUT_PTRS = {"CONV": [4, 7], "GN_STATS": [2], "GN_APPLY": [5], "GN_BWD_STATS": [7], "GN_BWD_APPLY": [7], "POOL2": [1], "UP2": [1], "ADD": [2],
             "COPY": [1], "ATTN_FWD": [3, 4], "ATTN_BWD": [6], "LINEAR_SMALL": [3], "TIMESTEP_EMB": [1], "LABEL_ADD": [0], "NCHW_TO_PM": [1],
             "PM_TO_NCHW": [1], "LN_FWD": [3, 4], "LN_BWD": [4], "QGELU_FWD": [1], "QGELU_BWD": [2], "VIT_EMBED": [0], "CUTOUTS_FWD": [2],
-            "CUTOUTS_BWD": [2], "SPHERICAL": [3, 4], "PMV_BLEND": [3, 4, 5, 6, 7], "GUIDE_GRAD": [4, 5, 6, 7, 8], "FINAL_GRAD": [2, 4], "SEED_QUANT": [1, 2], "MAG_CLAMP": [0], "ATTNPOOL_EMBED_FWD": [2], "ATTNPOOL_EMBED_BWD": [1],
+            "CUTOUTS_BWD": [2], "SPHERICAL": [3, 4], "PMV_BLEND": [3, 4, 5, 6, 7], "GUIDE_GRAD": [4, 5, 6, 7, 8], "FINAL_GRAD": [2, 4], "SEED_QUANT": [1, 2], "MAG_CLAMP": [0], "GN_APPLY_EPI": [4, 5], "ATTNPOOL_EMBED_FWD": [2], "ATTNPOOL_EMBED_BWD": [1],
             "SAMPLE_ANCESTRAL": [6], "SAMPLE_DDIM": [5], "TRANSPOSE": [1, 3, 5], "SOFTMAX_FWD": [0, 1], "SOFTMAX_BWD": [1],
             "GN_FWD_FUSED": [4, 5], "GN_BWD_FUSED": [6], "GN_FWD_GRID": [4, 5], "GN_BWD_GRID": [6],
             "RELU_FWD": [1], "RELU_BWD": [2], "MAXPOOL2_FWD": [1], "MAXPOOL2_BWD": [2], "LPIPS_TAP": [3, 4], "FILL": [0], "CUTOUTS_RR_FWD": [2], "CUTOUTS_RR_BWD": [2]}

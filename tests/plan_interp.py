@@ -77,6 +77,29 @@ class Interp:
             y = y + self.V(op.p[3], (NB, H, W, Cout), (rsn, rsh, rsw, 1)).float()
         out = self.V(op.p[4], (NB, H, W, Cout), (osn, osh, osw, osc))
         out.copy_(y)
+        if op.flags & 2:  # epilogue statistics: per (128 consecutive pixels, 8-channel octet) sum / sum of squares of the STORED values
+            assert (NB * H * W) % 128 == 0 and Cout % 8 == 0
+            stored = out.float().reshape(NB * H * W // 128, 128, Cout // 8, 8)
+            part = self.V(op.p[7], (NB * H * W // 128, Npad // 8, 2), (Npad // 8 * 2, 2, 1))
+            part[:, :Cout // 8, 0] = stored.sum(dim=(1, 3))
+            part[:, :Cout // 8, 1] = stored.square().sum(dim=(1, 3))
+
+    def op_GN_APPLY_EPI(self, op):
+        N, HW, C, ldx, ldy, _, octs, oct0 = op.i[:8]
+        tpi, cpg = HW // 128, C // 32
+        part = self.V(op.p[6], (N, tpi, octs, 2), (tpi * octs * 2, octs * 2, 2, 1))[:, :, oct0:oct0 + C // 8].double()
+        tot = part.sum(dim=1).view(N, 32, cpg // 8, 2).sum(dim=2)  # [N, 32, 2]
+        mean = tot[..., 0] / (cpg * HW)
+        var = (tot[..., 1] / (cpg * HW) - mean * mean).clamp_min(0)
+        st = self.V(op.p[5], (N, 32, 2), (64, 2, 1))
+        st[:, :, 0] = mean.float()
+        st[:, :, 1] = (1.0 / th.sqrt(var.float() + op.f[0]))
+        A, Bc, _, _, _ = self._gn_affine(op, op.p[5], op.p[1], op.p[2], op.p[3], N, C)
+        x = self.V(op.p[0], (N, HW, C), (HW * ldx, ldx, 1))
+        v = x.float() * A[:, None] + Bc[:, None]
+        if op.flags & 1:
+            v = F.silu(v)
+        self.V(op.p[4], (N, HW, C), (HW * ldy, ldy, 1)).copy_(v)
 
     def _gn_affine(self, op, stats_ptr, gamma_ptr, beta_ptr, emb_ptr, N, C):
         stats = self.V(stats_ptr, (N, 32, 2), (64, 2, 1))
