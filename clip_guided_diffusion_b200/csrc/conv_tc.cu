@@ -385,6 +385,7 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   if (p.splits > 1 && !want_cluster) CGD_CHECK_ARG(p.ws != nullptr, "conv: split-K needs a workspace");
   L.cluster_split = 0;
   p.sk_bar = reinterpret_cast<unsigned int*>(op.p[6]);
+  p.epi_stats = nullptr;  // set below for the pair kernel when CONV flags 2 asks for epilogue statistics
   L.BN = (int)BN;
   L.impl = (int)op.i[18];
   L.A = reinterpret_cast<const __half*>(op.p[0]);
