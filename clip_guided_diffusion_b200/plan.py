@@ -750,19 +750,8 @@ class Plan:
         return a
 
     # ------------------------------------------------------------------ finalize / run
-    def finalize(self, device):
-        """Allocate the arena on `device`, upload constants, lower ops.  On a CUDA device this also creates the
-        native plan (TMA descriptors); on CPU the arena exists only so tests can interpret the op list."""
-        device = th.device(device)
-        nbytes = _round_up(self._size, 256) + 256
-        self.arena = th.zeros(nbytes, dtype=th.uint8, device=device)
-        for b, t in self._consts:
-            self.arena[b.off:b.off + b.nbytes].copy_(t.view(-1).view(th.uint8))
-        self._consts_done = True
-        if device.type != "cuda":
-            return self
-        lib = _lib.load()
-        base = self.arena.data_ptr()
+    def lower(self, base: int):
+        """the op list as the C structs of include/cgd_b200.h, pointers = base + arena offsets"""
         assert base % 256 == 0
         arr = (CgdOp * len(self.ops))()
         for k, op in enumerate(self.ops):
@@ -775,6 +764,21 @@ class Plan:
                 c.f[j] = float(v)
             for j, v in enumerate(op.p):
                 c.p[j] = None if v is None else base + v[0].off + v[1] * _DT[v[0].dt][0]
+        return arr
+
+    def finalize(self, device):
+        """Allocate the arena on `device`, upload constants, lower ops.  On a CUDA device this also creates the
+        native plan (TMA descriptors); on CPU the arena exists only so tests can interpret the op list."""
+        device = th.device(device)
+        nbytes = _round_up(self._size, 256) + 256
+        self.arena = th.zeros(nbytes, dtype=th.uint8, device=device)
+        for b, t in self._consts:
+            self.arena[b.off:b.off + b.nbytes].copy_(t.view(-1).view(th.uint8))
+        self._consts_done = True
+        if device.type != "cuda":
+            return self
+        lib = _lib.load()
+        arr = self.lower(self.arena.data_ptr())
         h = ctypes.c_void_p()
         _lib.check(lib.cgd_plan_create(arr, len(self.ops), ctypes.byref(h)), "cgd_plan_create")
         self.handle, self._c_ops = h, arr

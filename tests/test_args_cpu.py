@@ -1,0 +1,66 @@
+"""CPU: every op a plan emits passes the C side's ARGUMENT validation (the launch_* / conv_tc_prepare checks of csrc/) -- without a GPU.
+Each op is lowered to the C struct with fake, aligned, non-null pointers and handed to `cgd_run_op`: with no device the call must fail
+with a CUDA error (rc > 0: the launch itself), never with rc = -1 (an argument rejected).  Convs stop at the tensor-map encoder
+("cuTensorMapEncodeTiled unavailable") after their dimension / alignment / stride checks.  This is how op layouts that have not run on
+a device yet (ModifiedResNet tower, epilogue-statistics GroupNorm) are checked against the kernels' contracts."""
+import ctypes
+
+import pytest
+import torch as th
+
+from clip_guided_diffusion_b200 import _lib
+from clip_guided_diffusion_b200 import plan as P
+from tests.plan_interp import CODE
+
+pytestmark = pytest.mark.skipif(th.cuda.is_available(), reason="needs a box WITHOUT a GPU: launches must fail, only the checks run")
+
+
+def _check_plan(plan, what):
+    lib = _lib.load()
+    base = 1 << 40  # fake device address, 256-byte aligned; nothing is dereferenced: no kernel can launch here
+    arr = plan.lower(base)
+    bad = []
+    for k, op in enumerate(plan.ops):
+        rc = lib.cgd_run_op(ctypes.byref(arr[k]), None)
+        msg = lib.cgd_last_error().decode("utf-8", "replace")
+        if rc > 0 or (rc == -1 and CODE[op.code] == "CONV" and "cuTensorMapEncodeTiled unavailable" in msg):
+            continue
+        bad.append((k, CODE[op.code], op.tag, rc, msg))
+    assert not bad, f"{what}: {len(bad)} op(s) rejected by the C-side argument checks, first: {bad[:3]}"
+    return len(plan.ops)
+
+
+def test_guided_step_ops_pass_c_side_checks():
+    from tests.step_parity import build_tiny
+    for kw in (dict(B=2, cutn=3, image=32), dict(B=1, cutn=4, image=32, use_magnitude=True, sat_scale=30.0, cutn_variants=(2, 4)),
+               dict(B=2, cutn=2, image=32, init_scale=1000.0), dict(B=1, cutn=3, image=64, cutout_resize="lanczos3"),
+               dict(B=2, cutn=3, image=32, tower="rn"), dict(B=1, cutn=2, image=32, hw=(32, 64))):
+        ctx = build_tiny("cpu", **kw)
+        assert _check_plan(ctx["eng"].plan, str(kw)) > 100
+
+
+def test_resnet_tower_ops_pass_c_side_checks():
+    from clip_guided_diffusion_b200 import rn as prn
+    from clip_guided_diffusion_b200 import weights as pw
+    cfg = prn.RNConfig(layers=(1, 2, 1, 1), output_dim=128, input_resolution=224, width=64)  # real spatial sizes: 112 .. 7, 50 tokens
+    sd = {k: th.zeros(v) for k, v in pw.rn_param_shapes(cfg).items()}
+    for k in sd:
+        if k.endswith("running_var"):
+            sd[k] += 1
+    tower = prn.RNB200(cfg, sd, n_images=4, device="cpu")
+    assert _check_plan(tower.plan, "RN tower") > 60
+
+
+def test_epilogue_statistics_ops_pass_c_side_checks():
+    for N, H, W, Cin, C in ((1, 128, 128, 256, 256), (2, 64, 64, 128, 512), (1, 256, 256, 256, 256)):
+        plan = P.Plan()
+        plan.gn_epi_stats, plan.fused_gn, plan.grid_gn = True, False, True
+        cw = P.pack_conv(plan, th.zeros(C, Cin, 3, 3), th.zeros(C), need_bwd=True, name="w")
+        x = plan.act(N, H, W, Cin, "x")
+        h = plan.conv(x, cw, res=plan.act(N, H, W, C, "res"), name="c")
+        y = plan.group_norm(h, plan.const(th.ones(C), "f", "g"), plan.const(th.zeros(C), "f", "b"), emb=(plan.const(th.zeros(N * 2 * C), "f", "e"), 0),
+                            silu=True, name="gn")
+        plan._grads[y.key()] = plan.act(N, H, W, C, "dy")
+        plan.backward()
+        assert P.OP["GN_APPLY_EPI"] in [o.code for o in plan.ops] and plan.ops[0].flags & 2
+        _check_plan(plan, f"epi stats {N}x{H}x{W}")
