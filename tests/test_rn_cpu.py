@@ -58,3 +58,22 @@ def test_rn_tower_matches_oracle(n):
     (g_ref,) = th.autograd.grad((ref * d_emb).sum(), xi)
     cos = float(th.nn.functional.cosine_similarity(d_img.flatten(), g_ref.flatten(), dim=0))
     assert cos > 0.995 and float((d_img - g_ref).norm() / g_ref.norm()) < 5e-2, cos
+
+
+def test_oracle_attention_pool_equals_torch_mha():
+    """the oracle's AttentionPool2d restatement against the call the published model makes (F.multi_head_attention_forward with separate
+    projection weights, query = the mean token)"""
+    import torch.nn.functional as F
+    th.manual_seed(0)
+    ap = orn.AttentionPool2d(7, 2048, 32, 1024)
+    f = th.randn(2, 2048, 7, 7)
+    x = f.flatten(start_dim=2).permute(2, 0, 1)
+    x = th.cat([x.mean(dim=0, keepdim=True), x], dim=0) + ap.positional_embedding[:, None, :]
+    with th.no_grad():
+        ref, _ = F.multi_head_attention_forward(
+            query=x[:1], key=x, value=x, embed_dim_to_check=x.shape[-1], num_heads=ap.num_heads, q_proj_weight=ap.q_proj.weight,
+            k_proj_weight=ap.k_proj.weight, v_proj_weight=ap.v_proj.weight, in_proj_weight=None,
+            in_proj_bias=th.cat([ap.q_proj.bias, ap.k_proj.bias, ap.v_proj.bias]), bias_k=None, bias_v=None, add_zero_attn=False, dropout_p=0,
+            out_proj_weight=ap.c_proj.weight, out_proj_bias=ap.c_proj.bias, use_separate_proj_weight=True, training=False, need_weights=False)
+        got = ap(f)
+    assert th.allclose(got, ref.squeeze(0), atol=1e-5)
