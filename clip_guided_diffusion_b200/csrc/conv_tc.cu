@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "conv_splitk.cuh"
+#include "conv_sched.cuh"
 #include "conv_tc.cuh"
 #include "pdl.cuh"
 #include "tc_ptx.cuh"
@@ -450,6 +451,31 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   // the image are clipped by the TMA unit; needs fp16 channel-contiguous output and whole 64-channel chunks
   p.epi_tma = (!L.cluster_split && conv_use_pair_kernel(L) && !p.out_f32 && p.out_sc == 1 && p.splits == 1 && BN >= 64 && Cout % 64 == 0) ? 1 : 0;
   if (const char* e = getenv("CGD_CONV_EPI_TMA")) if (e[0] == '0') p.epi_tma = 0;
+  // split last wave (opt-in: CGD_CONV_TAIL=1, device run pending): pair kernel with the TMA-store epilogue, no split-K, tail halves fit a wave
+  L.tail_units = 0;
+  p.tail_full = 0;
+  L.tmB4 = L.tmB2;
+  {
+    static int tail_on = -1;
+    if (tail_on < 0) {
+      const char* e = getenv("CGD_CONV_TAIL");
+      tail_on = (e && e[0] == '1') ? 1 : 0;
+    }
+    const int total = ((L.m_tiles + 1) / 2) * L.n_tiles;
+    if (tail_on && p.epi_tma && !L.cluster_split && !p.b_batched && (BN == 128 || BN == 256) && sched_tail_pays(total, 74)) {
+      const cuuint64_t K = (cuuint64_t)(taps * Cin);
+      const cuuint64_t row_bytes = (cuuint64_t)ldb * 2 * (cuuint64_t)Npad;
+      cuuint64_t dims4[4] = {K, (cuuint64_t)Npad, 1, 1};
+      cuuint64_t strides4[3] = {(cuuint64_t)ldb * 2, row_bytes, row_bytes};
+      cuuint32_t box4[4] = {64, (cuuint32_t)(BN / 4), 1, 1};
+      cuuint32_t estr4[4] = {1, 1, 1, 1};
+      CUresult r = enc(&L.tmB4, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, op.p[1], dims4, strides4, box4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W quarter) failed with %d", (int)r);
+      p.tail_full = sched_full_tiles(total, 74);
+      L.tail_units = sched_total_units(total, 74);
+    }
+  }
   // flags 2: the epilogue also reduces its output tile to per-octet sums for the GroupNorm that follows (GN_APPLY_EPI): needs the
   // TMA-store epilogue and tiles that are full and are 128 consecutive pixels of one image
   p.epi_stats = nullptr;

@@ -29,6 +29,7 @@ struct ConvTcParams {
   const __half* res;
   void* out;
   float* ws;                         // split-K partials [splits][m_tiles*128][Npad]
+  int tail_full;                     // pair kernel, TAIL instantiation: tiles kept whole (conv_sched.cuh); the rest is split in halves
   float* epi_stats;                  // flags 2: per (128-pixel tile, 8-channel octet) sum / sum of squares of the fp16 OUTPUT, [m_tiles][Npad/8][2]
 };
 
@@ -36,6 +37,8 @@ struct ConvTcLaunch {
   CUtensorMap tmA, tmB;              // A: 4-D pixel box; B: [BN x 64] weight slice (single-CTA kernel)
   CUtensorMap tmB2;                  // B: [BN/2 x 64] half slice per CTA of a pair (cta_group::2 kernel)
   CUtensorMap tmOut, tmRes;          // pair kernel epilogue: [64 ch x TW x TH x TN] boxes of the output / residual
+  CUtensorMap tmB4;                  // B: [BN/4 x 64] quarter slice per CTA (half tiles of the split last wave)
+  int tail_units;                    // > 0: launch the TAIL instantiation over this many schedule units
   ConvTcParams p;
   int BN, impl, m_tiles, n_tiles;
   int cluster_split;                 // split-K inside a 2*splits-CTA cluster, reduced through DSMEM (conv_tc3.cu): no workspace, one launch

@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "conv_sched.cuh"
 #include "conv_splitk.cuh"
 #include "conv_tc.cuh"
 #include "pdl.cuh"
@@ -64,10 +65,13 @@ __device__ __forceinline__ Tile2 decode_tile(const ConvTcParams& p, int t, int n
 
 // STATS: the epilogue additionally reduces every output chunk to per-octet sums for the GroupNorm that follows (CONV flags 2); a
 // separate instantiation so that the default kernel's code and shared-memory layout are untouched
-template <int BN, bool STATS = false>
+// TAIL: the tiles of the last partial wave are cut in two BN/2-wide halves (conv_sched.cuh); `total_tiles` then counts schedule units
+// (p.tail_full whole tiles first, then the halves) and tmB4 loads a quarter of the weight tile per CTA.  Also a separate instantiation.
+template <int BN, bool STATS = false, bool TAIL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
-                const __grid_constant__ CUtensorMap tmRes, const ConvTcParams p, int n_tiles, int pair_tiles, int total_tiles) {
+                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmB4, const ConvTcParams p, int n_tiles,
+                int pair_tiles, int total_tiles) {
   using Cfg = Tc2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -126,10 +130,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < total_tiles; t += n_clusters) {
-        const Tile2 tl = decode_tile(p, t, n_tiles, pair_tiles, rank);
+        ConvUnit cu = {t, -1};
+        if constexpr (TAIL) cu = sched_unit(t, p.tail_full);
+        const Tile2 tl = decode_tile(p, cu.tile, n_tiles, pair_tiles, rank);
         const int tw_i = tl.mt % p.tiles_w, th_i = (tl.mt / p.tiles_w) % p.tiles_h, tn_i = tl.mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
-        const int bcol = tl.n_tile * BN + (int)rank * (BN / 2);
+        int bcol = tl.n_tile * BN + (int)rank * (BN / 2);
+        if constexpr (TAIL) {
+          if (cu.half >= 0) bcol = tl.n_tile * BN + cu.half * (BN / 2) + (int)rank * (BN / 4);  // each CTA stages a quarter of the weight tile
+        }
         for (int kb = tl.kb0; kb < tl.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const int tap = kb / cblks, cb = kb - tap * cblks;
@@ -138,11 +147,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             dy = tap / 3 - 1;
             dx = tap % 3 - 1;
           }
+          bool half_unit = false;
+          if constexpr (TAIL) half_unit = cu.half >= 0;
           if (!(p.dbg & 1)) {
             tma2_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], cb * BK2, w0 + dx, h0 + dy, n0);
-            tma2_load_4d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK2, bcol, p.b_batched ? h0 : 0, p.b_batched ? n0 : 0);
+            if (half_unit) tma2_load_4d(smem_b + stage * Cfg::kBBytes, &tmB4, &full_bar[stage], kb * BK2, bcol, 0, 0);
+            else tma2_load_4d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK2, bcol, p.b_batched ? h0 : 0, p.b_batched ? n0 : 0);
           }
-          if (leader) mbar_expect_tx(&full_bar[stage], (p.dbg & 1) ? 0u : 2 * Cfg::kStageBytes);
+          const uint32_t tx_bytes = half_unit ? 2u * (Cfg::kABytes + Cfg::kBBytes / 2) : 2u * Cfg::kStageBytes;
+          if (leader) mbar_expect_tx(&full_bar[stage], (p.dbg & 1) ? 0u : tx_bytes);
           else mbar_arrive_remote(&full_bar[stage], 0);
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -154,11 +167,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the leader CTA
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16_mn(256, BN);
+      constexpr uint32_t idesc_full = make_idesc_f16_mn(256, BN);
+      constexpr uint32_t idesc_half = make_idesc_f16_mn(256, BN >= 32 ? BN / 2 : 16);
       int stage = 0, iter = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
-        const Tile2 tl = decode_tile(p, t, n_tiles, pair_tiles, rank);
+        ConvUnit cu = {t, -1};
+        if constexpr (TAIL) cu = sched_unit(t, p.tail_full);
+        uint32_t idesc = idesc_full;
+        if constexpr (TAIL) idesc = cu.half >= 0 ? idesc_half : idesc_full;
+        const Tile2 tl = decode_tile(p, cu.tile, n_tiles, pair_tiles, rank);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogues of both CTAs have drained this accumulator
@@ -204,13 +222,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool issuer = threadIdx.x == 64;  // warp 2, lane 0: issues every TMA store / residual load of this CTA
         const bool has_res = p.res != nullptr;
         uint8_t* st_out = smem_epi;  // residual chunks are TMA-loaded INTO the staging tile and updated in place
-        auto tile_origin = [&](int tt, int& w0, int& h0, int& n0, int& ncol0) {
-          const Tile2 tl = decode_tile(p, tt, n_tiles, pair_tiles, rank);
+        auto tile_origin = [&](int tt, int& w0, int& h0, int& n0, int& ncol0) {  // tt: tile index, or schedule unit with TAIL
+          ConvUnit cu = {tt, -1};
+          if constexpr (TAIL) cu = sched_unit(tt, p.tail_full);
+          const Tile2 tl = decode_tile(p, cu.tile, n_tiles, pair_tiles, rank);
           const int tw_i = tl.mt % p.tiles_w, th_i = (tl.mt / p.tiles_w) % p.tiles_h, tn_i = tl.mt / (p.tiles_w * p.tiles_h);
           w0 = tw_i * p.TW;
           h0 = th_i * p.TH;
           n0 = tn_i * p.TN;
-          ncol0 = tl.n_tile * BN;
+          ncol0 = tl.n_tile * BN + (cu.half > 0 ? BN / 2 : 0);
+        };
+        auto unit_chunks = [&](int tt) {  // 64-channel chunks of unit tt
+          if constexpr (TAIL) return sched_unit_chunks(sched_unit(tt, p.tail_full).half, BN);
+          else return kChunks;
         };
         auto issue_res = [&](int tt, int c, int buf) {  // issuer only
           int w0, h0, n0, ncol0;
@@ -222,9 +246,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           int tt = cluster_id, c = 0;
           for (int k = 0; k < 2 && tt < total_tiles; ++k) {
             issue_res(tt, c, k);
-            if (++c == kChunks) {
-              c = 0;
-              tt += n_clusters;
+            if constexpr (TAIL) {
+              sched_next_chunk(tt, c, p.tail_full, BN, n_clusters);
+            } else {
+              if (++c == kChunks) {
+                c = 0;
+                tt += n_clusters;
+              }
             }
           }
         }
@@ -237,8 +265,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(&tmem_full_bar[acc], (iter >> 1) & 1);
           tc_fence_after();
           const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+          const int n_chunks = unit_chunks(t);
 #pragma unroll 1
-          for (int c = 0; c < kChunks; ++c, ++g) {
+          for (int c = 0; c < n_chunks; ++c, ++g) {
             const int buf = (int)(g & 1u);
             const int col = ncol0 + c * 64;
             uint32_t v[64];
@@ -247,7 +276,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc_ld_32x32(taddr_row + c * 64 + 32, v + 32);
             if (has_res) mbar_wait(&res_full_bar[buf], (g >> 1) & 1u);
             tc_ld_wait();
-            if (c == kChunks - 1) {  // accumulator fully read: hand it back to the MMA thread before the stores
+            if (c == n_chunks - 1) {  // accumulator fully read: hand it back to the MMA thread before the stores
               tc_fence_before();
               mbar_arrive_remote(&tmem_empty_bar[acc], 0);
             }
@@ -313,7 +342,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (STATS && r < 16) {  // thread (octet j = r / 2, kind = r % 2): fixed-order sum over the four warps
               const float* src = stat_red + (buf * 4 * 8) * 2 + r;
               const float v = (src[0] + src[16]) + (src[32] + src[48]);
-              const Tile2 tl2 = decode_tile(p, t, n_tiles, pair_tiles, rank);
+              ConvUnit cu2 = {t, -1};
+              if constexpr (TAIL) cu2 = sched_unit(t, p.tail_full);
+              const Tile2 tl2 = decode_tile(p, cu2.tile, n_tiles, pair_tiles, rank);
               p.epi_stats[((size_t)tl2.mt * (p.Npad / 8) + (size_t)(col / 8 + (r >> 1))) * 2 + (r & 1)] = v;
             }
             if (issuer) {
@@ -321,10 +352,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               bulk_commit_group();
               if (has_res) {  // once this store has read tile `buf`, the residual of chunk g + 2 may land in it
                 bulk_wait_group_read<0>();
-                int tt = t, c2 = c + 2;
-                while (c2 >= kChunks) {
-                  c2 -= kChunks;
-                  tt += n_clusters;
+                int tt = t, c2 = c;
+                if constexpr (TAIL) {
+                  sched_next_chunk(tt, c2, p.tail_full, BN, n_clusters);
+                  if (tt < total_tiles) sched_next_chunk(tt, c2, p.tail_full, BN, n_clusters);
+                } else {
+                  c2 += 2;
+                  while (c2 >= kChunks) {
+                    c2 -= kChunks;
+                    tt += n_clusters;
+                  }
                 }
                 if (tt < total_tiles) issue_res(tt, c2, buf);
               }
@@ -334,7 +371,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (issuer) bulk_wait_group<0>();
       }
     }
-    if (!p.epi_tma)
+    if (!TAIL && !p.epi_tma)  // (the TAIL instantiation is only launched with the TMA-store epilogue)
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
       const Tile2 tl = decode_tile(p, t, n_tiles, pair_tiles, rank);
       const int tw_i = tl.mt % p.tiles_w, th_i = (tl.mt / p.tiles_w) % p.tiles_h, tn_i = tl.mt / (p.tiles_w * p.tiles_h);
@@ -431,17 +468,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BN, bool STATS>
+template <int BN, bool STATS, bool TAIL>
 static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   using Cfg = Tc2Cfg<BN>;
   constexpr int kSmem = Cfg::kSmemBytes + (STATS ? Cfg::kStatBytes : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    CGD_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    CGD_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STATS, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
   const int pair_tiles = (L.m_tiles + 1) / 2;
-  const int total = pair_tiles * L.n_tiles * L.p.splits;
+  const int total = TAIL ? L.tail_units : pair_tiles * L.n_tiles * L.p.splits;  // schedule units
   static int dbg = -1;
   if (dbg < 0) {
     const char* e = getenv("CGD_CONV_DBG");
@@ -450,27 +487,36 @@ static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   ConvTcParams prm = L.p;
   prm.dbg = dbg;
   const int clusters = std::min(total, 74);  // 148 SMs = 74 TPC pairs
-  CGD_CUDA(launch_pdl(conv_tc2_kernel<BN, STATS>, dim3(2 * clusters), dim3(kThreads2), kSmem, st, L.tmA, L.tmB2, L.tmOut, L.tmRes, prm, L.n_tiles, pair_tiles, total));
+  CGD_CUDA(launch_pdl(conv_tc2_kernel<BN, STATS, TAIL>, dim3(2 * clusters), dim3(kThreads2), kSmem, st, L.tmA, L.tmB2, L.tmOut, L.tmRes, L.tmB4, prm,
+                      L.n_tiles, pair_tiles, total));
   return 0;
 }
 
-int conv_tc2_launch(const ConvTcLaunch& L, cudaStream_t st) {
-  if (L.p.epi_stats) {  // prepare() has checked the TMA-store epilogue (BN >= 64) and full tiles
-    switch (L.BN) {
-      case 64: return launch_tc2<64, true>(L, st);
-      case 128: return launch_tc2<128, true>(L, st);
-      case 192: return launch_tc2<192, true>(L, st);
-      case 256: return launch_tc2<256, true>(L, st);
-      default: set_error("conv: epilogue statistics need BN >= 64, got %d", L.BN); return -1;
-    }
-  }
+template <bool STATS, bool TAIL>
+static int launch_tc2_wide(const ConvTcLaunch& L, cudaStream_t st) {  // the instantiations that need the TMA-store epilogue (BN >= 64)
   switch (L.BN) {
-    case 16: return launch_tc2<16, false>(L, st);
-    case 32: return launch_tc2<32, false>(L, st);
-    case 64: return launch_tc2<64, false>(L, st);
-    case 128: return launch_tc2<128, false>(L, st);
-    case 192: return launch_tc2<192, false>(L, st);
-    case 256: return launch_tc2<256, false>(L, st);
+    case 64: if constexpr (!TAIL) return launch_tc2<64, STATS, false>(L, st); else break;
+    case 128: return launch_tc2<128, STATS, TAIL>(L, st);
+    case 192: if constexpr (!TAIL) return launch_tc2<192, STATS, false>(L, st); else break;
+    case 256: return launch_tc2<256, STATS, TAIL>(L, st);
+    default: break;
+  }
+  set_error("conv: BN %d has no %s%s instantiation", L.BN, STATS ? "epilogue-statistics " : "", TAIL ? "split-tail " : "");
+  return -1;
+}
+
+int conv_tc2_launch(const ConvTcLaunch& L, cudaStream_t st) {
+  const bool stats = L.p.epi_stats != nullptr, tail = L.tail_units > 0;  // prepare() has checked the TMA-store epilogue for both
+  if (stats && tail) return launch_tc2_wide<true, true>(L, st);
+  if (stats) return launch_tc2_wide<true, false>(L, st);
+  if (tail) return launch_tc2_wide<false, true>(L, st);
+  switch (L.BN) {
+    case 16: return launch_tc2<16, false, false>(L, st);
+    case 32: return launch_tc2<32, false, false>(L, st);
+    case 64: return launch_tc2<64, false, false>(L, st);
+    case 128: return launch_tc2<128, false, false>(L, st);
+    case 192: return launch_tc2<192, false, false>(L, st);
+    case 256: return launch_tc2<256, false, false>(L, st);
     default: set_error("conv: unsupported BN %d", L.BN); return -1;
   }
 }
