@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import torch as th
 
-from .plan import Act, Buf, Plan, pack_conv
+from .plan import Buf, Plan, pack_conv
 
 SHIFT = (-0.030, -0.088, -0.188)
 SCALE = (0.458, 0.448, 0.450)

@@ -16,7 +16,6 @@ import os
 from dataclasses import dataclass, field
 from typing import Callable, Optional
 
-import numpy as np
 import torch as th
 
 from . import _lib
