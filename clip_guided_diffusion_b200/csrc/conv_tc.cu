@@ -387,6 +387,8 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   L.cluster_split = 0;
   p.sk_bar = reinterpret_cast<unsigned int*>(op.p[6]);
   p.epi_stats = nullptr;  // set below for the pair kernel when CONV flags 2 asks for epilogue statistics
+  p.tail_full = 0;        // split last wave (CGD_CONV_TAIL): decided below
+  L.tail_units = 0;
   L.BN = (int)BN;
   L.impl = (int)op.i[18];
   L.A = reinterpret_cast<const __half*>(op.p[0]);
