@@ -27,16 +27,36 @@ from .vit import VIT_CONFIGS, vit_config_from_state_dict
 CACHE_PATH = os.path.expanduser("~/.cache/clip-guided-diffusion")  # cgd/script_util.py:18
 
 
-def parse_prompt(prompt: str):  # cgd/script_util.py:60-67
-    vals = prompt.rsplit(":", 1)
+def parse_prompt(prompt: str):
+    """"<text or url>:<weight>" -> (text, weight), weight 1 when absent; a URL keeps its scheme colon (cgd/script_util.py:60-67)"""
+    is_url = prompt.startswith(("http://", "https://"))
+    vals = prompt.rsplit(":", 2 if is_url else 1)
+    if is_url:
+        vals = [vals[0] + ":" + vals[1], *vals[2:]]
     vals = vals + ["", "1"][len(vals):]
     return vals[0], float(vals[1])
 
 
+def alphanumeric_filter(s: str) -> str:  # cgd/script_util.py:81-84: drop everything but word characters and blanks, blanks -> "_"
+    import re
+    return re.sub(r"[^\w\s]", "", s).replace(" ", "_")
+
+
+def clean_and_combine_prompts(base_path, txts, batch_idx, max_length=255) -> str:  # cgd/script_util.py:87-90
+    return os.path.join(base_path, "_".join(alphanumeric_filter(t) for t in txts)[:max_length], f"{batch_idx:02}")
+
+
+# checkpoint file names of data/diffusion_model_flags.py (DIFFUSION_LOOKUP[cond|uncond][image_size]["filename"])
+DIFFUSION_FILENAMES = {
+    (True, 64): "64x64_diffusion.pt", (True, 128): "128x128_diffusion.pt", (True, 256): "256x256_diffusion.pt",
+    (True, 512): "512x512_diffusion.pt", (False, 256): "256x256_diffusion_uncond.pt",
+    (False, 512): "512x512_diffusion_uncond_finetune_008100.pt",
+}
+
+
 def log_image(image: th.Tensor, prefix_path, prompts, step: int, batch_idx: int) -> str:  # cgd/script_util.py:93-101
     from PIL import Image
-    txt = "_".join(prompts).replace(" ", "_")[:200] or "no_prompt"
-    dirname = Path(prefix_path) / txt / f"{batch_idx:02d}"
+    dirname = Path(clean_and_combine_prompts(str(prefix_path), prompts, batch_idx))
     dirname.mkdir(parents=True, exist_ok=True)
     arr = image.detach().float().add(1).div(2).clamp(0, 1).mul(255).round().byte().permute(1, 2, 0).cpu().numpy()
     path = str(dirname / f"{step:04d}.png")
@@ -47,8 +67,10 @@ def log_image(image: th.Tensor, prefix_path, prompts, step: int, batch_idx: int)
 
 
 def _load_unet_sd(image_size, class_cond, checkpoints_dir):
-    name = f"{image_size}x{image_size}_diffusion{'' if class_cond else '_uncond'}.pt"
-    path = os.path.join(checkpoints_dir, name)
+    if (class_cond, image_size) not in DIFFUSION_FILENAMES:
+        raise ValueError(f"no published {'class-conditional' if class_cond else 'unconditional'} checkpoint at {image_size}x{image_size} "
+                         "(data/diffusion_model_flags.py)")
+    path = os.path.join(checkpoints_dir, DIFFUSION_FILENAMES[(class_cond, image_size)])
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} not found: pass unet_state_dict=... or place the guided-diffusion checkpoint there "
                                 "(downloads are outside this framework's scope)")
@@ -133,9 +155,15 @@ def clip_guided_diffusion(
     Path(prefix_path).mkdir(parents=True, exist_ok=True)
 
     clip_sd = clip_state_dict if clip_state_dict is not None else _load_clip_sd(clip_model_name, checkpoints_dir)
-    vit_cfg = _tower_config(clip_sd) if clip_state_dict is not None else {**VIT_CONFIGS, **RN_CONFIGS}[clip_model_name]
+    towers = {**VIT_CONFIGS, **RN_CONFIGS}
+    if clip_state_dict is None and clip_model_name not in towers:
+        raise NotImplementedError(f"CLIP tower {clip_model_name!r} is not supported (supported: {sorted(towers)}; RN50x4 / x16 / x64 have "
+                                  "widths that are not multiples of the 64-channel K-slice)")
+    vit_cfg = _tower_config(clip_sd) if clip_state_dict is not None else towers[clip_model_name]
     if target_embeds is None:
         target_embeds, weights = _encode_text(prompts, clip_model_name, device)
+    if weights is None:  # target_embeds= given without weights=: every prompt weighs 1 (parse_prompt's default)
+        weights = th.ones(target_embeds.shape[0])
     weights = th.as_tensor(weights, dtype=th.float32)
     if weights.sum().abs() < 1e-3:
         raise RuntimeError("The weights must not sum to 0.")

@@ -356,10 +356,10 @@ int launch_attn_fwd(const CgdOp& op, cudaStream_t st) {
   if (attn_use_small(a.T)) return launch_attn_small_fwd(op, st);
   if (attn_use_mma()) return launch_attn_mma_fwd(op, st);
   const int smem = 4 * AT * ALD * (int)sizeof(float);
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce set;
+  if (set.needed()) {
     CGD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
+    set.mark();
   }
   CGD_CUDA(launch_pdl(attn_fwd_kernel, dim3((unsigned)ceil_div(a.T, AT), a.heads, a.B), dim3(256), smem, st, a));
   CGD_LAUNCH_CHECK();
@@ -372,11 +372,11 @@ int launch_attn_bwd(const CgdOp& op, cudaStream_t st) {
   if (attn_use_small(a.T)) return launch_attn_small_bwd(op, st);
   if (attn_use_mma()) return launch_attn_mma_bwd(op, st);
   const int smem_kv = 8 * AT * ALD * (int)sizeof(float), smem_q = 6 * AT * ALD * (int)sizeof(float);
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce set;
+  if (set.needed()) {
     CGD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
     CGD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
-    set = true;
+    set.mark();
   }
   const int64_t rows = (int64_t)a.B * a.heads * a.T;
   CGD_CUDA(launch_pdl(attn_delta_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, st, a));

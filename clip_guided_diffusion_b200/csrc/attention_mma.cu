@@ -326,10 +326,10 @@ int launch_attn_mma_bwd(const CgdOp& op, cudaStream_t st) {
   AttnMmaArgs a{};
   am_args(op, a, true);
   constexpr int smem = 8 * AM_TILE * (int)sizeof(__half);  // the dK / dV half needs 8 tiles, the dQ half 6
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce set;
+  if (set.needed()) {
     CGD_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
+    set.mark();
   }
   const int64_t rows = (int64_t)a.B * a.heads * a.T;
   CGD_CUDA(launch_pdl(attn_mma_delta_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, st, a));

@@ -146,10 +146,10 @@ int launch_attn_small_bwd(const CgdOp& op, cudaStream_t st) {
   AttnSmallArgs a{};
   attn_small_args(op, a, true);
   constexpr int smem = 6 * AS_T * AS_LD * (int)sizeof(__half);
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce set;
+  if (set.needed()) {
     CGD_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
+    set.mark();
   }
   CGD_CUDA(launch_pdl(attn_small_bwd_kernel, dim3(a.heads, a.B), dim3(128), smem, st, a));
   return 0;

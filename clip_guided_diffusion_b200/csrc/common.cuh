@@ -45,6 +45,24 @@ void set_error(const char* fmt, ...);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// "done once per device": function attributes (opt-in dynamic shared memory), occupancy checks and the SM count belong to the
+// CURRENT device, and one process may drive several GPUs (one engine per device).  Not a lock: a race sets an attribute twice.
+struct DeviceOnce {
+  bool done[64] = {};
+  int value[64] = {};
+  static int cur() {
+    int d = 0;
+    return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : 0;
+  }
+  bool needed() const { return !done[cur()]; }
+  void mark(int v = 0) {
+    const int d = cur();
+    value[d] = v;
+    done[d] = true;
+  }
+  int get() const { return value[cur()]; }
+};
+
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

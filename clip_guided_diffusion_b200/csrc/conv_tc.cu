@@ -513,10 +513,10 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
 template <int BN>
 static int launch_tc(const ConvTcLaunch& L, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
     CGD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.mark();
   }
   dim3 grid(L.m_tiles, L.n_tiles, L.p.splits);
   CGD_CUDA(launch_pdl(conv_tc_kernel<BN>, grid, dim3(kThreads), Cfg::kSmemBytes, st, L.tmA, L.tmB, L.p));

@@ -472,10 +472,10 @@ template <int BN, bool STATS, bool TAIL>
 static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   using Cfg = Tc2Cfg<BN>;
   constexpr int kSmem = Cfg::kSmemBytes + (STATS ? Cfg::kStatBytes : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
     CGD_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STATS, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set = true;
+    attr_set.mark();
   }
   const int pair_tiles = (L.m_tiles + 1) / 2;
   const int total = TAIL ? L.tail_units : pair_tiles * L.n_tiles * L.p.splits;  // schedule units

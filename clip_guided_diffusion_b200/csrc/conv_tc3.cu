@@ -238,11 +238,11 @@ template <int BN>
 static int launch_tc3(const ConvTcLaunch& L, cudaStream_t st) {
   using Cfg = Tc3Cfg<BN>;
   const int S = L.p.splits;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
     CGD_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     CGD_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
+    attr_set.mark();
   }
   const int pair_tiles = (L.m_tiles + 1) / 2;
   const int tiles = pair_tiles * L.n_tiles;

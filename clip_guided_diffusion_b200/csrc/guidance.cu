@@ -357,7 +357,7 @@ int launch_pmv_blend(const CgdOp& op, cudaStream_t st) {
 __global__ void guide_grad_kernel(const float* __restrict__ xin, const float* __restrict__ x0, const float* __restrict__ gclip,
                                   const float* __restrict__ sc, __half* __restrict__ seed, float* __restrict__ dxd, float* __restrict__ loss,
                                   int B, int H, int W, int64_t ld, float tvs, float rs, float ss, float seed_scale,
-                                  float* __restrict__ seed_f32, float* __restrict__ dyn) {
+                                  float* __restrict__ seed_f32, float* __restrict__ dyn, int Bg) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float red[32];
@@ -382,7 +382,7 @@ __global__ void guide_grad_kernel(const float* __restrict__ xin, const float* __
     if (ss != 0.f) {
       const float ex = v - fminf(fmaxf(v, -1.f), 1.f);
       l_s += fabsf(ex);
-      d_xin += ss * inv_n / (float)B * (ex > 0.f ? 1.f : (ex < 0.f ? -1.f : 0.f));
+      d_xin += ss * inv_n / (float)Bg * (ex > 0.f ? 1.f : (ex < 0.f ? -1.f : 0.f));
     }
     if (gclip) d_xin += gclip[((int64_t)b * 3 + c) * HW + p];
     const float x0v = x0[((int64_t)b * 3 + c) * HW + p];
@@ -410,7 +410,7 @@ __global__ void guide_grad_kernel(const float* __restrict__ xin, const float* __
   if (threadIdx.x == 0 && loss) {
     atomicAdd(&loss[b], l_tv * inv_n * tvs);
     atomicAdd(&loss[B + b], l_r * inv_n * rs);
-    if (ss != 0.f) atomicAdd(&loss[2 * B + b], l_s * inv_n / (float)B * ss);
+    if (ss != 0.f) atomicAdd(&loss[2 * B + b], l_s * inv_n / (float)Bg * ss);
   }
 }
 // Dynamic seed scaling (flags & 1 of GUIDE_GRAD): d L / d eps = -sqrt(1/abar - 1) * d L / d pred_xstart spans many orders of
@@ -449,11 +449,14 @@ int launch_guide_grad(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(B > 0 && H > 0 && W > 0 && ld >= 3 && op.p[0] && op.p[1] && op.p[3] && op.p[4] && op.p[5], "guide_grad: bad args");
   const bool dynamic = op.flags & 1;
   CGD_CHECK_ARG(!dynamic || (op.p[7] && op.p[8]), "guide_grad: dynamic seed scaling needs p7 (fp32 seed) and p8 (max / scale)");
+  // i[4] = batch of the WHOLE job: the sat loss is a mean over every rank's images (cgd/cgd.py:215); 0 = this launch's batch
+  const int64_t Bg = op.i[4] > 0 ? op.i[4] : B;
+  CGD_CHECK_ARG(Bg >= B, "guide_grad: global batch smaller than the local one");
   int chunks = (int)std::min<int64_t>(ceil_div(3 * H * W, 256 * 4), std::max<int64_t>(1, 592 / B));
   CGD_CUDA(launch_pdl(guide_grad_kernel, dim3(chunks, (unsigned)B), dim3(256), 0, st, (const float*)op.p[0], (const float*)op.p[1], (const float*)op.p[2],
                                                               (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (float*)op.p[6], (int)B,
                                                               (int)H, (int)W, ld, op.f[0], op.f[1], op.f[2], op.f[3],
-                                                              dynamic ? (float*)op.p[7] : (float*)nullptr, dynamic ? (float*)op.p[8] : (float*)nullptr));
+                                                              dynamic ? (float*)op.p[7] : (float*)nullptr, dynamic ? (float*)op.p[8] : (float*)nullptr, (int)Bg));
   CGD_LAUNCH_CHECK();
   return 0;
 }

@@ -78,10 +78,10 @@ __global__ void linear_small_kernel(const XT* __restrict__ x, const WT* __restri
 
 template <typename XT, typename WT>
 static int ls_launch(const CgdOp& op, cudaStream_t st, dim3 grid, int smem, int M, int K, int N, int64_t ldx, int64_t ldy, int silu, int acc, int yh) {
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce set;
+  if (set.needed()) {
     CGD_CUDA(cudaFuncSetAttribute(linear_small_kernel<XT, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    set = true;
+    set.mark();
   }
   CGD_CUDA(launch_pdl(linear_small_kernel<XT, WT>, grid, dim3(256), smem, st, (const XT*)op.p[0], (const WT*)op.p[1], (const float*)op.p[2], op.p[3],
                       (const int2*)op.p[4], M, K, N, ldx, ldy, silu, acc, yh));

@@ -463,10 +463,10 @@ int launch_gn_fwd_grid(const CgdOp& op, cudaStream_t st) {
   if (int rc = gng_check("gn_fwd_grid", N, HW, C, Gn)) return rc;
   CGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[4] && op.p[5] && op.p[6] && op.p[7], "gn_fwd_grid: bad args");
   if (gng_use_direct(false, HW, C)) return launch_gn_fwd_grid2(op, st);
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce set;
+  if (set.needed()) {
     if (int rc = gng_prepare(gn_fwd_grid_kernel)) return rc;
-    set = true;
+    set.mark();
   }
   CGD_CUDA(launch_pdl(gn_fwd_grid_kernel, dim3((unsigned)(N * Gn)), dim3(kGngThreads), kGngDynSmem, st, (const __half*)op.p[0], (const float*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (float*)op.p[6], (unsigned int*)op.p[7],
@@ -481,10 +481,10 @@ int launch_gn_bwd_grid(const CgdOp& op, cudaStream_t st) {
                     op.p[8],
                 "gn_bwd_grid: bad args");
   if (gng_use_direct(true, HW, C)) return launch_gn_bwd_grid2(op, st);
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce set;
+  if (set.needed()) {
     if (int rc = gng_prepare(gn_bwd_grid_kernel)) return rc;
-    set = true;
+    set.mark();
   }
   CGD_CUDA(launch_pdl(gn_bwd_grid_kernel, dim3((unsigned)(N * Gn)), dim3(kGngThreads), kGngDynSmem, st, (const __half*)op.p[0], (const __half*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (const float*)op.p[4], (const float*)op.p[5], (__half*)op.p[6],

@@ -423,12 +423,12 @@ int launch_gn_apply_epi(const CgdOp& op, cudaStream_t st) {
 
 int launch_gn_fwd_grid2(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], HW = op.i[1], C = op.i[2], ldx = op.i[3], ldy = op.i[4], Gn = op.i[5];
-  static bool checked = false;
-  if (!checked) {
+  static DeviceOnce checked;
+  if (checked.needed()) {
     int occ = 0;
     CGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fwd_grid2_kernel<kG2FwdU>, kG2Threads, 0));
     CGD_CHECK_ARG(occ >= 1, "gn_fwd_grid2: the 1024-thread CTA does not fit an SM (occupancy %d)", occ);
-    checked = true;
+    checked.mark();
   }
   CGD_CUDA(launch_pdl(gn_fwd_grid2_kernel<kG2FwdU>, dim3((unsigned)(N * Gn)), dim3(kG2Threads), 0, st, (const __half*)op.p[0],
                       (const float*)op.p[1], (const float*)op.p[2], (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (float*)op.p[6],
@@ -438,12 +438,12 @@ int launch_gn_fwd_grid2(const CgdOp& op, cudaStream_t st) {
 
 int launch_gn_bwd_grid2(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], HW = op.i[1], C = op.i[2], ld_dy = op.i[3], ldx = op.i[4], ld_dx = op.i[5], Gn = op.i[6];
-  static bool checked = false;
-  if (!checked) {
+  static DeviceOnce checked;
+  if (checked.needed()) {
     int occ = 0;
     CGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_bwd_grid2_kernel<kG2BwdU>, kG2Threads, 0));
     CGD_CHECK_ARG(occ >= 1, "gn_bwd_grid2: the 1024-thread CTA does not fit an SM (occupancy %d)", occ);
-    checked = true;
+    checked.mark();
   }
   CGD_CUDA(launch_pdl(gn_bwd_grid2_kernel<kG2BwdU>, dim3((unsigned)(N * Gn)), dim3(kG2Threads), 0, st, (const __half*)op.p[0],
                       (const __half*)op.p[1], (const float*)op.p[2], (const float*)op.p[3], (const float*)op.p[4], (const float*)op.p[5],

@@ -224,7 +224,7 @@ class GuidedStepB200:
             if dyn:
                 self.seed_f32 = p.new(n3, "f", "seed_f32")
                 self.seed_dyn = p.new(2 * B, "f", "seed_dyn")
-            p.emit("GUIDE_GRAD", flags=1 if dyn else 0, i=[B, H, W, IN_PAD],
+            p.emit("GUIDE_GRAD", flags=1 if dyn else 0, i=[B, H, W, IN_PAD, self.global_batch],
                    f=[self.scales["tv"], self.scales["rng"], self.scales["sat"], self.seed_scale],
                    p=[(self.x_inb, 0), (self.x0, 0), (self.g_clip, 0), (self.sc, 0), (self.unet.seed, 0), (self.dx_direct, 0), (self.loss, B)]
                    + ([(self.seed_f32, 0), (self.seed_dyn, 0)] if dyn else []), tag="tv+range+sat")
@@ -256,8 +256,14 @@ class GuidedStepB200:
         self.shape = (B, 3, H, W)
         # pinned staging for the per-step host->device refresh
         self._n_stage = SC["COUNT"] * 4 + self.cutn * 3 * 4 + B * 4 + B * 8
+        # The host runs ahead of the GPU (a step is ~1 ms of host work and ~10 ms of device work, and nothing synchronises between
+        # saved frames), so the async copies of step k may still be queued when the host stages step k+1: the pinned buffers are a
+        # ring of STAGE_SLOTS slots, each guarded by the event recorded after its copies were enqueued.
         pin = self.device.type == "cuda"
-        self._stage = th.zeros(self._n_stage, dtype=th.uint8, pin_memory=pin)
+        self._stage_ring = [th.zeros(self._n_stage, dtype=th.uint8, pin_memory=pin) for _ in range(self.STAGE_SLOTS)]
+        self._stage_events = [None] * self.STAGE_SLOTS
+        self._stage_i = 0
+        self._rr_ring = None
         self._graphs = {}
         self._side_streams = [th.cuda.Stream(device=self.device) for _ in range((self.vit.parts if self.vit is not None else 1) - 1)] \
             if self.device.type == "cuda" else []
@@ -439,9 +445,27 @@ class GuidedStepB200:
                 ("upd_anc_g", "upd_anc") if mode == "ancestral" else ("upd_ddim_g", "upd_ddim")]  # "mag" lies inside (final, upd_anc_g)
         return sum(self.plan.num_launches(m[a], m[b] - m[a]) for a, b in segs)
 
+    STAGE_SLOTS = 4
+
+    def _stage_acquire(self):
+        """next slot of the pinned ring; blocks (host only) until the copies last issued from it have executed"""
+        k = self._stage_i % self.STAGE_SLOTS
+        self._stage_i += 1
+        ev = self._stage_events[k]
+        if ev is not None:
+            ev.synchronize()
+        return k
+
+    def _stage_release(self, k):
+        if self.device.type == "cuda":
+            ev = self._stage_events[k] or th.cuda.Event()
+            ev.record(th.cuda.current_stream(self.device))
+            self._stage_events[k] = ev
+
     def stage_step(self, sc: np.ndarray, coords, t_model: float, y=None):
-        """One pinned staging buffer -> small async H2D copies (classes, scalars, timestep, cutout windows)."""
-        st = self._stage
+        """One pinned staging slot -> small async H2D copies (classes, scalars, timestep, cutout windows)."""
+        k = self._stage_acquire()
+        st = self._stage_ring[k]
         o = self.B * 8  # [0, 8B): int64 classes (kept first for alignment)
         self.h2d_bytes = 0
         if y is not None and self.unet.cfg.class_cond:
@@ -469,19 +493,24 @@ class GuidedStepB200:
             st[o:o + n].view(th.int32).copy_(th.tensor(coords, dtype=th.int32).view(-1))
             self.v(self.coords).view(th.uint8)[:n].copy_(st[o:o + n], non_blocking=True)
             self.h2d_bytes += n
-            self._stage_resize_tables(coords)
+            self._stage_resize_tables(coords, k)
+        self._stage_release(k)
 
-    def _stage_resize_tables(self, coords):
+    def _stage_resize_tables(self, coords, slot=None):
         """ResizeRight mode: per-cutout resampling tables of this step's crop sizes (cached per size on the host) -> device"""
         if self.vit is None or self.cutout_resize != "lanczos3":
             return
         from . import resize_right as rr
         cs, S_max = self.vit_cfg.input_resolution, self.H
-        if not hasattr(self, "_rr_pin"):
+        if self._rr_ring is None:
             pin = self.device.type == "cuda"
-            self._rr_pin = (th.zeros(self.cutn, cs, dtype=th.int32, pin_memory=pin), th.zeros(self.cutn, cs, rr.T_MAX, pin_memory=pin),
-                            th.zeros(self.cutn, dtype=th.int32, pin_memory=pin), th.zeros(self.cutn, S_max, 2, dtype=th.int32, pin_memory=pin))
-        pl, pw, pt, pi_ = self._rr_pin
+            self._rr_ring = [(th.zeros(self.cutn, cs, dtype=th.int32, pin_memory=pin), th.zeros(self.cutn, cs, rr.T_MAX, pin_memory=pin),
+                              th.zeros(self.cutn, dtype=th.int32, pin_memory=pin), th.zeros(self.cutn, S_max, 2, dtype=th.int32, pin_memory=pin))
+                             for _ in range(self.STAGE_SLOTS)]
+        own = slot is None  # segment path (cond_grad): take and guard a slot of its own
+        if own:
+            slot = self._stage_acquire()
+        pl, pw, pt, pi_ = self._rr_ring[slot]
         for k, (_, _, S) in enumerate(coords):
             left, w, T = rr.tables(int(S), cs)
             pl[k].copy_(left)
@@ -493,6 +522,8 @@ class GuidedStepB200:
         self.v(self.rr_taps, (self.cutn,)).copy_(pt, non_blocking=True)
         self.v(self.rr_inv, (self.cutn, S_max, 2)).copy_(pi_, non_blocking=True)
         self.h2d_bytes += pl.numel() * 4 + pw.numel() * 4 + pt.numel() * 4 + pi_.numel() * 4
+        if own:
+            self._stage_release(slot)
 
     def fused_step(self, diffusion, mode, t_index, img, y, cond_fn, eta=0.0) -> dict:
         # RNG order of the reference: the ancestral sampler draws its noise BEFORE cond_fn (whose MakeCutouts draws the windows

@@ -145,7 +145,8 @@ enum {
   /* tv_loss + range_loss (+ sat) forward and analytic backward, merged with the CLIP-path gradient
    * (cgd/losses.py:5-7,17-22, cgd/cgd.py:201-218).
    * p0 x_in(f) p1 pred_xstart(f) p2 g_clip(f, dL/dx_in from the CLIP path)|0 p3 sc p4 seed(h pixel-major [B*HW, ld], UNet dgrad seed)
-   * p5 dx_direct(f NCHW) p6 loss(f [3B] = tv[B], range[B], sat[B]) ; i0 B i1 H i2 W i3 ld ; f0 tv_scale f1 range_scale f2 sat_scale f3 seed scale
+   * p5 dx_direct(f NCHW) p6 loss(f [3B] = tv[B], range[B], sat[B]) ; i0 B i1 H i2 W i3 ld i4 batch of the whole job (sat is
+   * mean over ALL ranks' images, cgd/cgd.py:215; 0 = B) ; f0 tv_scale f1 range_scale f2 sat_scale f3 seed scale
    * flags 1 = dynamic seed scaling: p7 seed_f32(f [B,HW,3]) p8 dyn(f [2B]) are written instead of p4 (see CGD_OP_SEED_QUANT), f3 unused */
   CGD_OP_GUIDE_GRAD = 25,
   /* g = -(dx_direct + dx_unet / seed scale), optional RMS clamp (cgd/cgd.py:228-232).

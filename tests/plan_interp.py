@@ -528,6 +528,7 @@ class Interp:
 
     def op_GUIDE_GRAD(self, op):
         B, H, W, ld = op.i[:4]
+        Bg = op.i[4] if op.i[4] > 0 else B  # batch of the whole job: sat is a mean over every rank's images
         tvs, rs, ss, seed_scale = op.f[:4]
         sc = self.flat(op.p[3], SC["COUNT"])
         a, bb, fac, omf = (float(sc[SC[k]]) for k in ("SQRT_RECIP_AC", "SQRT_RECIPM1_AC", "FAC", "ONE_MINUS_FAC"))
@@ -540,7 +541,7 @@ class Interp:
         loss = tv.sum() * tvs + rl.sum() * rs
         sat = None
         if ss != 0:
-            sat = th.abs(xin - xin.clamp(-1, 1)).mean() * ss
+            sat = th.abs(xin - xin.clamp(-1, 1)).mean() * (B / Bg) * ss
             loss = loss + sat
         d_xin, d_x0r = th.autograd.grad(loss, (xin, x0), allow_unused=True)
         if op.p[2] is not None:
@@ -560,7 +561,7 @@ class Interp:
             lo[:B] += (tv * tvs).detach()
             lo[B:2 * B] += (rl * rs).detach()
             if sat is not None:
-                per = th.abs(xin - xin.clamp(-1, 1)).detach().mean([1, 2, 3]) / B * ss
+                per = th.abs(xin - xin.clamp(-1, 1)).detach().mean([1, 2, 3]) / Bg * ss
                 lo[2 * B:3 * B] += per
 
     def op_SEED_QUANT(self, op):

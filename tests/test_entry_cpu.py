@@ -50,3 +50,19 @@ def test_clip_guided_diffusion_generator_on_the_interpreter(tmp_path, monkeypatc
     with pytest.raises(NotImplementedError):
         next(cgd.clip_guided_diffusion(image_size=64, device="cpu", image_prompts=["x.png"], unet_state_dict=usd, clip_state_dict=vsd,
                                        target_embeds=tgt, weights=[1.0, 1.0]))
+
+
+def test_parse_prompt_and_log_image_known_answers(tmp_path, monkeypatch):
+    """the reference's own known-answer tests for the entry's helpers (test.py:106-119, 178-194), plus the url branch and the
+    file-name sanitising of cgd/script_util.py:60-67, 81-90"""
+    monkeypatch.chdir(tmp_path)
+    assert cgd.parse_prompt("Loose seal.:0.4") == ("Loose seal.", 0.4)
+    assert cgd.parse_prompt("Loose seal.:-0.4") == ("Loose seal.", -0.4)
+    assert cgd.parse_prompt("Loose seal.") == ("Loose seal.", 1.0)
+    assert cgd.parse_prompt("https://a.b/c.png:2") == ("https://a.b/c.png", 2.0)
+    assert cgd.parse_prompt("https://a.b/c.png") == ("https://a.b/c.png", 1.0)
+    got = cgd.log_image(th.rand(3, 3, 3), str(tmp_path), ["a", "b", "c"], 1, 4)
+    assert got == os.path.join(str(tmp_path), "a_b_c/04/0001.png") and os.path.exists(got)
+    assert cgd.clean_and_combine_prompts("o", ["a cat: 0.5/x!", "b"], 0) == os.path.join("o", "a_cat_05x_b", "00")
+    assert len(os.path.basename(os.path.dirname(cgd.clean_and_combine_prompts("o", ["x" * 400], 0)))) == 255
+    assert cgd.DIFFUSION_FILENAMES[(False, 512)] == "512x512_diffusion_uncond_finetune_008100.pt"

@@ -71,3 +71,38 @@ def test_cfg1_chain_vs_oracle():
         drift.append(rel(xe, xo))
     res = dict(drift_max=max(drift), drift_last=drift[-1], psnr=psnr(xe, xo), finite=bool(th.isfinite(xe).all()))
     assert res["finite"] and res["drift_max"] < 5e-2 and res["psnr"] > 35.0, res
+
+
+@pytest.mark.parametrize("resize", ["pool", "lanczos3"])
+def test_loop_without_per_step_sync_equals_synced_run(resize):
+    """The host runs ahead of the device between saved frames (default save_frequency 25, cgd/cgd.py:41): the per-step pinned
+    staging (scalars, t, classes, cutout windows, ResizeRight tables) must not be rewritten before its copy executed.  The device
+    is held busy while the host enqueues the whole chain, so an unguarded staging buffer would feed the last step's scalars to
+    every step; the result must equal the run that synchronises after every step."""
+    from clip_guided_diffusion_b200 import guidance as pg
+    from tests.step_parity import build_tiny
+    ctx = build_tiny("cuda:0", B=2, cutn=3, image=64, use_magnitude=True, use_graph=True, cutout_resize=resize)
+    eng, pdiff = ctx["eng"], ctx["pdiff"]
+    mc = pg.MakeCutouts(32, 3)
+    finals = []
+    for sync in (True, False):
+        th.manual_seed(5)
+        cond = pg.CondFnB200(eng, pdiff, mc)
+        x_T = eng.draw_initial_noise()
+        if not sync:
+            th.cuda.synchronize()
+            th.cuda._sleep(int(1.5e9))  # ~1 s at 1.5 GHz: every step of the chain is enqueued behind it
+        loop = pdiff.ddim_sample_loop_progressive(eng.model, eng.shape, noise=x_T, clip_denoised=False, cond_fn=cond,
+                                                  model_kwargs={"y": th.zeros(2, dtype=th.long, device="cuda")}, randomize_class=True,
+                                                  cond_fn_with_grad=True)
+        n, out = 0, None
+        for out in loop:
+            cond.step_done()
+            n += 1
+            if sync:
+                th.cuda.synchronize()
+        th.cuda.synchronize()
+        assert n == 25
+        finals.append((out["sample"].float().cpu(), out["pred_xstart"].float().cpu()))
+    (s0, p0), (s1, p1) = finals
+    assert th.isfinite(s0).all() and rel(s1, s0) < 1e-5 and rel(p1, p0) < 1e-5, (rel(s1, s0), rel(p1, p0))

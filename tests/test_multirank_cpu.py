@@ -77,3 +77,16 @@ def test_two_rank_whole_batch_rms_clamp():
     assert abs(float(r_ref[0] / r_ref[1]) - 1.0) > 0.02, "degenerate case: both images have the same gradient norm"
     assert abs(float(r_got[0] / r_got[1]) / float(r_ref[0] / r_ref[1]) - 1.0) < 1e-2
     assert abs(float(g_got.square().mean().sqrt()) - 0.05) < 1e-3
+
+
+def test_two_rank_sat_loss_is_a_whole_batch_mean():
+    """sat loss = mean over the WHOLE batch (cgd/cgd.py:214-218): a rank holding B/G images must still divide by B_global"""
+    kw = dict(sat_scale=500.0)
+    ref = _one_step(build_tiny("cpu", B=2, cutn=3, image=32, **kw), scale_rows=True)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, 29521, ret, kw, "ddim"), nprocs=2, join=True)
+    got = ret["gathered"]
+    assert th.equal(got[:, 3:12], ref[:, 3:12])
+    rel_g = float((got[:, 12:15] - ref[:, 12:15]).norm() / ref[:, 12:15].norm())
+    assert rel_g < 1e-2, rel_g
