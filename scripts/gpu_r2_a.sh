@@ -9,6 +9,8 @@ echo "=== GN epilogue stats (CGD_TEST_EPI=1)"
 CGD_TEST_EPI=1 timeout 400 python -m pytest tests/test_gpu_epi_stats.py -q -m gpu -x --tb=short -p no:cacheprovider 2>&1 | tail -20 | tee gpurun_out/test_gpu_epi.log
 echo "=== tail (CGD_TEST_TAIL=1)"
 CGD_TEST_TAIL=1 timeout 400 python -m pytest tests/test_gpu_tail.py -q -m gpu -x --tb=short -p no:cacheprovider 2>&1 | tail -20 | tee gpurun_out/test_gpu_tail.log
+echo "=== unsynced loop (staging ring)"
+timeout 400 python -m pytest tests/test_gpu_chain.py -q -m gpu -x --tb=short -p no:cacheprovider -k sync 2>&1 | tail -8
 echo "=== microbench default / tail"
 timeout 200 python scripts/conv_microbench.py 2>&1 | tail -12
 CGD_CONV_TAIL=1 timeout 200 python scripts/conv_microbench.py 2>&1 | tail -12
