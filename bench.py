@@ -179,6 +179,32 @@ def dominant_kernel_time(device, reps=24):
     return e0.elapsed_time(e1) * 1e-3 / (rounds * nbuf)
 
 
+def conv_share(eng, mode, reps=3):
+    """Summed duration and algorithmic FLOPs of every contraction (op CONV: 3x3 / 1x1 convs and the GEMMs, forward and dgrad) of
+    one step, launched back to back on the current stream."""
+    from clip_guided_diffusion_b200._lib import OP
+    plan = eng.plan
+    m = plan.marks
+    segs = [("unet_emb", "unet_bwd"), ("vit_fwd", "vit_bwd"), ("vit_bwd", "vit_end"), ("unet_bwd", "unet_end")]
+    if eng.lpips is not None:
+        segs.append(("lpips", "lpips_end"))
+    ks = [k for a, b in segs for k in range(m[a], m[b]) if plan.ops[k].code == OP["CONV"]]
+    flop = 0.0
+    for k in ks:
+        flop += plan.conv_flops(k)
+    for k in ks:
+        plan.run(k, 1)
+    th.cuda.synchronize()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for k in ks:
+            plan.run(k, 1)
+    e1.record()
+    th.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps, flop, len(ks)
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +238,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         img = step_resident(idx, img)
         idx = max(idx - 1, 0)
+    eng.gather_final(img)  # warm-up of the collective too: communicator / channel set-up stays out of the timed region
     if world > 1:
         dist.barrier()
     th.cuda.synchronize()
@@ -223,9 +250,7 @@ def run_ours(args):
     for _ in range(args.steps):
         img = step_resident(idx, img)
         idx = max(idx - 1, 0)
-    if world > 1:  # the run's single collective: gather the images of all ranks
-        gathered = [th.empty_like(img) for _ in range(world)]
-        dist.all_gather(gathered, img.contiguous())
+    gathered = eng.gather_final(img)  # the run's single collective (one all_gather_into_tensor; identity at N = 1)
     e1.record()
     th.cuda.synchronize()
     if world > 1:
@@ -235,7 +260,7 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = float(ms.item())
-    finite = bool(th.isfinite(img).all())
+    finite = bool(th.isfinite(img).all()) and tuple(gathered.shape) == (eng.global_batch, 3, eng.H, eng.W)
 
     # ---------------- end-to-end loop: host buffers, H2D of x_t and D2H of the sample inside every step
     host_x = th.empty(B, 3, eng.H, eng.W, pin_memory=True)
@@ -268,11 +293,19 @@ def run_ours(args):
     h2d = B * 3 * eng.H * eng.W * 4 + eng.h2d_bytes
     d2h = B * 3 * eng.H * eng.W * 4
 
+    # ---------------- the PyTorch-CUDA build of the same step (north_star's ">= 2.5x" denominator), on every rank like our arm
+    torch_base = None
+    if not args.no_torch_baseline:
+        try:
+            torch_base = torch_cuda_baseline(device, max(5, min(10, args.steps)), dist if world > 1 else None, world)
+        except Exception as e:  # context only: never lose the measured line
+            torch_base = {"error": repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
+    conv_s, conv_flop, n_conv = conv_share(eng, MODE)
     launches = eng.launches_per_step(MODE)
     value = args.steps * eng.global_batch / (ms_total * 1e-3)
     e2e = args.steps * eng.global_batch / (ms_e2e * 1e-3)
@@ -301,15 +334,18 @@ def run_ours(args):
                      "avg_launch_s": t_dom},
         "step_tensor_frac": CFG["tflop"] * 1e12 * value / world / (pk["sustained"] * 1e12),
     }
-    if world == 1 and args.torch_baseline:
-        del eng
-        th.cuda.empty_cache()
-        try:
-            line["torch_cuda_baseline"] = torch_cuda_baseline(device, max(5, args.steps // 2))
-        except Exception as e:  # context only: never lose the measured line
-            line["torch_cuda_baseline"] = {"error": repr(e)[:300]}
+    # time-weighted fraction over EVERY contraction of the step (convs + GEMMs, both directions), so that `frac` above -- one layer
+    # shape -- cannot be read as "the step runs at that fraction": their algorithmic FLOPs / their summed duration / peak
+    line["roofline"].update({"step_conv_frac": conv_flop / conv_s / 1e12 / pk["sustained"], "step_conv_tflops": conv_flop / conv_s / 1e12,
+                             "step_conv_ms": conv_s * 1e3, "step_conv_launches": n_conv,
+                             "step_conv_note": "all CONV ops of one step launched back to back (no graph), CUDA events; vs the sustained peak"})
+    if torch_base is not None:
+        line["torch_cuda_baseline"] = torch_base
+        if "value" in torch_base:
+            line["vs_torch_cuda"] = value / torch_base["value"]
+            line["vs_torch_cuda_e2e"] = e2e / torch_base["value_with_item_logging"]
     if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2":
-        line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+        line["cpu_baseline"] = cpu_baseline(sample_steps=3)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -320,27 +356,12 @@ _CPU_THREADS = None
 
 
 def pick_cpu_threads() -> int:
-    """Thread count that runs a representative fp32 conv fastest on this host (all cores is often slower on many-core boxes:
-    the build box' 8 cores take 30 s/step, a 128-core host with 128 threads took 206 s/step)."""
+    """Deterministic thread count of the CPU arms: every host core up to 32 (PyTorch's CPU convs stop scaling there: the build box'
+    8 cores take 30 s/step, the B200 host ran 5-6 s/step with 16-48 threads and 206 s/step with 128; CGD_CPU_THREADS overrides)."""
     global _CPU_THREADS
-    if _CPU_THREADS is not None:
-        return _CPU_THREADS
-    ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 48, 64, 96, ncpu) if c <= ncpu})
-    x = th.randn(1, 256, 128, 128)
-    w = th.randn(256, 256, 3, 3)
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        th.set_num_threads(c)
-        th.nn.functional.conv2d(x, w, padding=1)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            th.nn.functional.conv2d(x, w, padding=1)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    _CPU_THREADS = best
-    return best
+    if _CPU_THREADS is None:
+        _CPU_THREADS = int(os.environ.get("CGD_CPU_THREADS", "0")) or min(os.cpu_count() or 1, 32)
+    return _CPU_THREADS
 
 
 def oracle_cpu_setup():
@@ -378,11 +399,14 @@ def oracle_cpu_steps(unet, diff, cond, n_steps, x=None):
     return times, x
 
 
-def torch_cuda_baseline(device, n_steps):
-    """The reference's PyTorch-CUDA configuration (SURVEY.md BASELINE section 5): the same op sequence on cuDNN / cuBLAS / ATen with
-    eager autograd -- fp16 UNet trunk (convert_to_fp16: conv weights of input/middle/output blocks), fp16 CLIP, fp32 norms -- here
-    via the oracle port because the reference's third-party packages cannot be installed offline.  Context only."""
+def torch_cuda_baseline(device, n_steps, dist=None, world=1):
+    """The reference's PyTorch-CUDA configuration: the same op sequence on cuDNN / cuBLAS / ATen with eager
+    autograd -- fp16 UNet trunk (convert_to_fp16: conv weights of input/middle/output blocks), fp16 CLIP, fp32 norms -- via the
+    oracle port because the reference's third-party packages cannot be installed offline.  One image per rank like our arm (weak
+    scaling), time = max over ranks, measured twice: with the reference's per-step `.item()` loss logging (cgd/cgd.py:234-236,
+    three host syncs per step) and without it."""
     from oracle import guidance as og
+    th.backends.cudnn.benchmark = True
     unet, diff, cond = oracle_cpu_setup()
     unet = unet.to(device)
     for blocks in (unet.input_blocks, unet.middle_block, unet.output_blocks):
@@ -397,55 +421,86 @@ def torch_cuda_baseline(device, n_steps):
     cond = og.OracleCondFn(diff, clip, cond.target_embeds.to(device), cond.weights.to(device), cut_size=224, num_cutouts=CFG["cutn"])
     B = CFG["per_gpu_batch"]
     i = diff.num_timesteps - 1
+    fn = diff.ddim_sample_with_grad if CFG["respacing"].startswith("ddim") else diff.p_sample_with_grad
 
     def one(i):
         x = th.randn(B, 3, CFG["image_size"], CFG["image_size"], device=device)
         t = th.full((B,), i, dtype=th.long, device=device)
         y = th.randint(0, 1000, (B,), device=device)
-        return diff.ddim_sample_with_grad(unet, x, t, clip_denoised=False, cond_fn=cond, model_kwargs={"y": y})["sample"]
+        return fn(unet, x, t, clip_denoised=False, cond_fn=cond, model_kwargs={"y": y})["sample"]
 
-    for _ in range(3):
-        one(i)
-    th.cuda.synchronize()
-    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(n_steps):
-        out = one(i - k)
-    e1.record()
-    th.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n_steps
-    return {"value": 1e3 / ms, "unit": "image-steps/s", "ms_per_step": ms, "steps": n_steps,
-            "what": "oracle port on cuda: eager PyTorch autograd, fp16 UNet trunk + fp16 CLIP (cuDNN/cuBLAS/ATen), no .item() logging",
+    res = {}
+    for key, log_items in (("value", False), ("value_with_item_logging", True)):
+        cond.log_items = log_items
+        for _ in range(3):
+            one(i)
+        if dist is not None:
+            dist.barrier()
+        th.cuda.synchronize()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(n_steps):
+            out = one(i - k)
+        e1.record()
+        th.cuda.synchronize()
+        ms = th.tensor([e0.elapsed_time(e1) / n_steps], device=device)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        res[key] = 1e3 * world * B / float(ms.item())
+    return {"value": res["value"], "value_with_item_logging": res["value_with_item_logging"], "unit": "image-steps/s (whole job)",
+            "ms_per_step": 1e3 * world * B / res["value"], "steps": n_steps, "n_gpus": world,
+            "what": "oracle port on cuda: eager PyTorch autograd, fp16 UNet trunk + fp16 CLIP (cuDNN benchmark mode / cuBLAS / ATen), "
+                    "one image per rank, max over ranks; with and without the reference's per-step .item() loss logging",
             "torch": th.__version__, "finite": bool(th.isfinite(out).all())}
 
 
-def cpu_baseline(sample_steps=1):
+def cpu_baseline(sample_steps=3):
+    """rank 0, N = 1: one untimed (cold) step, then `sample_steps` timed ones -- the same protocol as the reference arm"""
     unet, diff, cond = oracle_cpu_setup()
-    times, _ = oracle_cpu_steps(unet, diff, cond, sample_steps)
-    t = float(np.median(times))
+    _, x = oracle_cpu_steps(unet, diff, cond, 1)
+    times, _ = oracle_cpu_steps(unet, diff, cond, sample_steps, x)
+    t = float(np.mean(times))
     return {"value": 1.0 / t, "unit": "image-steps/s", "cores": pick_cpu_threads(), "host_cpus": os.cpu_count(), "kind": "port",
-            "sample": f"{sample_steps} full cfg2 step(s) of the fp32 oracle port (PyTorch CPU, all host threads), {t:.2f} s/step"}
+            "sample": f"{sample_steps} full cfg2 steps of the fp32 oracle port after 1 untimed step (PyTorch CPU, {pick_cpu_threads()} threads), "
+                      f"{t:.2f} s/step"}
 
 
 def run_reference(args):
+    """The reference's own algorithm on the host cores (fp32 oracle port: guided_diffusion / clip / lpips are not installable
+    offline).  Same metric / unit / config strings as our arm; --warmup W untimed steps, --steps K timed ones.
+    One cfg2 step is 5-6 s on the B200 host: W + K steps fit a few minutes; on a slower host the run is cut to a time budget and
+    says so (`steps` / `warmup` then report what actually ran)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     unet, diff, cond = oracle_cpu_setup()
-    budget_s = 170.0
-    t_first, x = oracle_cpu_steps(unet, diff, cond, 1)  # warm-up step, also sizes the run
-    per = t_first[0]
-    n_timed = int(max(1, min(args.steps, budget_s // per)))
+    budget_s = float(os.environ.get("CGD_REF_BUDGET_S", "240"))
+    t_last, x = oracle_cpu_steps(unet, diff, cond, 1)  # cold step (allocator, thread pool): always run, the first warm-up step
+    warm_done, n_timed = 1, args.steps
+    if args.warmup >= 2:
+        t_last, x = oracle_cpu_steps(unet, diff, cond, 1, x)  # a warm step sizes the rest of the run
+        warm_done = 2
+    per = t_last[0]
+    more_warm = max(args.warmup - warm_done, 0)
+    if per * (more_warm + n_timed) > budget_s:  # slow host: drop the remaining warm-up first, then cut the timed sample
+        more_warm = 0
+        n_timed = int(max(1, min(args.steps, budget_s // per)))
+    if more_warm:
+        _, x = oracle_cpu_steps(unet, diff, cond, more_warm, x)
+        warm_done += more_warm
     times, _ = oracle_cpu_steps(unet, diff, cond, n_timed, x)
     total = float(sum(times))
     value = n_timed / total
-    line = {"impl": "reference", "metric": "diffusion-steps/sec", "value": value, "unit": "image-steps/s (1 step of one 256x256 image, 16 cutouts)",
-            "n_gpus": args.gpus, "steps": n_timed, "requested_steps": args.steps, "warmup": 1, "ms_per_step": total / n_timed * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: image_size=256, respace=ddim250, batch=1, cutn=16, ViT-B/32 -- the reference's own "
-                                   "algorithm (fp32 oracle port; guided_diffusion / clip packages are not installable offline) on the host CPU",
-                       "global_batch": 1},
+    line = {"impl": "reference", "metric": "diffusion-steps/sec", "value": value,
+            "unit": f"image-steps/s (1 step of one {CFG['image_size']}x{CFG['image_size']} image, {CFG['cutn']} cutouts)",
+            "n_gpus": args.gpus, "steps": n_timed, "requested_steps": args.steps, "warmup": warm_done,
+            "ms_per_step": total / n_timed * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic (seeded random weights)",
+            "config": {"workload": CFG["name"] + ", class-cond UNet, seeded random weights", "global_batch": 1,
+                       "parallelism": "host CPU threads (rank 0 only)",
+                       "note": "the reference's own algorithm as the fp32 oracle port on the host CPU; guided_diffusion / clip are not "
+                               "installable offline"},
             "cpu_baseline": {"value": value, "unit": "image-steps/s", "cores": pick_cpu_threads(), "host_cpus": os.cpu_count(), "kind": "port",
-                             "sample": f"{n_timed} full cfg2 steps (bounded to ~{budget_s:.0f} s of CPU work; {args.steps} requested)"},
+                             "sample": f"{n_timed} full cfg2 steps after {warm_done} untimed (time budget {budget_s:.0f} s; {args.steps} requested)"},
             "e2e": {"value": value, "unit": "image-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -458,7 +513,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-baseline", action="store_true", help="also time the PyTorch-CUDA (cuDNN/cuBLAS eager autograd) oracle port")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the PyTorch-CUDA (cuDNN/cuBLAS eager autograd) oracle-port arm")
+    ap.add_argument("--torch-baseline", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="per-GPU shard of a BASELINE.json configuration (default: the metric's)")
     args = ap.parse_args()
     global CFG

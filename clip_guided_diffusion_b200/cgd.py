@@ -211,8 +211,18 @@ def clip_guided_diffusion(
     samples = loop(engine.model, (local_b, 3, H, W), clip_denoised=False, model_kwargs=model_kwargs, cond_fn=cond_fn, progress=progress,
                    skip_timesteps=skip_timesteps, init_image=init_tensor, randomize_class=randomize_class, cond_fn_with_grad=True)
     cond_fn.current_timestep = diffusion.num_timesteps - 1  # cgd/cgd.py:265
+    last_step = diffusion.num_timesteps - skip_timesteps - 1
     for step, sample in enumerate(samples):
         cond_fn.step_done()
-        if step % save_frequency == 0 or cond_fn.current_timestep == -1:
+        save = step % save_frequency == 0 or cond_fn.current_timestep == -1
+        if world_size > 1 and step == last_step:
+            # the run's one collective: all ranks' final images -> rank 0, which saves and yields the whole batch;
+            # earlier frames stay with the rank that owns the image (no traffic)
+            final = engine.gather_final(sample["pred_xstart"])
+            if save and rank == 0:
+                for batch_idx, image_tensor in enumerate(final):
+                    yield batch_idx, log_image(image_tensor, prefix_path, prompts, step, batch_idx)
+            continue
+        if save:
             for batch_idx, image_tensor in enumerate(sample["pred_xstart"]):
                 yield batch_idx + rank * local_b, log_image(image_tensor, prefix_path, prompts, step, batch_idx + rank * local_b)

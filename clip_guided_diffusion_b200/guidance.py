@@ -312,6 +312,23 @@ class GuidedStepB200:
         self.img(self.noise).copy_(self.local_rows(full))
         return self.img(self.noise)
 
+    def gather_final(self, t: th.Tensor) -> th.Tensor:
+        """The run's single collective: every rank's rows of ``t`` ([B_local, ...], e.g. the final sample or
+        pred_xstart) -> [B_global, ...] in rank order on every rank.  One ``all_gather_into_tensor`` (NCCL over NVLink; gloo in the
+        CPU tests) into a buffer allocated once per shape -- no list of outputs, no copies, no per-call channel set-up after the
+        first.  A single rank returns its tensor unchanged."""
+        if self.world == 1:
+            return t
+        import torch.distributed as dist
+        t = t.contiguous()
+        key = (tuple(t.shape), t.dtype)
+        bufs = self.__dict__.setdefault("_gather_bufs", {})
+        out = bufs.get(key)
+        if out is None:
+            out = bufs[key] = th.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out
+
     def draw_classes(self) -> th.Tensor:
         full = th.randint(0, self.unet.num_classes, (self.global_batch,), device=self.device)
         return self.local_rows(full)

@@ -798,6 +798,13 @@ class Plan:
     def run_range(self, a: str, b: str, stream=None):
         self.run(self.marks[a], self.marks[b] - self.marks[a], stream)
 
+    def conv_flops(self, k: int) -> float:
+        """2 * MACs of CONV op k from its executed dims (image channels padded 3 -> 64 count as executed: +1 % on a UNet)"""
+        op = self.ops[k]
+        assert op.code == OP["CONV"]
+        NB, H, W, Cin, Cout, _npad_, taps = op.i[:7]
+        return 2.0 * NB * H * W * Cin * Cout * taps
+
     def num_launches(self, first=0, count=None) -> int:
         count = len(self.ops) - first if count is None else count
         return int(_lib.load().cgd_plan_num_launches(self.handle, first, count))

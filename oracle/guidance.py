@@ -130,6 +130,7 @@ class OracleCondFn:
         self.current_timestep = diffusion.num_timesteps - 1
         self.last_coords = None
         self.last_terms = None
+        self.log_items = True
 
     def step_done(self):
         self.current_timestep -= 1
@@ -141,7 +142,9 @@ class OracleCondFn:
         self.last_coords = coords
         loss, terms = guidance_loss(x, out["pred_xstart"], fac, coords, self.clip_model, self.target_embeds,
                                     self.weights, **self.kw)
-        self.last_terms = {k: float(v.detach()) for k, v in terms.items()}
+        # the reference logs the loss terms with .item() every step (cgd/cgd.py:234-236: three host syncs); log_items=False keeps
+        # them on the device (bench.py times the PyTorch-CUDA arm both ways)
+        self.last_terms = {k: float(v.detach()) for k, v in terms.items()} if self.log_items else {k: v.detach() for k, v in terms.items()}
         g = -th.autograd.grad(loss, x)[0]
         if self.use_magnitude:
             g = magnitude_clamp(g)

@@ -35,10 +35,9 @@ def _worker(rank, world, port, ret, kw=None, mode="ddim"):
     th.set_num_threads(2)
     ctx = build_tiny("cpu", B=1, cutn=3, image=32, rank=rank, world_size=world, **(kw or {}))
     s = _one_step(ctx, mode=mode, scale_rows=bool(kw))
-    out = [th.empty_like(s) for _ in range(world)]
-    dist.all_gather(out, s)
+    out = ctx["eng"].gather_final(s)  # the product's collective: one all_gather_into_tensor, rank order
     if rank == 0:
-        ret["gathered"] = th.cat(out)
+        ret["gathered"] = out.clone()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -90,3 +89,43 @@ def test_two_rank_sat_loss_is_a_whole_batch_mean():
     assert th.equal(got[:, 3:12], ref[:, 3:12])
     rel_g = float((got[:, 12:15] - ref[:, 12:15]).norm() / ref[:, 12:15].norm())
     assert rel_g < 1e-2, rel_g
+
+
+def _entry_worker(rank, world, port, outdir, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    th.set_num_threads(2)
+    os.chdir(os.path.join(outdir, f"cwd{rank}"))  # log_image also writes ./current.png
+    from clip_guided_diffusion_b200 import cgd
+    from clip_guided_diffusion_b200 import unet as pu
+    from clip_guided_diffusion_b200 import vit as pv
+    from clip_guided_diffusion_b200 import weights as pw
+    from tests.test_entry_cpu import _InterpretedEngine
+    cgd._require_cuda = lambda device: None
+    cgd.GuidedStepB200 = _InterpretedEngine
+    ucfg, vcfg = pu.config_for(64, True), pv.ViTConfig(32, 16, 64, 1, 32)
+    usd = pw.seeded_state_dict(pw.unet_param_shapes(ucfg), 1234)
+    vsd = pw.seeded_state_dict(pw.vit_param_shapes(vcfg), 1235)
+    tgt = th.randn(1, 32, generator=th.Generator().manual_seed(0))
+    got = list(cgd.clip_guided_diffusion(image_size=64, num_cutouts=2, prompts=["two ranks"], batch_size=world, timestep_respacing="25",
+                                         skip_timesteps=23, save_frequency=1, prefix_path=os.path.join(outdir, "out"), progress=False, seed=0,
+                                         device="cpu", unet_state_dict=usd, clip_state_dict=vsd, target_embeds=tgt, rank=rank, world_size=world))
+    ret[rank] = got
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_entry_gathers_final_images_on_rank0(tmp_path):
+    """`clip_guided_diffusion(rank=, world_size=)`: intermediate frames are saved by the rank that owns the image, the final frame is
+    all-gathered (the run's single collective, `GuidedStepB200.gather_final`) and saved / yielded for the WHOLE batch by rank 0."""
+    for r in range(2):
+        os.makedirs(tmp_path / f"cwd{r}")
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_entry_worker, args=(2, 29523, str(tmp_path), ret), nprocs=2, join=True)
+    # 25 - 23 = 2 steps, save_frequency 1: step 0 by each owner, step 1 (the last) for both images by rank 0 only
+    assert [b for b, _ in ret[0]] == [0, 0, 1] and [b for b, _ in ret[1]] == [1]
+    paths = sorted(p for _, p in list(ret[0]) + list(ret[1]))
+    assert [os.path.relpath(p, tmp_path / "out") for p in paths] == ["two_ranks/00/0000.png", "two_ranks/00/0001.png",
+                                                                    "two_ranks/01/0000.png", "two_ranks/01/0001.png"]
+    assert all(os.path.exists(p) for p in paths)
