@@ -29,6 +29,12 @@ CASES = [
     ("conv3x3_32x32_c512_cluster8", 1, 32, 32, 512, 512, 9, True, True),      # in-cluster split-K: 16 CTAs per tile (BN 256, S = 8)
     ("conv1x1_16x16_k3072", 1, 16, 16, 3072, 1024, 1, True, False),
     ("linear_k2304_m800", 1, 1, 800, 2304, 768, 1, False, True),              # BN 192, S = 4, ragged last pixel tile
+    # the dominant layer of the benchmarked configuration: 31 % of the 256x256 UNet's FLOPs (M = 65536, N = 256, K = 2304), the
+    # shape bench.py's `roofline` line times -- 256 tiles on 74 CTA pairs (3.46 waves), with and without the ResBlock residual
+    ("conv3x3_256x256_c256_dominant", 1, 256, 256, 256, 256, 9, True, False),
+    ("conv3x3_256x256_c256_dominant_res", 1, 256, 256, 256, 256, 9, True, True),
+    ("conv3x3_256x256_c512_to_256", 1, 256, 256, 512, 256, 9, True, False),      # output blocks at 256x256: K = 4608
+    ("conv3x3_128x128_c256", 1, 128, 128, 256, 256, 9, True, True),
 ]
 
 
