@@ -1,13 +1,11 @@
-"""GPU: the CLIP ModifiedResNet tower (rn.py) on the device.  The tower was built after the round's GPU budget was spent: it is
-verified through the op-list interpreter (tests/test_rn_cpu.py, tests/test_step_cpu.py[tower=rn]) and every kernel it uses except
-the two AttentionPool token-assembly kernels is covered by the other GPU tests, but these device tests have not run yet.  They are
-opt-in (CGD_TEST_RN=1) so that an unvalidated test cannot stop the round-end `pytest -m gpu -x`; first item of the next round."""
+"""GPU: the CLIP ModifiedResNet tower (rn.py) on the device -- a shallow tower op by op, the published RN50 / RN101 towers as a
+whole, and a guided step with an RN tower, each against the fp32 oracle (oracle/clip_rn.py)."""
 import os
 
 import pytest
 import torch as th
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("CGD_TEST_RN") != "1", reason="device run of the RN tower not validated yet: CGD_TEST_RN=1")]
+pytestmark = pytest.mark.gpu  # device-validated in round 2 (gpurun call A: passed on a B200), no longer opt-in
 
 
 def test_rn_tower_matches_oracle_on_device():
@@ -31,6 +29,36 @@ def test_rn_tower_matches_oracle_on_device():
     dp = tower.backward_patches(d_emb.cuda()).float().cpu()
     (g_ref,) = th.autograd.grad((ref * d_emb).sum(), xi)
     d_img = Interp._unpatchify(dp, 2, 224)
+    cos = float(th.nn.functional.cosine_similarity(d_img.flatten(), g_ref.flatten(), dim=0))
+    assert cos > 0.99, cos
+
+
+@pytest.mark.parametrize("name", ["RN50", "RN101"])
+def test_published_rn_towers_vs_oracle_on_device(name):
+    """the towers the reference lists (cgd/clip_util.py:17) and its own test uses (RN50, test.py:139-143) at their published depth /
+    width / embedding size: forward and input gradient of the whole tower vs the fp32 oracle (oracle/clip_rn.py)"""
+    from clip_guided_diffusion_b200 import rn as prn
+    from clip_guided_diffusion_b200 import weights as pw
+    from oracle import clip_rn as orn
+    from tests.plan_interp import Interp
+    n = 2
+    cfg = prn.RN_CONFIGS[name]
+    sd = pw.seeded_rn_state_dict(cfg, seed=3)
+    oracle = orn.ModifiedResNet(orn.RNConfig(layers=tuple(cfg.layers), output_dim=cfg.output_dim, input_resolution=cfg.input_resolution,
+                                             width=cfg.width)).eval()
+    oracle.load_state_dict({k[len("visual."):]: v for k, v in sd.items()}, strict=False)
+    tower = prn.RNB200(cfg, sd, n_images=n, device="cuda")
+    g = th.Generator().manual_seed(1)
+    img = th.randn(n, 3, cfg.input_resolution, cfg.input_resolution, generator=g)
+    got = tower.encode_patches(Interp._patchify(img, 2, cfg.kpad).cuda().half()).float().cpu()
+    xi = img.clone().requires_grad_()
+    ref = oracle(xi)
+    assert got.shape == ref.shape == (n, cfg.output_dim)
+    assert float((got - ref.detach()).norm() / ref.detach().norm()) < 3e-2
+    d_emb = th.randn(n, cfg.output_dim, generator=g)
+    dp = tower.backward_patches(d_emb.cuda()).float().cpu()
+    (g_ref,) = th.autograd.grad((ref * d_emb).sum(), xi)
+    d_img = Interp._unpatchify(dp, 2, cfg.input_resolution)
     cos = float(th.nn.functional.cosine_similarity(d_img.flatten(), g_ref.flatten(), dim=0))
     assert cos > 0.99, cos
 
