@@ -112,10 +112,32 @@ class EngineModel:
         return self
 
     def load_state_dict(self, state_dict, strict=True):
-        """Weights are packed into kernel layouts (K-major fp16 tiles, tap-flipped dgrad copies, fused emb matrix) when the engine is
-        built: pass the checkpoint's state_dict to ``GuidedStepB200(unet_cfg, state_dict, ...)`` (cgd/script_util.py:316-317
-        becomes that constructor call)."""
-        raise NotImplementedError("pass the state_dict to GuidedStepB200(...) -- weights are packed once at construction")
+        """cgd/script_util.py:317 ``model.load_state_dict(th.load(checkpoint_path))``: re-pack a checkpoint in upstream key layout
+        into the kernel layouts (K-major fp16 tiles, tap-flipped dgrad copies, the fused emb_layers matrix) IN PLACE -- the engine's
+        op lists, TMA descriptors and captured CUDA graphs hold addresses and stay valid.  The packing code runs once more on the
+        host against a shadow plan (seconds, like construction); shapes must match the architecture the engine was built for."""
+        from . import weights as W
+        from .plan import Plan
+        eng = self.engine
+        want = W.unet_param_shapes(eng.unet.cfg)
+        missing = [k for k in want if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in want]
+        bad = [k for k in want if k in state_dict and tuple(state_dict[k].shape) not in (tuple(want[k]), tuple(want[k]) + (1,))]
+        if bad:
+            raise RuntimeError("size mismatch for " + ", ".join(f"{k}: {tuple(state_dict[k].shape)} vs {tuple(want[k])}" for k in bad[:4]))
+        if missing or (strict and unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:4]}{'...' if len(missing) > 4 else ''}, "
+                               f"unexpected {unexpected[:4]}{'...' if len(unexpected) > 4 else ''}")
+        shadow = Plan(conv_impl=eng.plan.conv_impl)
+        for flag in ("grid_gn", "fused_gn", "tc_attention", "cluster_splitk", "gn_epi_stats"):
+            setattr(shadow, flag, getattr(eng.plan, flag))
+        UNetB200(eng.unet.cfg, state_dict, batch=eng.B, height=eng.H, width=eng.W, device="cpu", seed_scale=eng.unet.seed_scale, plan=shadow,
+                 build_backward=eng.vit is not None)
+        eng.plan.reload_consts(shadow, first=0)  # the UNet is the first network of the engine's plan
+        if eng.device.type == "cuda":
+            th.cuda.synchronize(eng.device)
+        import collections
+        return collections.namedtuple("IncompatibleKeys", "missing_keys unexpected_keys")(missing, unexpected)
 
 
 class GuidedStepB200:
@@ -507,6 +529,7 @@ class GuidedStepB200:
                     raise RuntimeError(f"cutout window (x={ox}, y={oy}, size={size}) lies outside the {self.H}x{self.W} image: the reference's "
                                        "adaptive_avg_pool2d raises on the empty crop (non-square images, cgd/modules.py:52,61)")
             n = len(coords) * 12
+        if self.cutn and len(coords):
             st[o:o + n].view(th.int32).copy_(th.tensor(coords, dtype=th.int32).view(-1))
             self.v(self.coords).view(th.uint8)[:n].copy_(st[o:o + n], non_blocking=True)
             self.h2d_bytes += n
@@ -547,9 +570,13 @@ class GuidedStepB200:
         # from the CPU generator), DDIM AFTER it.  On a GPU the two come from different generators and the order is immaterial;
         # it is kept anyway so a CPU run (tests/test_loops_cpu.py) consumes the default generator exactly like the reference.
         fac_index = cond_fn.current_timestep
+        # reduce_clip (cgd/cgd.py:157-164): on the steps its rule skips, cond_fn returns zeros -- no cutout windows are drawn, CLIP
+        # and both backward passes have nothing to do, the sampler takes its unguided update.  Those steps replay a second, short
+        # graph (UNet forward -> p_mean_variance -> update), which is where the option's speed-up comes from.
+        guided = not cond_fn.skips_guidance()
         if mode == "ancestral":
             self.draw_noise()
-        coords = cond_fn.next_coords(self.H, self.W)
+        coords = cond_fn.next_coords(self.H, self.W) if guided else []
         if mode != "ancestral":
             self.draw_noise()
         sc = diffusion.scalar_table(t_index, fac_index, eta)
@@ -557,12 +584,36 @@ class GuidedStepB200:
         xin = self.img(self.unet.x_in)
         if img.data_ptr() != xin.data_ptr():
             xin.copy_(img, non_blocking=True)
-        self.replay(mode, len(coords) if self.cutn else None)
+        self.replay(mode, len(coords) if (self.cutn and guided) else None, guided=guided)
         return {"sample": self.img(self.sample).clone(), "pred_xstart": self.img(self.x0).clone()}
 
-    def replay(self, mode, cutn=None):
+    def _run_unguided(self, mode, pr=None):
+        """a step whose guidance gradient is zero (reduce_clip's skipped steps): UNet forward, p_mean_variance, plain update"""
+        pr = pr or self.plan.run_range
+        pr("unet_emb", "unet_bwd")
+        pr("pmv", "cond")
+        if mode == "ancestral":
+            pr("upd_anc", "upd_ddim_g")
+        else:
+            pr("upd_ddim", "engine_end")
+
+    def replay(self, mode, cutn=None, guided=True):
         if cutn == self.cutn:
             cutn = None
+        if not guided:
+            if not self.use_graph:
+                self._run_unguided(mode)
+                return
+            g = self._graphs.get((mode, "unguided"))
+            if g is None:
+                self._run_unguided(mode)
+                th.cuda.synchronize()
+                g = th.cuda.CUDAGraph()
+                with th.cuda.graph(g):
+                    self._run_unguided(mode)
+                self._graphs[(mode, "unguided")] = g
+            g.replay()
+            return
         if not self.use_graph:
             self._run_all(mode, None, cutn)
             return
@@ -636,7 +687,16 @@ class CondFnB200:
         return lo if pct < 0.3 else (mid if pct < 0.7 else hi)
 
     def fusable(self):
-        return not self.reduce_clip
+        return True
+
+    def skips_guidance(self) -> bool:
+        """reduce_clip's rule (cgd/cgd.py:157-164): below 70 % progress CLIP guidance runs on every 4th step only (the first 20 % are
+        skipped altogether through skip_timesteps, cgd/cgd.py:141-144); on the other steps cond_fn returns zeros"""
+        if not self.reduce_clip:
+            return False
+        total = self.diffusion.num_timesteps
+        pct = (total - self.current_timestep) / total
+        return pct < 0.7 and int((pct - 0.2) * total) % 4 != 0
 
     def step_done(self):  # cgd/cgd.py:267
         self.current_timestep -= 1
@@ -649,10 +709,7 @@ class CondFnB200:
         if out.get("engine") is not eng:
             raise RuntimeError("cond_fn: `out` must come from this engine's p_mean_variance (the UNet backward re-enters its saved "
                                "activations)")
-        if self.reduce_clip:  # cgd/cgd.py:157-164
-            total = self.diffusion.num_timesteps
-            pct = (total - self.current_timestep) / total
-            if pct < 0.7 and int((pct - 0.2) * total) % 4 != 0:
-                return th.zeros_like(x)
+        if self.skips_guidance():  # cgd/cgd.py:157-164
+            return th.zeros_like(x)
         coords = self.next_coords(x.shape[2], x.shape[3])
         return eng.cond_grad(self.diffusion, coords, self.current_timestep)

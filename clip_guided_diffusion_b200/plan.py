@@ -773,6 +773,9 @@ class Plan:
         self.arena = th.zeros(nbytes, dtype=th.uint8, device=device)
         for b, t in self._consts:
             self.arena[b.off:b.off + b.nbytes].copy_(t.view(-1).view(th.uint8))
+        # the host copies (2.3 GB for the 256x256 UNet) are not kept: the index is what `reload_consts` needs to re-pack a checkpoint
+        self.const_index = [(b.name, b.off, b.nbytes) for b, _ in self._consts]
+        self._consts = []
         self._consts_done = True
         if device.type != "cuda":
             return self
@@ -782,6 +785,29 @@ class Plan:
         _lib.check(lib.cgd_plan_create(arr, len(self.ops), ctypes.byref(h)), "cgd_plan_create")
         self.handle, self._c_ops = h, arr
         return self
+
+    def reload_consts(self, shadow: "Plan", first: int = 0) -> int:
+        """Overwrite this (finalized) plan's packed constants with those of `shadow` -- a plan built by the same constructor calls
+        from another state_dict and never finalized -- starting at constant number `first`.  Names, offsets and sizes must agree
+        one by one (same network, same shapes, same packing decisions); nothing else of the arena is touched, op lists, TMA
+        descriptors and captured CUDA graphs stay valid (they hold addresses, not values).  Returns the number re-loaded."""
+        if self.arena is None:
+            raise RuntimeError("reload_consts: the plan is not finalized")
+        new = shadow._consts
+        if first + len(new) > len(self.const_index):
+            raise ValueError(f"reload_consts: {len(new)} constants from #{first} exceed the plan's {len(self.const_index)}")
+        base = shadow_off = None
+        for j, (b, t) in enumerate(new):
+            name, off, nbytes = self.const_index[first + j]
+            if base is None:
+                base, shadow_off = off, b.off
+            if (b.name, b.nbytes, b.off - shadow_off) != (name, nbytes, off - base):
+                raise ValueError(f"reload_consts: constant #{first + j} is {name!r} ({nbytes} B at +{off - base}) in the plan but "
+                                 f"{b.name!r} ({b.nbytes} B at +{b.off - shadow_off}) in the new pack: different architecture or flags")
+        for j, (b, t) in enumerate(new):
+            _, off, nbytes = self.const_index[first + j]
+            self.arena[off:off + nbytes].copy_(t.view(-1).view(th.uint8), non_blocking=False)
+        return len(new)
 
     def view(self, b: Buf, shape=None) -> th.Tensor:
         t = self.arena[b.off:b.off + b.nbytes].view(_DT[b.dt][1])

@@ -106,3 +106,37 @@ def test_loop_without_per_step_sync_equals_synced_run(resize):
         finals.append((out["sample"].float().cpu(), out["pred_xstart"].float().cpu()))
     (s0, p0), (s1, p1) = finals
     assert th.isfinite(s0).all() and rel(s1, s0) < 1e-5 and rel(p1, p0) < 1e-5, (rel(s1, s0), rel(p1, p0))
+
+
+@pytest.mark.parametrize("mode", ["ancestral", "ddim"])
+def test_reduce_clip_fused_graphs_equal_segment_path(mode):
+    """reduce_clip on the device (cgd/cgd.py:141-144, 157-164): the fused path replays two CUDA graphs -- the full guided step and the
+    short unguided one (UNet forward -> p_mean_variance -> update) on the steps the rule skips -- and must reproduce the segment path
+    (p_mean_variance -> cond_fn returning zeros / the gradient -> update, eager launches) over the whole chain."""
+    from clip_guided_diffusion_b200 import guidance as pg
+    from tests.step_parity import build_tiny
+    ctx = build_tiny("cuda:0", B=2, cutn=3, image=64, use_magnitude=True, use_graph=True)
+    eng, pdiff = ctx["eng"], ctx["pdiff"]
+    T = pdiff.num_timesteps
+    skip = int(T * 0.2)
+    loop = pdiff.p_sample_loop_progressive if mode == "ancestral" else pdiff.ddim_sample_loop_progressive
+    finals, kinds = [], []
+    for fused in (True, False):
+        th.manual_seed(7)
+        cond = pg.CondFnB200(eng, pdiff, pg.MakeCutouts(32, 3), reduce_clip=True)
+        if not fused:
+            eng.can_fuse = lambda *a, **k: False
+        else:
+            orig = eng.replay
+            eng.replay = lambda m, cutn=None, guided=True: (kinds.append(guided), orig(m, cutn, guided=guided))[1]
+        out, n = None, 0
+        for out in loop(eng.model, eng.shape, clip_denoised=False, cond_fn=cond, model_kwargs={"y": th.zeros(2, dtype=th.long, device="cuda")},
+                        randomize_class=True, cond_fn_with_grad=True, skip_timesteps=skip):
+            cond.step_done()
+            n += 1
+        th.cuda.synchronize()
+        assert n == T - skip
+        finals.append((out["sample"].float().cpu(), out["pred_xstart"].float().cpu()))
+    assert 0 < sum(kinds) < len(kinds) == T - skip and (("ancestral", "unguided") in eng._graphs or ("ddim", "unguided") in eng._graphs)
+    (s0, p0), (s1, p1) = finals
+    assert th.isfinite(s0).all() and rel(s0, s1) < 1e-3 and rel(p0, p1) < 1e-3, (rel(s0, s1), rel(p0, p1))

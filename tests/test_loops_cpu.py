@@ -65,12 +65,20 @@ def test_sampling_loops_follow_the_reference_draw_order(mode, fused, skip):
         assert rel(se, so) < 2e-2 and rel(xe, xo) < 2e-2, (k, rel(se, so), rel(xe, xo))
 
 
-def test_reduce_clip_schedule_matches_the_reference_rule():
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_step", "segments"])
+def test_reduce_clip_schedule_matches_the_reference_rule(fused):
     """reduce_clip (cgd/cgd.py:141-144, 157-164): the first 20 % of the steps are skipped through skip_timesteps, up to 70 % CLIP
-    guidance runs on every 4th step and cond_fn returns zeros otherwise (the sampler then takes an unguided step)."""
+    guidance runs on every 4th step and cond_fn returns zeros otherwise (the sampler then takes an unguided step).  Fused path: the
+    skipped steps run the short op list (UNet forward -> p_mean_variance -> unguided update), on a GPU a second CUDA graph."""
     B, cutn, image = 1, 2, 32
     ctx = build_tiny("cpu", B=B, cutn=cutn, image=image, use_magnitude=True)
     eng = _interpreted(ctx)
+    ran = []
+    if fused:
+        orig = eng.replay
+        eng.replay = lambda mode, cutn=None, guided=True: (ran.append(guided), orig(mode, cutn, guided=guided))[1]
+    else:
+        eng.can_fuse = lambda *a, **k: False
     pdiff, odiff = ctx["pdiff"], ctx["odiff"]
     T = pdiff.num_timesteps
     skip = int(T * 0.2)
@@ -102,5 +110,7 @@ def test_reduce_clip_schedule_matches_the_reference_rule():
         cond.step_done()
     assert th.equal(th.get_rng_state(), state)  # skipped steps draw no cutout windows on either side
     assert len(outs_e) == len(outs_o) == T - skip and 0 < sum(guided) < len(guided)
+    if fused:
+        assert ran == guided  # the engine replayed the unguided op list exactly on the steps the reference's rule skips
     worst = max(rel(a, b) for a, b in zip(outs_e, outs_o))
     assert worst < 3e-2, worst

@@ -167,3 +167,41 @@ def test_groupnorm_from_conv_epilogue_statistics():
     ref = F.group_norm(h1.permute(0, 3, 1, 2), 32, gamma_t, beta_t, eps=1e-5) * (1 + e[:, :C, None, None]) + e[:, C:, None, None]
     ref = F.silu(ref).permute(0, 2, 3, 1)
     assert float((y1 - ref).abs().max()) < 4e-3 * float(ref.abs().max())
+
+
+def test_engine_model_load_state_dict_repacks_in_place():
+    """cgd/script_util.py:317: `model.load_state_dict(checkpoint)` on the engine's UNet handle re-packs the checkpoint into the
+    kernel layouts in place: the arena must equal, byte for byte, the arena of an engine CONSTRUCTED from that checkpoint."""
+    import pytest
+    from clip_guided_diffusion_b200 import weights as pw
+    from tests.step_parity import build_tiny
+    a = build_tiny("cpu", B=1, cutn=2, image=32)["eng"]
+    b = build_tiny("cpu", B=1, cutn=2, image=32)["eng"]
+    sd2 = pw.seeded_state_dict(pw.unet_param_shapes(a.unet.cfg), seed=4321)  # other weights, same architecture (upstream keys)
+    before = a.plan.arena.clone()
+    res = a.model.load_state_dict(sd2)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert not th.equal(a.plan.arena, before)
+    b.model.load_state_dict(sd2)
+    assert th.equal(a.plan.arena, b.plan.arena)
+    # and equal to construction from sd2: compare the forward through the interpreter against the oracle loaded with sd2
+    from oracle.unet import UNetModel
+    from tests.plan_interp import Interp
+    from tests.step_parity import tiny_config
+    ocfg = tiny_config(image_size=32, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(16,), class_cond=True,
+                       use_new_attention_order=False)
+    ounet = UNetModel(ocfg).eval()
+    ounet.load_state_dict(sd2)
+    th.manual_seed(0)
+    x, t, y = th.randn(1, 3, 32, 32), th.tensor([500.0]), th.tensor([3])
+    a.unet.set_inputs(x, t, y)
+    it = Interp(a.plan)
+    it.run_range("unet_emb", "unet_bwd")
+    got = a.unet.out_view.float()
+    ref = ounet(x, t, y).detach()
+    assert float((got - ref).norm() / ref.norm()) < 2e-2
+    with pytest.raises(RuntimeError, match="missing"):
+        a.model.load_state_dict({k: v for k, v in sd2.items() if k != "out.2.weight"})
+    with pytest.raises(RuntimeError, match="unexpected"):
+        a.model.load_state_dict({**sd2, "bogus.weight": th.zeros(1)})
+    assert a.model.load_state_dict({**sd2, "bogus.weight": th.zeros(1)}, strict=False).unexpected_keys == ["bogus.weight"]
