@@ -2,7 +2,7 @@
 
 Same keyword arguments and the same generator contract (yields ``(batch_idx, png_path)``); set-up stays Python and
 runs once (seed, prompt encoding, weight loading, cutout cache), the per-timestep work is the engine's fused step.
-Out of scope here, exactly as SURVEY.md section 2 marks them: checkpoint download, W&B, GIF/MP4, torchvision augmentations,
+Out of scope here, exactly as SURVEY.md section 2 marks them: checkpoint download, W&B, GIF/MP4,
 image prompts (the reference's ``encode_image_prompt`` crashes, quirk B5).  The LPIPS init loss (``init_image`` + ``init_scale``)
 runs on the engine when the VGG weights are given (``lpips_state_dict=``) or the ``lpips`` package is installed.
 
@@ -187,7 +187,7 @@ def clip_guided_diffusion(
                             world_size=world_size,
                             cutn_variants=tuple(c for c in counts if c != max(counts)),
                             lpips_sd=_lpips_sd(lpips_state_dict) if (init_image is not None and init_scale != 0) else None,
-                            init_scale=init_scale, cutout_resize=cutout_resize)
+                            init_scale=init_scale, cutout_resize=cutout_resize, use_augs=use_augs)
     engine.set_targets(target_embeds, weights)
     make_cutouts = MakeCutouts(cut_size=vit_cfg.input_resolution, num_cutouts=num_cutouts, cutout_size_power=cutout_power, use_augs=use_augs)
     if cached_cutouts:

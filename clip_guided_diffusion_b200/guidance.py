@@ -30,12 +30,12 @@ class MakeCutouts(th.nn.Module):
 
     def __init__(self, cut_size: int, num_cutouts: int, cutout_size_power: float = 1.0, use_augs: bool = False):
         super().__init__()
-        if use_augs:
-            raise NotImplementedError("torchvision augmentations are outside the B200 hot path (the reference CLI hard-disables "
-                                      "them, cgd/cgd.py:402)")
         self.cut_size, self.cutn, self.cut_pow = cut_size, num_cutouts, cutout_size_power
         self.cached_coords = None
-        self.augs = th.nn.Identity()  # the reference's empty tvt.Compose([]) when use_augs is off (cgd/modules.py:24)
+        # use_augs (cgd/modules.py:12-24): flip / affine / perspective / grayscale / noise run inside the cutout kernels
+        # (csrc/augs.cu) from parameters drawn in torchvision's order (augs.py); `augs` stays an attribute like the reference's
+        self.use_augs = bool(use_augs)
+        self.augs = th.nn.Identity()
 
     def _generate_coords(self, side_x: int, side_y: int, cutn: int):
         max_size = min(side_y, side_x)
@@ -71,9 +71,25 @@ class MakeCutouts(th.nn.Module):
         x = input.detach().float().contiguous()
         cdev = th.tensor(coords, dtype=th.int32, device=x.device)
         out = th.empty(len(coords) * B, 1, 3 * cs * cs, dtype=th.float16, device=x.device)
+        lib = _lib.load()
+        if self.use_augs:  # the reference applies its augmentations to the raw cutout values: feed 2x - 1, mean 0 / std 1
+            from . import augs
+            Smax = min(H, W)
+            noise = th.zeros(len(coords), 4, B, 3, Smax, Smax, device=x.device)
+            prm = augs.draw_aug_params(coords, B, H, W, noise_device=x.device, noise_out=noise).to(x.device)
+            xin = x * 2 - 1
+            op = _lib.CgdOp()
+            op.code = _lib.OP["CUTOUTS_AUG_FWD"]
+            for j, v in enumerate([B, H, W, len(coords), cs, cs, 3 * cs * cs, Smax]):
+                op.i[j] = v
+            for j, v in enumerate([0.0, 0.0, 0.0, 1.0, 1.0, 1.0]):
+                op.f[j] = v
+            for j, t in enumerate([xin, cdev, out, prm, noise]):
+                op.p[j] = t.data_ptr()
+            _lib.check(lib.cgd_run_op(ctypes.byref(op), ctypes.c_void_p(th.cuda.current_stream().cuda_stream)), "cutouts_aug_fwd")
+            return out.view(len(coords) * B, 3, cs, cs).float()
         mean = (ctypes.c_float * 3)(0.5, 0.5, 0.5)  # with std 0.5 and the kernel's (x+1)/2 this yields the raw pooled value
         std = (ctypes.c_float * 3)(0.5, 0.5, 0.5)
-        lib = _lib.load()
         # patch = cut_size -> a single "patch" per cutout whose (c, ky, kx) order is exactly CHW
         rc = lib.cgd_cutouts_fwd(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(cdev.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                  ctypes.c_int64(B), ctypes.c_int64(H), ctypes.c_int64(W), ctypes.c_int64(len(coords)),
@@ -147,7 +163,8 @@ class GuidedStepB200:
                  height: int = None, width: int = None, num_cutouts: int = 16, max_prompts: int = 1, clip_guidance_scale=1000.0,
                  tv_scale=150.0, range_scale=50.0, sat_scale=0.0, use_magnitude=False, device="cuda", seed_scale=0.0,
                  vit_grad_scale=1.0, conv_impl=0, rank: int = 0, world_size: int = 1, use_graph: bool = True, vit_streams: int = 1,
-                 cutn_variants: tuple = (), lpips_sd: dict = None, init_scale: float = 0.0, cutout_resize: str = "pool"):
+                 cutn_variants: tuple = (), lpips_sd: dict = None, init_scale: float = 0.0, cutout_resize: str = "pool",
+                 use_augs: bool = False):
         self.device = th.device(device)
         self.B = batch
         self.rank, self.world = rank, world_size
@@ -182,6 +199,7 @@ class GuidedStepB200:
         p.mark("cond")
         self.vit = None
         self.lpips = None
+        self.use_augs = False
         if vit_cfg is not None:
             cutn, cs, ps, kp, D = self.cutn, vit_cfg.input_resolution, vit_cfg.patch_size, vit_cfg.kpad, vit_cfg.output_dim
             self.vit_cfg = vit_cfg
@@ -202,6 +220,14 @@ class GuidedStepB200:
             if cutout_resize not in ("pool", "lanczos3"):
                 raise ValueError("cutout_resize must be 'pool' or 'lanczos3'")
             self.cutout_resize = cutout_resize
+            self.use_augs = bool(use_augs)
+            if self.use_augs:
+                if cutout_resize != "pool":
+                    raise NotImplementedError("use_augs runs with the reference's adaptive_avg_pool2d cutouts (cutout_resize='pool')")
+                from .augs import AUG_NP
+                self.aug_smax = min(H, W)
+                self.aug_prm = p.new(cutn * AUG_NP, "f", "aug_params")
+                self.aug_noise = p.new(cutn * 4 * B * 3 * self.aug_smax * self.aug_smax, "f", "aug_noise")
             if cutout_resize == "lanczos3":
                 if H != W or cutn_variants:
                     raise NotImplementedError("ResizeRight cutouts: square images and a single cutout count only")
@@ -221,6 +247,10 @@ class GuidedStepB200:
                     p.emit("CUTOUTS_RR_FWD", i=[B, H, W, c, cs, ps, kp], f=[*CLIP_MEAN, *CLIP_STD],
                            p=[(self.x_inb, 0), (self.coords, 0), (vt.patches, 0), (self.rr_left, 0), (self.rr_w, 0), (self.rr_taps, 0)],
                            tag="make_cutouts(resize_right lanczos3)+normalize")
+                elif self.use_augs:
+                    p.emit("CUTOUTS_AUG_FWD", i=[B, H, W, c, cs, ps, kp, self.aug_smax], f=[*CLIP_MEAN, *CLIP_STD],
+                           p=[(self.x_inb, 0), (self.coords, 0), (vt.patches, 0), (self.aug_prm, 0), (self.aug_noise, 0)],
+                           tag="make_cutouts(use_augs)+normalize")
                 else:
                     p.emit("CUTOUTS_FWD", i=[B, H, W, c, cs, ps, kp], f=[*CLIP_MEAN, *CLIP_STD], p=[(self.x_inb, 0), (self.coords, 0), (vt.patches, 0)],
                            tag="make_cutouts+normalize")
@@ -232,6 +262,10 @@ class GuidedStepB200:
                     p.emit("CUTOUTS_RR_BWD", i=[B, H, W, c, cs, ps, kp, H], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
                            p=[(vt.d_patches, 0), (self.coords, 0), (self.g_clip, 0), (self.rr_left, 0), (self.rr_w, 0), (self.rr_inv, 0)],
                            tag="d_make_cutouts(resize_right)")
+                elif self.use_augs:
+                    p.emit("FILL", i=[n3], f=[0.0], p=[(self.g_clip, 0)], tag="zero g_clip")
+                    p.emit("CUTOUTS_AUG_BWD", i=[B, H, W, c, cs, ps, kp], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
+                           p=[(vt.d_patches, 0), (self.coords, 0), (self.g_clip, 0), (self.aug_prm, 0)], tag="d_make_cutouts(use_augs)")
                 else:
                     p.emit("CUTOUTS_BWD", i=[B, H, W, c, cs, ps, kp], f=[0, 0, 0, *CLIP_STD, 1.0 / self.vit_grad_scale],
                            p=[(vt.d_patches, 0), (self.coords, 0), (self.g_clip, 0)], tag="d_make_cutouts")
@@ -277,7 +311,7 @@ class GuidedStepB200:
         self.model = EngineModel(self)
         self.shape = (B, 3, H, W)
         # pinned staging for the per-step host->device refresh
-        self._n_stage = SC["COUNT"] * 4 + self.cutn * 3 * 4 + B * 4 + B * 8
+        self._n_stage = SC["COUNT"] * 4 + self.cutn * 3 * 4 + B * 4 + B * 8 + self.cutn * 20 * 4
         # The host runs ahead of the GPU (a step is ~1 ms of host work and ~10 ms of device work, and nothing synchronises between
         # saved frames), so the async copies of step k may still be queued when the host stages step k+1: the pinned buffers are a
         # ring of STAGE_SLOTS slots, each guarded by the event recorded after its copies were enqueued.
@@ -388,6 +422,8 @@ class GuidedStepB200:
         sfx = self._sfx(cutn)
         self.v(self.coords, (self.cutn, 3))[:cutn].copy_(th.tensor(coords, dtype=th.int32), non_blocking=True)
         self._stage_resize_tables(coords)
+        if self.use_augs:
+            self._stage_augs(coords)
         self.plan.run_range("cut_fwd" + sfx, "sph" + sfx)
         self._run_vit("fwd", None, cutn)
         self.plan.run_range("sph" + sfx, "cut_bwd" + sfx)
@@ -533,8 +569,27 @@ class GuidedStepB200:
             st[o:o + n].view(th.int32).copy_(th.tensor(coords, dtype=th.int32).view(-1))
             self.v(self.coords).view(th.uint8)[:n].copy_(st[o:o + n], non_blocking=True)
             self.h2d_bytes += n
+            o += self.cutn * 12
             self._stage_resize_tables(coords, k)
+            if getattr(self, "use_augs", False):
+                self._stage_augs(coords, st, o)
         self._stage_release(k)
+
+    def _stage_augs(self, coords, st=None, o=0):
+        """use_augs: this step's flip / affine / perspective / grayscale parameters (CPU generator, torchvision's order) and the four
+        noise fields per cutout (device generator, the reference's shapes; full batch drawn, own rows kept when sharded)"""
+        from . import augs
+        n = len(coords) * augs.AUG_NP * 4
+        noise = self.v(self.aug_noise, (self.cutn, 4, self.B, 3, self.aug_smax, self.aug_smax))
+        rows = None if self.world == 1 else (self.rank * self.B, (self.rank + 1) * self.B)
+        prm = augs.draw_aug_params(coords, self.global_batch, self.H, self.W, noise_device=self.device, noise_out=noise, rows=rows)
+        dst = self.v(self.aug_prm).view(th.uint8)[:n]
+        if st is None:
+            dst.copy_(prm.view(-1).view(th.uint8))
+        else:
+            st[o:o + n].view(th.float32).copy_(prm.view(-1))
+            dst.copy_(st[o:o + n], non_blocking=True)
+        self.h2d_bytes += n
 
     def _stage_resize_tables(self, coords, slot=None):
         """ResizeRight mode: per-cutout resampling tables of this step's crop sizes (cached per size on the host) -> device"""

@@ -37,14 +37,40 @@ def clip_normalize(x):  # cgd/clip_util.py:45 (torchvision Normalize)
     return (x - mean) / std
 
 
+def apply_augs(cut, prm, noise=None):
+    """The reference's ``self.augs(cutout)`` (cgd/modules.py:12-24, 62) with EXPLICIT randomness: ``prm`` = the 20 numbers
+    clip_guided_diffusion_b200/augs.py draws per cutout in torchvision's order (flip | inverse affine matrix | perspective on |
+    coefficients | grayscale), ``noise`` = the four N(0, .01^2) fields [4, B, 3, S, S] (None: none).  The image operations are
+    torchvision's own functional kernels -- the ones RandomAffine / RandomPerspective / RandomGrayscale call -- so this IS the
+    reference pipeline, only with the random draws lifted out (pinned against cgd.modules.MakeCutouts(use_augs=True) itself in
+    tests/test_oracle.py)."""
+    import torchvision.transforms._functional_tensor as FT
+    prm = [float(v) for v in prm]
+    fill = [0.0, 0.0, 0.0]
+
+    def nz(k, x):
+        return x if noise is None else x + noise[k]
+
+    x = cut.flip(-1) if prm[0] else cut
+    x = nz(0, x)
+    x = FT.affine(x, matrix=prm[1:7], interpolation="nearest", fill=fill)
+    x = nz(1, x)
+    if prm[7]:
+        x = FT.perspective(x, prm[8:16], interpolation="bilinear", fill=fill)
+    x = nz(2, x)
+    if prm[16]:
+        x = FT.rgb_to_grayscale(x, num_output_channels=3)
+    return nz(3, x)
+
+
 class MakeCutouts(th.nn.Module):
-    """cgd/modules.py:5-66 without the (CLI-disabled) torchvision augmentations."""
+    """cgd/modules.py:5-66; the torchvision augmentations (use_augs) with explicit parameters through ``apply_augs``."""
 
     def __init__(self, cut_size, num_cutouts, cutout_size_power=1.0, use_augs=False):
         super().__init__()
-        assert not use_augs, "oracle covers the augmentation-free path (CLI hard-disables augs, cgd/cgd.py:402)"
         self.cut_size, self.cutn, self.cut_pow = cut_size, num_cutouts, cutout_size_power
         self.cached_coords = None
+        self.use_augs = use_augs
 
     def _generate_coords(self, side_x, side_y, cutn):  # modules.py:38-48; CPU default generator, 3 draws/cutout
         max_size = min(side_y, side_x)
@@ -62,7 +88,8 @@ class MakeCutouts(th.nn.Module):
 
     resize = "pool"  # "lanczos3": the ResizeRight mode named by north_star (oracle/resize_right.py) instead of the reference's pooling
 
-    def forward(self, x, use_cache=False, num_cutouts_override=None, coords=None):
+    def forward(self, x, use_cache=False, num_cutouts_override=None, coords=None, aug_params=None, aug_noise=None):
+        """aug_params [cutn, 20] (+ aug_noise [cutn, 4, B, 3, Smax, Smax]): the use_augs pipeline with explicit randomness"""
         cutn = num_cutouts_override if num_cutouts_override is not None else self.cutn
         side_x, side_y = x.shape[2:4]  # sic: (H, W) named (x, y), modules.py:52 (quirk B3)
         if coords is None:
@@ -73,13 +100,20 @@ class MakeCutouts(th.nn.Module):
         if self.resize == "lanczos3":
             from .resize_right import resize_lanczos3
             return th.cat([resize_lanczos3(x[:, :, oy:oy + s, ox:ox + s], (self.cut_size, self.cut_size)) for ox, oy, s in coords])
+        if aug_params is not None:
+            outs = []
+            for k, (ox, oy, s) in enumerate(coords):
+                cut = x[:, :, oy:oy + s, ox:ox + s]
+                nz = None if aug_noise is None else aug_noise[k][..., :cut.shape[-2], :cut.shape[-1]]
+                outs.append(F.adaptive_avg_pool2d(apply_augs(cut, aug_params[k], nz), self.cut_size))
+            return th.cat(outs)
         outs = [F.adaptive_avg_pool2d(x[:, :, oy:oy + s, ox:ox + s], self.cut_size) for ox, oy, s in coords]
         return th.cat(outs)
 
 
 def guidance_loss(x, pred_xstart, fac, coords, clip_model, target_embeds, weights, *, cut_size,
                   clip_guidance_scale=1000.0, tv_scale=150.0, range_scale=50.0, sat_scale=0.0,
-                  lpips_model=None, init_tensor=None, init_scale=0.0, cutout_resize="pool"):
+                  lpips_model=None, init_tensor=None, init_scale=0.0, cutout_resize="pool", aug_params=None, aug_noise=None):
     """The differentiable body of cond_fn (cgd/cgd.py:177-226) with explicit cutout coordinates; the LPIPS term
     (cgd/cgd.py:220-224) when ``lpips_model`` (oracle/lpips.py) and ``init_tensor`` are given.
     Returns (total_loss, dict of per-term scalars)."""
@@ -88,7 +122,7 @@ def guidance_loss(x, pred_xstart, fac, coords, clip_model, target_embeds, weight
     x_in = pred_xstart * fac + x * (1 - fac)
     mk = MakeCutouts(cut_size, cutn)
     mk.resize = cutout_resize
-    clip_in = clip_normalize(mk(x_in.add(1).div(2), coords=coords))
+    clip_in = clip_normalize(mk(x_in.add(1).div(2), coords=coords, aug_params=aug_params, aug_noise=aug_noise))
     embeds = clip_model.encode_image(clip_in).float().view([cutn, n, -1])
     dists = spherical_dist_loss(embeds.unsqueeze(0), target_embeds.unsqueeze(0)).view([cutn, n, -1])
     clip_l = dists.mul(weights).sum(2).mean(0).sum() * clip_guidance_scale
@@ -135,13 +169,13 @@ class OracleCondFn:
     def step_done(self):
         self.current_timestep -= 1
 
-    def __call__(self, x, t, out, y=None, coords=None):
+    def __call__(self, x, t, out, y=None, coords=None, aug_params=None, aug_noise=None):
         fac = float(self.diffusion.sqrt_one_minus_alphas_cumprod[self.current_timestep])
         if coords is None:
             coords = self.mk._generate_coords(x.shape[2], x.shape[3], self.mk.cutn)
         self.last_coords = coords
         loss, terms = guidance_loss(x, out["pred_xstart"], fac, coords, self.clip_model, self.target_embeds,
-                                    self.weights, **self.kw)
+                                    self.weights, aug_params=aug_params, aug_noise=aug_noise, **self.kw)
         # the reference logs the loss terms with .item() every step (cgd/cgd.py:234-236: three host syncs); log_items=False keeps
         # them on the device (bench.py times the PyTorch-CUDA arm both ways)
         self.last_terms = {k: float(v.detach()) for k, v in terms.items()} if self.log_items else {k: v.detach() for k, v in terms.items()}

@@ -14,7 +14,7 @@ OUT_PTRS = {"CONV": [4, 7], "GN_STATS": [2], "GN_APPLY": [5], "GN_BWD_STATS": [7
             "CUTOUTS_BWD": [2], "SPHERICAL": [3, 4], "PMV_BLEND": [3, 4, 5, 6, 7], "GUIDE_GRAD": [4, 5, 6, 7, 8], "FINAL_GRAD": [2, 4], "SEED_QUANT": [1, 2], "MAG_CLAMP": [0], "GN_APPLY_EPI": [4, 5], "ATTNPOOL_EMBED_FWD": [2], "ATTNPOOL_EMBED_BWD": [1],
             "SAMPLE_ANCESTRAL": [6], "SAMPLE_DDIM": [5], "TRANSPOSE": [1, 3, 5], "SOFTMAX_FWD": [0, 1], "SOFTMAX_BWD": [1],
             "GN_FWD_FUSED": [4, 5], "GN_BWD_FUSED": [6], "GN_FWD_GRID": [4, 5], "GN_BWD_GRID": [6],
-            "RELU_FWD": [1], "RELU_BWD": [2], "MAXPOOL2_FWD": [1], "MAXPOOL2_BWD": [2], "LPIPS_TAP": [3, 4], "FILL": [0], "CUTOUTS_RR_FWD": [2], "CUTOUTS_RR_BWD": [2]}
+            "CUTOUTS_AUG_FWD": [2], "CUTOUTS_AUG_BWD": [2], "RELU_FWD": [1], "RELU_BWD": [2], "MAXPOOL2_FWD": [1], "MAXPOOL2_BWD": [2], "LPIPS_TAP": [3, 4], "FILL": [0], "CUTOUTS_RR_FWD": [2], "CUTOUTS_RR_BWD": [2]}
 
 
 def cpu_twin(plan):
@@ -54,6 +54,10 @@ def compare_ops(plan, ranges, tol_h=4e-3, tol_f=2e-4, verbose=False):
                 err = float((ref - got).abs().max()) / scale
                 bad = not th.isfinite(got).all()
                 tol = tol_h if buf.dt == "h" else tol_f
+                if name.startswith("CUTOUTS_AUG"):
+                    # nearest-neighbour sampling: a source coordinate within float round-off of .5 may pick the other pixel than
+                    # torchvision's grid does (a handful of pixels per cutout) -- judged by the L2 error, not the worst element
+                    err, tol = float((ref - got).norm() / (ref.norm() + 1e-20)), 1e-2
                 if name in ("ATTN_FWD", "ATTN_BWD", "SPHERICAL", "GN_BWD_APPLY", "GN_BWD_STATS", "GN_BWD_FUSED", "GN_BWD_GRID", "LN_BWD", "CUTOUTS_BWD", "CUTOUTS_RR_BWD", "SOFTMAX_FWD", "SOFTMAX_BWD"):
                     tol = max(tol, 4e-3)
                 if verbose or bad or err > tol:

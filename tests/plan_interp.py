@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import math
 
+import copy
+
 import torch as th
 import torch.nn.functional as F
 
@@ -461,6 +463,44 @@ class Interp:
         cuts = th.cat([F.adaptive_avg_pool2d(x[:, :, oy:oy + s, ox:ox + s], cs) for ox, oy, s in self._coords(op)])
         (gx,) = th.autograd.grad(((cuts + 1) * 0.5 / std * dimg).sum(), x)
         self.V(op.p[2], (B, 3, H, W), (3 * H * W, H * W, W, 1)).copy_(gx * op.f[6])
+
+    def _aug_cuts(self, op, x):
+        """use_augs cutouts of x [B,3,H,W] (values in [0, 1]) with the op's device parameters / noise: torchvision's own kernels"""
+        from oracle.guidance import apply_augs
+        B, H, W, cutn, cs = op.i[:5]
+        prm = self.V(op.p[3], (cutn, 20), (20, 1))
+        Smax = op.i[7] if len(op.i) > 7 and op.i[7] else min(H, W)
+        nz = self.V(op.p[4], (cutn, 4, B, 3, Smax, Smax), (4 * B * 3 * Smax * Smax, B * 3 * Smax * Smax, 3 * Smax * Smax, Smax * Smax, Smax, 1)) \
+            if len(op.p) > 4 and op.p[4] is not None else None
+        cuts = []
+        for k, (ox, oy, s) in enumerate(self._coords(op)):
+            cut = x[:, :, oy:oy + s, ox:ox + s]
+            n4 = None if nz is None else nz[k][..., :cut.shape[-2], :cut.shape[-1]]
+            cuts.append(F.adaptive_avg_pool2d(apply_augs(cut, prm[k], n4), cs))
+        return th.cat(cuts)
+
+    def op_CUTOUTS_AUG_FWD(self, op):
+        B, H, W, cutn, cs, P, kpad = op.i[:7]
+        x = self.V(op.p[0], (B, 3, H, W), (3 * H * W, H * W, W, 1))
+        mean = th.tensor(op.f[0:3]).view(1, 3, 1, 1)
+        std = th.tensor(op.f[3:6]).view(1, 3, 1, 1)
+        img = (self._aug_cuts(op, (x + 1) * 0.5) - mean) / std
+        g2 = (cs // P) ** 2
+        self.V(op.p[2], (cutn * B, g2, kpad), (g2 * kpad, kpad, 1)).copy_(self._patchify(img, P, kpad))
+
+    def op_CUTOUTS_AUG_BWD(self, op):
+        B, H, W, cutn, cs, P, kpad = op.i[:7]
+        g2 = (cs // P) ** 2
+        dp = self.V(op.p[0], (cutn * B, g2, kpad), (g2 * kpad, kpad, 1)).float()
+        dimg = self._unpatchify(dp, P, cs)
+        std = th.tensor(op.f[3:6]).view(1, 3, 1, 1)
+        x = th.zeros(B, 3, H, W, requires_grad=True)
+        op_nonoise = copy.copy(op)
+        op_nonoise.p = list(op.p[:4]) + [None]  # the noise is additive: it does not enter the gradient
+        cuts = self._aug_cuts(op_nonoise, (x + 1) * 0.5)
+        (gx,) = th.autograd.grad((cuts / std * dimg).sum(), x)
+        dst = self.V(op.p[2], (B, 3, H, W), (3 * H * W, H * W, W, 1))
+        dst.add_(gx * op.f[6])  # scatter-add into a zeroed buffer (CGD_OP_FILL precedes it)
 
     def _rr_resize(self, op, crop, k):
         """separable resample of crop [B,3,S,S] with cutout k's device tables (left, weights, taps): zero outside the crop"""

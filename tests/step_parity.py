@@ -31,7 +31,7 @@ def prod_unet_cfg(ocfg):
 
 
 def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0, respacing="25", conv_impl=0, use_graph=False, P=1,
-               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None, hw=None, rank=0, world_size=1, tower="vit"):
+               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None, hw=None, rank=0, world_size=1, tower="vit", use_augs=False):
     ocfg = tiny_config(image_size=image, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(image // 2,),
                        class_cond=True, use_new_attention_order=new_order)
     ounet = seeded_init_(UNetModel(ocfg)).eval()
@@ -64,14 +64,15 @@ def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0
     eng = pg.GuidedStepB200(prod_unet_cfg(ocfg), ounet.state_dict(), pvit_cfg, oclip.state_dict(), batch=B,
                             num_cutouts=cutn, max_prompts=P, use_magnitude=use_magnitude, device=device, conv_impl=conv_impl,
                             height=(hw or (image, image))[0], width=(hw or (image, image))[1],
-                            rank=rank, world_size=world_size, use_graph=use_graph, vit_streams=vit_streams, cutn_variants=cutn_variants, lpips_sd=lp_sd, init_scale=init_scale, cutout_resize=cutout_resize, **kw)
+                            rank=rank, world_size=world_size, use_graph=use_graph, vit_streams=vit_streams, cutn_variants=cutn_variants, lpips_sd=lp_sd, init_scale=init_scale, cutout_resize=cutout_resize, use_augs=use_augs, **kw)
     eng.set_targets(targets, weights)
     return dict(ounet=ounet, oclip=oclip, odiff=odiff, pdiff=pdiff, eng=eng, targets=targets, weights=weights, kw=kw, olp=olp, init=init,
                 init_scale=init_scale, cutout_resize=cutout_resize,
                 use_magnitude=use_magnitude, cutn=run_cutn or cutn, B=B, image=image, hw=hw or (image, image))
 
 
-def oracle_step(ctx, mode, x, t_index, y, noise_seed, coords, fac_index):
+def oracle_step(ctx, mode, x, t_index, y, noise_seed, coords, fac_index, aug=None):
+    """aug = (params [cutn, 20], noise [cutn, 4, B, 3, Smax, Smax]): the use_augs pipeline with the engine's draws (run the engine first)"""
     odiff = ctx["odiff"]
     cond = og.OracleCondFn(odiff, ctx["oclip"], ctx["targets"], ctx["weights"], cut_size=32, num_cutouts=ctx["cutn"],
                            use_magnitude=ctx["use_magnitude"], lpips_model=ctx.get("olp"), init_tensor=ctx.get("init"),
@@ -80,7 +81,7 @@ def oracle_step(ctx, mode, x, t_index, y, noise_seed, coords, fac_index):
     grabbed = {}
 
     def cond_fn(xx, tt, out, y=None):
-        g = cond(xx, tt, out, y=y, coords=coords)
+        g = cond(xx, tt, out, y=y, coords=coords, **(dict(aug_params=aug[0], aug_noise=aug[1]) if aug is not None else {}))
         grabbed["g"] = g.detach().clone()
         return g
 
@@ -132,9 +133,18 @@ def run_tiny_step_parity(device="cuda:0", mode="ancestral", t_index=14, runner_f
     if ctx["init"] is not None:
         ctx["eng"].set_init_image(ctx["init"], runner_factory(ctx["eng"]) if runner_factory else None)
     x, y, noise, nseed, coords = make_inputs(ctx)
-    o = oracle_step(ctx, mode, x, t_index, y, nseed, coords, fac_index=t_index)
     runner = runner_factory(ctx["eng"]) if runner_factory else None
-    e = engine_step(ctx, mode, x, t_index, y, noise, coords, fac_index=t_index, runner=runner)
+    aug = None
+    if build_kw.get("use_augs"):  # the engine draws this step's aug parameters / noise while staging; the oracle gets the same ones
+        th.manual_seed(4242)
+        e = engine_step(ctx, mode, x, t_index, y, noise, coords, fac_index=t_index, runner=runner)
+        eng = ctx["eng"]
+        aug = (eng.v(eng.aug_prm, (eng.cutn, 20)).float().cpu().clone(),
+               eng.v(eng.aug_noise, (eng.cutn, 4, eng.B, 3, eng.aug_smax, eng.aug_smax)).float().cpu().clone())
+        assert float(aug[0][:, 1:7].abs().sum()) > 0 and float(aug[1].abs().sum()) > 0
+    o = oracle_step(ctx, mode, x, t_index, y, nseed, coords, fac_index=t_index, aug=aug)
+    if aug is None:
+        e = engine_step(ctx, mode, x, t_index, y, noise, coords, fac_index=t_index, runner=runner)
     res = compare(o, e)
     res["clip_loss_rel"] = abs(float(e["losses"]["clip"].sum()) - o["terms"]["clip"]) / (abs(o["terms"]["clip"]) + 1e-9)
     res["tv_loss_rel"] = abs(float(e["losses"]["tv"].sum()) - o["terms"]["tv"]) / (abs(o["terms"]["tv"]) + 1e-9)

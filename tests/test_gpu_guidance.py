@@ -95,3 +95,54 @@ def test_sharded_rms_clamp_ops_equal_fused():
     assert th.allclose(outs["split"], outs["fused"], rtol=1e-6, atol=1e-9)
     # twice the element count with the same sum of squares: the RMS halves by sqrt(2) but still exceeds the cap -> 0.05 * sqrt(2) locally
     assert abs(float(outs["split_2x"].square().mean().sqrt()) - 0.05 * 2 ** 0.5) < 1e-5
+
+
+def test_use_augs_cutout_kernels_vs_reference_goldens():
+    """MakeCutouts(use_augs=True): the CUDA gather / scatter kernels (csrc/augs.cu) against tests/golden/augs_golden.npz -- outputs and
+    autograd gradients of the REFERENCE's own module (cgd/modules.py + torchvision transforms, CPU) with the parameters and noise its
+    seed produces.  fp16 patch output; nearest-neighbour sampling may pick the neighbouring pixel where a source coordinate lies
+    within float round-off of .5, hence an L2 criterion next to the element-wise one."""
+    import os
+    from clip_guided_diffusion_b200.plan import Plan
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "augs_golden.npz"))
+    B, H, W, CS, CUTN = (int(v) for v in d["meta"])
+    P, kpad = CS, 3 * CS * CS
+    for s in d["seeds"]:
+        s = int(s)
+        plan = Plan()
+        bx, bc, bp = plan.new(B * 3 * H * W, "f", "x"), plan.new(CUTN * 3, "i32", "coords"), plan.new(CUTN * 20, "f", "prm")
+        bn = plan.new(CUTN * 4 * B * 3 * H * W, "f", "noise")
+        bo, bd, bg = plan.new(CUTN * B * kpad, "h", "patches"), plan.new(CUTN * B * kpad, "h", "dpatches"), plan.new(B * 3 * H * W, "f", "dx")
+        plan.emit("CUTOUTS_AUG_FWD", i=[B, H, W, CUTN, CS, P, kpad, min(H, W)], f=[0, 0, 0, 1, 1, 1], p=[(bx, 0), (bc, 0), (bo, 0), (bp, 0), (bn, 0)])
+        plan.emit("FILL", i=[B * 3 * H * W], f=[0.0], p=[(bg, 0)])
+        plan.emit("CUTOUTS_AUG_BWD", i=[B, H, W, CUTN, CS, P, kpad], f=[0, 0, 0, 1, 1, 1, 1.0], p=[(bd, 0), (bc, 0), (bg, 0), (bp, 0)])
+        plan.finalize("cuda")
+        plan.view(bx, (B, 3, H, W)).copy_(T(d[f"x_{s}"]) * 2 - 1)
+        plan.view(bc, (CUTN, 3)).copy_(T(d[f"coords_{s}"]))
+        plan.view(bp, (CUTN, 20)).copy_(T(d[f"prm_{s}"]))
+        plan.view(bn).copy_(T(d[f"noise_{s}"]).flatten())
+        plan.view(bd, (CUTN * B, 1, kpad)).copy_(T(d[f"cot_{s}"]).reshape(CUTN * B, 1, kpad))
+        plan.run()
+        th.cuda.synchronize()
+        y = plan.view(bo, (CUTN * B, 3, CS, CS)).float().cpu()
+        ref = th.from_numpy(d[f"y_{s}"])
+        assert float((y - ref).norm() / ref.norm()) < 2e-3, (s, float((y - ref).norm() / ref.norm()))
+        assert float(((y - ref).abs() > 5e-3).float().mean()) < 5e-3
+        gx = plan.view(bg, (B, 3, H, W)).cpu()
+        gref = th.from_numpy(d[f"gx_{s}"]) * 0.5  # the op differentiates through its own (x_in + 1) / 2
+        assert float((gx - gref).norm() / gref.norm()) < 2e-2, (s, float((gx - gref).norm() / gref.norm()))
+
+
+def test_make_cutouts_use_augs_surface():
+    """the drop-in surface: MakeCutouts(cut_size, n, power, use_augs=True)(x) returns [cutn * B, 3, cut_size, cut_size] like the
+    reference.  (On a GPU the reference takes its noise from the CUDA generator and its decisions from the CPU one; the goldens were
+    made on the CPU where both interleave on one stream, so values are compared by the kernel test above, not here.)"""
+    mk = MakeCutouts(24, 5, 1.0, use_augs=True)
+    th.manual_seed(0)
+    x = th.rand(2, 3, 48, 48, device="cuda")
+    out = mk(x)
+    assert out.shape == (10, 3, 24, 24) and th.isfinite(out).all()
+    assert 0.2 < float(out.mean()) < 0.6 and float(out.min()) > -0.1 and float(out.max()) < 1.1  # [0, 1] images, zero fill, .01 noise
+    th.manual_seed(0)
+    x2 = th.rand(2, 3, 48, 48, device="cuda")
+    assert th.equal(mk(x2), out)  # same seeds -> same windows, parameters and noise

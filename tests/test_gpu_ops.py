@@ -17,13 +17,14 @@ SEGS = [("unet_emb", "unet_bwd"), ("pmv", "cond"), ("cut_fwd", "sph"), ("vit_fwd
 
 
 @pytest.mark.parametrize("kw", [dict(image=32), dict(image=64, B=1, cutn=2, use_magnitude=True, sat_scale=20.0, new_order=True),
-                                dict(image=64, B=2, cutn=3, cutout_resize="lanczos3")],
-                         ids=["b2_32px", "b1_64px_mag_sat_neworder", "b2_64px_resize_right"])
+                                dict(image=64, B=2, cutn=3, cutout_resize="lanczos3"), dict(image=64, B=2, cutn=4, use_augs=True)],
+                         ids=["b2_32px", "b1_64px_mag_sat_neworder", "b2_64px_resize_right", "b2_64px_use_augs"])
 def test_every_op_matches_interpreter(kw):
     ctx = build_tiny("cuda", conv_impl=IMPL, **kw)
     eng = ctx["eng"]
     x, y, noise, nseed, coords = make_inputs(ctx)
     sc = ctx["pdiff"].scalar_table(14, 14, 0.0)
+    th.manual_seed(77)  # use_augs: the aug parameters / noise fields are drawn while staging
     eng.stage_step(sc, coords, ctx["pdiff"].model_timestep(14), y)
     eng.img(eng.unet.x_in).copy_(x)
     eng.img(eng.noise).copy_(noise)
@@ -95,5 +96,24 @@ def test_step_with_resize_right_cutouts_vs_oracle():
     x, y, noise, nseed, coords = make_inputs(ctx)
     o = oracle_step(ctx, "ancestral", x, 14, y, nseed, coords, fac_index=14)
     e = engine_step(ctx, "ancestral", x, 14, y, noise, coords, fac_index=14, fused=True)
+    res = compare(o, e)
+    assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["eager", "graph"])
+def test_step_with_use_augs_vs_oracle(fused):
+    """use_augs (cgd/modules.py:12-24, 62): random flip / affine / perspective / grayscale / noise on every cutout inside the cutout
+    kernels.  The engine draws the parameters (CPU generator, torchvision's order) and noise fields (device generator) while staging
+    the step; the oracle runs torchvision's own kernels with exactly those draws (oracle.guidance.apply_augs, pinned bit-exactly on
+    the reference's MakeCutouts(use_augs=True) by tests/test_oracle.py)."""
+    ctx = build_tiny("cuda", conv_impl=IMPL, image=64, use_graph=True, B=2, cutn=4, use_augs=True)
+    eng = ctx["eng"]
+    x, y, noise, nseed, coords = make_inputs(ctx)
+    th.manual_seed(4242)
+    e = engine_step(ctx, "ddim", x, 14, y, noise, coords, fac_index=14, fused=fused)
+    aug = (eng.v(eng.aug_prm, (eng.cutn, 20)).float().cpu().clone(),
+           eng.v(eng.aug_noise, (eng.cutn, 4, eng.B, 3, eng.aug_smax, eng.aug_smax)).float().cpu().clone())
+    assert float(aug[1].abs().sum()) > 0
+    o = oracle_step(ctx, "ddim", x, 14, y, nseed, coords, fac_index=14, aug=aug)
     res = compare(o, e)
     assert res["cos_g"] > 0.995 and res["rel_x0"] < 2e-2 and res["rel_sample"] < 2e-2, res

@@ -184,3 +184,65 @@ def test_resize_tables_reproduce_reference(name):
     for r in (0, S // 3, S - 1):  # every output whose field of view holds r lies in [lo, hi], and none outside
         touching = [o for o in range(O) if left[o] <= r <= left[o] + T - 1]
         assert touching == list(range(int(inv[r, 0]), int(inv[r, 1]) + 1))
+
+
+# ---------------------------------------------------------------------- use_augs (cgd/modules.py:12-24, 62), pinned on the reference
+def _aug_cases():
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "augs_golden.npz"))
+    B, H, W, CS, CUTN = (int(v) for v in d["meta"])
+    return d, B, H, W, CS, CUTN
+
+
+def test_aug_draw_order_and_oracle_reproduce_the_reference_bit_exactly():
+    """tests/golden/augs_golden.npz was written by the reference's MakeCutouts(use_augs=True) (torchvision transforms, CPU).  From
+    the same seed, clip_guided_diffusion_b200/augs.py must consume the default generator identically (same final RNG state, same
+    parameters and noise) and oracle.guidance.apply_augs must reproduce the reference's cutouts and input gradient bit for bit."""
+    from clip_guided_diffusion_b200 import augs
+    from oracle import guidance as og
+    d, B, H, W, CS, CUTN = _aug_cases()
+    for s in d["seeds"]:
+        s = int(s)
+        x, cot = th.from_numpy(d[f"x_{s}"]), th.from_numpy(d[f"cot_{s}"])
+        mk = og.MakeCutouts(CS, CUTN, 1.0, use_augs=True)
+        th.manual_seed(s)
+        coords = mk._generate_coords(H, W, CUTN)
+        noise = th.zeros(CUTN, 4, B, 3, min(H, W), min(H, W))
+        prm = augs.draw_aug_params(coords, B, H, W, noise_device="cpu", noise_out=noise)
+        assert th.equal(th.get_rng_state(), th.from_numpy(d[f"rng_{s}"]))
+        assert coords == [tuple(int(v) for v in r) for r in d[f"coords_{s}"]]
+        assert th.equal(prm, th.from_numpy(d[f"prm_{s}"])) and th.equal(noise, th.from_numpy(d[f"noise_{s}"]))
+        xr = x.clone().requires_grad_()
+        y = mk(xr, coords=coords, aug_params=prm, aug_noise=noise)
+        (gx,) = th.autograd.grad((y * cot).sum(), xr)
+        assert th.equal(y.detach(), th.from_numpy(d[f"y_{s}"])), s
+        assert th.equal(gx, th.from_numpy(d[f"gx_{s}"])), s
+
+
+def test_aug_ops_of_the_interpreter_match_the_reference_goldens():
+    """the CUTOUTS_AUG_FWD / _BWD op contract (what the CUDA kernels implement), executed by tests/plan_interp.py"""
+    from clip_guided_diffusion_b200.plan import Plan
+    from tests.plan_interp import Interp
+    d, B, H, W, CS, CUTN = _aug_cases()
+    s = int(d["seeds"][0])
+    P, kpad = CS, 3 * CS * CS
+    plan = Plan()
+    bx, bc, bp = plan.new(B * 3 * H * W, "f", "x"), plan.new(CUTN * 3, "i32", "coords"), plan.new(CUTN * 20, "f", "prm")
+    bn = plan.new(CUTN * 4 * B * 3 * H * W, "f", "noise")
+    bo, bd, bg = plan.new(CUTN * B * kpad, "h", "patches"), plan.new(CUTN * B * kpad, "h", "dpatches"), plan.new(B * 3 * H * W, "f", "dx")
+    plan.emit("CUTOUTS_AUG_FWD", i=[B, H, W, CUTN, CS, P, kpad, min(H, W)], f=[0, 0, 0, 1, 1, 1], p=[(bx, 0), (bc, 0), (bo, 0), (bp, 0), (bn, 0)])
+    plan.emit("FILL", i=[B * 3 * H * W], f=[0.0], p=[(bg, 0)])
+    plan.emit("CUTOUTS_AUG_BWD", i=[B, H, W, CUTN, CS, P, kpad], f=[0, 0, 0, 1, 1, 1, 1.0], p=[(bd, 0), (bc, 0), (bg, 0), (bp, 0)])
+    plan.finalize("cpu")
+    plan.view(bx, (B, 3, H, W)).copy_(th.from_numpy(d[f"x_{s}"]) * 2 - 1)  # the op takes x_in in [-1, 1] and applies (x + 1) / 2
+    plan.view(bc, (CUTN, 3)).copy_(th.from_numpy(d[f"coords_{s}"]))
+    plan.view(bp, (CUTN, 20)).copy_(th.from_numpy(d[f"prm_{s}"]))
+    plan.view(bn).copy_(th.from_numpy(d[f"noise_{s}"]).flatten())
+    plan.view(bd, (CUTN * B, 1, kpad)).copy_(th.from_numpy(d[f"cot_{s}"]).reshape(CUTN * B, 1, kpad))
+    Interp(plan).run(0, 3)
+    y = plan.view(bo, (CUTN * B, 3, CS, CS)).float()
+    ref = th.from_numpy(d[f"y_{s}"])
+    assert float((y - ref).abs().max()) < 2e-3  # fp16 output
+    gx = plan.view(bg, (B, 3, H, W))
+    gref = th.from_numpy(d[f"gx_{s}"]) * 0.5  # d/dx_in of ((x_in + 1) / 2); fp16 cotangent
+    assert float((gx - gref).abs().max() / gref.abs().max()) < 2e-3

@@ -20,6 +20,9 @@ def _interp_runner(eng):
                                      # swapped sides are clipped at the border (quirk B3) and still pooled to a square
                                      ("ddim", dict(B=1, cutn=6, image=32, hw=(32, 64))),
                                      ("ddim", dict(B=2, cutn=3, tower="rn")),  # CLIP ModifiedResNet tower instead of the ViT
+                                     # use_augs (cgd/modules.py:12-24): flip / affine / perspective / grayscale / noise inside the cutout ops
+                                     ("ddim", dict(B=2, cutn=4, image=64, use_augs=True)),
+                                     ("ancestral", dict(B=1, cutn=6, image=32, hw=(32, 48), use_augs=True)),
                                      ("ancestral", dict(B=2, cutn=4, image=32, hw=(48, 32)))])
 def test_step_plan_matches_oracle(mode, kw):
     res = run_tiny_step_parity(device="cpu", mode=mode, runner_factory=_interp_runner, **{"image": 32, **kw})
@@ -107,7 +110,6 @@ def test_make_cutouts_surface():
     ref.cache_coordinates(256, 320)
     assert mk.cached_coords == ref.cached_coords and len(mk.cached_coords) == 16
     assert mk.coords_for(256, 320, use_cache=True, num_cutouts_override=4) == ref.cached_coords[:4]
-    with pytest.raises(NotImplementedError):
-        MakeCutouts(224, 16, use_augs=True)
+    assert MakeCutouts(224, 16, use_augs=True).use_augs  # cgd/modules.py:12-24: the augmentations run inside the cutout kernels
     with pytest.raises(Exception):
         mk(th.zeros(1, 3, 256, 256))  # forward is the CUDA kernel: no CPU fallback
