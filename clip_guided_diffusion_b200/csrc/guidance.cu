@@ -109,6 +109,135 @@ __global__ void cutouts_bwd_kernel(const __half* __restrict__ dpatch, const int*
   }
 }
 
+// ---------------------------------------------------------------- cutouts, row-per-warp version (default)
+// The element-per-thread kernels above decode (row, patch, c, ky, kx) with div / mod chains and recompute both pooling bins for
+// every element: 43 us forward / 108 us backward at cfg2 for ~15 MB of (mostly L2-resident) traffic.  Here the bin tables are built
+// once per block in shared memory, a warp owns one output row (forward) or one image row (backward), lanes walk consecutive x --
+// coalesced reads of the source row(s), contiguous fp16 writes per patch row -- and nothing is divided in the inner loops.
+// Same arithmetic in the same order as the kernels above (bit-identical results: tests/test_gpu_guidance.py goldens).
+constexpr int CUT_MAX_CS = 1024;   // shared tables: output extent
+constexpr int CUT_FWD_ROWS = 8;    // output rows (= warps) per block
+
+// block = (cutout k, image b, 8 output rows); warp = one output row oy, all 3 channels; lane -> ox = lane, lane + 32, ...
+__global__ void __launch_bounds__(32 * CUT_FWD_ROWS)
+cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coords, __half* __restrict__ out, int B, int H, int W, int cutn,
+                        int cs, int P, int Kpad, float3 mean, float3 stdv) {
+  __shared__ short xs_t[CUT_MAX_CS], xe_t[CUT_MAX_CS];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int rb = cs / CUT_FWD_ROWS + (cs % CUT_FWD_ROWS ? 1 : 0);  // row blocks per (k, b)
+  const int blk = blockIdx.x;
+  const int rblk = blk % rb, b = (blk / rb) % B, k = blk / (rb * B);
+  const int offx = coords[k * 3 + 0], offy = coords[k * 3 + 1], S = coords[k * 3 + 2];
+  const int Sy = min(S, H - offy), Sx = min(S, W - offx);
+  for (int o = threadIdx.x; o < cs; o += blockDim.x) {
+    int s0, e0;
+    pool_bin(o, Sx, cs, s0, e0);
+    xs_t[o] = (short)s0;
+    xe_t[o] = (short)e0;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int oy = rblk * CUT_FWD_ROWS + warp;
+  const int g = cs / P, G2 = g * g, PP = P * P;
+  __half* orow = out + ((int64_t)k * B + b) * G2 * Kpad;
+  if (oy < cs) {
+    int ys, ye;
+    pool_bin(oy, Sy, cs, ys, ye);
+    const int py = oy / P, ky = oy - py * P;
+    for (int c = 0; c < 3; ++c) {
+      const float* src = x + ((int64_t)b * 3 + c) * H * W + (int64_t)offy * W + offx;
+      const float mu = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
+      const float sd = c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z);
+      for (int ox = lane; ox < cs; ox += 32) {
+        const int xs = xs_t[ox], xe = xe_t[ox];
+        float acc = 0.f;
+        for (int yy = ys; yy < ye; ++yy)
+          for (int xx = xs; xx < xe; ++xx) acc += src[(int64_t)yy * W + xx];
+        acc /= (float)((ye - ys) * (xe - xs));
+        const int px = ox / P, kx = ox - px * P;
+        orow[(int64_t)(py * g + px) * Kpad + c * PP + ky * P + kx] = __float2half_rn(((acc + 1.f) * 0.5f - mu) / sd);
+      }
+    }
+  }
+  // zero padding of the patch vectors (Kpad > 3 P^2: ViT-L/14): the patches whose first row this block owns
+  if (Kpad > 3 * PP) {
+    const int pad = Kpad - 3 * PP;
+    for (int r = 0; r < CUT_FWD_ROWS; ++r) {
+      const int oyr = rblk * CUT_FWD_ROWS + r;
+      if (oyr >= cs || oyr % P) continue;
+      for (int i = threadIdx.x; i < g * pad; i += blockDim.x) orow[(int64_t)((oyr / P) * g + i / pad) * Kpad + 3 * PP + i % pad] = __float2half_rn(0.f);
+    }
+  }
+}
+
+// block = (image b, image row yg); thread -> xg = tid, tid + blockDim, ...; per cutout the row's output-row range is found once per
+// block (thread 0 .. cutn-1 fill the shared table), the column range once per (thread, cutout) and shared by the 3 channels
+constexpr int CUT_MAX_CUTN = 128;
+constexpr int CUT_MAX_ROWS = 8;  // output rows whose bins contain one input row: <= ceil(cs / S) + 1 (up-sampling 64 -> 224: 5)
+__global__ void __launch_bounds__(256)
+cutouts_bwd_rows_kernel(const __half* __restrict__ dpatch, const int* __restrict__ coords, float* __restrict__ dx, int B, int H, int W, int cutn,
+                        int cs, int P, int Kpad, float3 stdv, float scale) {
+  // per cutout, for image row yg: window geometry + the (at most CUT_MAX_ROWS) output rows whose bins contain it, with their bin heights
+  __shared__ int c_offx[CUT_MAX_CUTN], c_Sx[CUT_MAX_CUTN], r_n[CUT_MAX_CUTN], r_oy[CUT_MAX_CUTN][CUT_MAX_ROWS], r_h[CUT_MAX_CUTN][CUT_MAX_ROWS];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int yg = blockIdx.x % H, b = blockIdx.x / H;
+  for (int k = threadIdx.x; k < cutn; k += blockDim.x) {
+    const int offx = coords[k * 3 + 0], offy = coords[k * 3 + 1], S = coords[k * 3 + 2];
+    const int Sy = min(S, H - offy), Sx = min(S, W - offx);
+    c_offx[k] = offx;
+    c_Sx[k] = Sx;
+    const int ry = yg - offy;
+    int n = 0;
+    if (ry >= 0 && ry < Sy) {
+      const int oy0 = (int)(((unsigned)ry * (unsigned)cs) / (unsigned)Sy);
+      const int oy1 = min(cs - 1, (int)((((unsigned)(ry + 1)) * (unsigned)cs + Sy - 1) / (unsigned)Sy) - 1);
+      for (int oy = oy0; oy <= oy1 && n < CUT_MAX_ROWS; ++oy) {
+        int ys, ye;
+        pool_bin(oy, Sy, cs, ys, ye);
+        if (ry < ys || ry >= ye) continue;
+        r_oy[k][n] = oy;
+        r_h[k][n] = ye - ys;
+        ++n;
+      }
+    }
+    r_n[k] = n;
+  }
+  __syncthreads();
+  const int g = cs / P, G2 = g * g, PP = P * P;
+  const float sd3[3] = {stdv.x, stdv.y, stdv.z};
+  for (int xg = threadIdx.x; xg < W; xg += blockDim.x) {
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < cutn; ++k) {
+      const int nr = r_n[k];
+      if (nr == 0) continue;
+      const int Sx = c_Sx[k], rx = xg - c_offx[k];
+      if (rx < 0 || rx >= Sx) continue;
+      const int ox0 = (int)(((unsigned)rx * (unsigned)cs) / (unsigned)Sx);
+      const int ox1 = min(cs - 1, (int)((((unsigned)(rx + 1)) * (unsigned)cs + Sx - 1) / (unsigned)Sx) - 1);
+      const __half* dp = dpatch + ((int64_t)k * B + b) * G2 * Kpad;
+      for (int i = 0; i < nr; ++i) {
+        const int oy = r_oy[k][i], bh = r_h[k][i];
+        const int py = oy / P, ky = oy - py * P;
+        for (int ox = ox0; ox <= ox1; ++ox) {
+          int xs, xe;
+          pool_bin(ox, Sx, cs, xs, xe);
+          if (rx < xs || rx >= xe) continue;
+          const int px = ox / P, kx = ox - px * P;
+          const __half* q = dp + (int64_t)(py * g + px) * Kpad + ky * P + kx;
+          const float inv = (float)(bh * (xe - xs));
+          acc[0] += __half2float(q[0]) / inv;
+          acc[1] += __half2float(q[PP]) / inv;
+          acc[2] += __half2float(q[2 * PP]) / inv;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dx[(((int64_t)b * 3 + c) * H + yg) * W + xg] = acc[c] * (0.5f / sd3[c]) * scale;
+  }
+}
+
 // ---------------------------------------------------------------- cutouts, ResizeRight (lanczos3, antialiased) mode
 // Same contract as cutouts_fwd / cutouts_bwd, but every square S x S crop is resampled to cs x cs with the separable tables the
 // host builds per crop size (clip_guided_diffusion_b200/resize_right.py, following cgd/ResizeRight/resize_right.py:31-122):
@@ -227,6 +356,14 @@ int launch_cutouts_fwd(const CgdOp& op, cudaStream_t st) {
   if (int rc = cutout_check(op)) return rc;
   const int64_t B = op.i[0], cutn = op.i[3], cs = op.i[4], P = op.i[5], Kpad = op.i[6];
   const int64_t total = cutn * B * (cs / P) * (cs / P) * Kpad;
+  if (cs <= CUT_MAX_CS && op.i[1] < 32768 && op.i[2] < 32768) {  // row-per-warp kernel: bin tables in shared memory
+    const int64_t rb = ceil_div(cs, CUT_FWD_ROWS);
+    CGD_CUDA(launch_pdl(cutouts_fwd_rows_kernel, dim3((unsigned)(cutn * B * rb)), dim3(32 * CUT_FWD_ROWS), 0, st, (const float*)op.p[0], (const int*)op.p[1],
+                        (__half*)op.p[2], (int)B, (int)op.i[1], (int)op.i[2], (int)cutn, (int)cs, (int)P, (int)Kpad,
+                        make_float3(op.f[0], op.f[1], op.f[2]), make_float3(op.f[3], op.f[4], op.f[5])));
+    CGD_LAUNCH_CHECK();
+    return 0;
+  }
   CGD_CUDA(launch_pdl(cutouts_fwd_kernel, dim3(gw_blocks(total)), dim3(256), 0, st, (const float*)op.p[0], (const int*)op.p[1], (__half*)op.p[2], (int)B, (int)op.i[1],
                                                       (int)op.i[2], (int)cutn, (int)cs, (int)P, (int)Kpad,
                                                       make_float3(op.f[0], op.f[1], op.f[2]), make_float3(op.f[3], op.f[4], op.f[5])));
@@ -236,6 +373,13 @@ int launch_cutouts_fwd(const CgdOp& op, cudaStream_t st) {
 int launch_cutouts_bwd(const CgdOp& op, cudaStream_t st) {
   if (int rc = cutout_check(op)) return rc;
   const int64_t B = op.i[0], H = op.i[1], W = op.i[2];
+  const int64_t s_min = std::min<int64_t>(std::min(H, W), op.i[4]);  // smallest window the reference draws (cgd/modules.py:40-41)
+  if (op.i[3] <= CUT_MAX_CUTN && op.i[4] <= 32768 && ceil_div(op.i[4], s_min) + 1 <= CUT_MAX_ROWS) {  // row-per-block gather, shared row tables
+    CGD_CUDA(launch_pdl(cutouts_bwd_rows_kernel, dim3((unsigned)(B * H)), dim3(256), 0, st, (const __half*)op.p[0], (const int*)op.p[1], (float*)op.p[2],
+                        (int)B, (int)H, (int)W, (int)op.i[3], (int)op.i[4], (int)op.i[5], (int)op.i[6], make_float3(op.f[3], op.f[4], op.f[5]), op.f[6]));
+    CGD_LAUNCH_CHECK();
+    return 0;
+  }
   CGD_CUDA(launch_pdl(cutouts_bwd_kernel, dim3(gw_blocks(B * 3 * H * W)), dim3(256), 0, st, (const __half*)op.p[0], (const int*)op.p[1], (float*)op.p[2], (int)B, (int)H,
                                                               (int)W, (int)op.i[3], (int)op.i[4], (int)op.i[5], (int)op.i[6],
                                                               make_float3(op.f[3], op.f[4], op.f[5]), op.f[6]));
