@@ -178,8 +178,11 @@ constexpr int CUT_MAX_ROWS = 8;  // output rows whose bins contain one input row
 __global__ void __launch_bounds__(256)
 cutouts_bwd_rows_kernel(const __half* __restrict__ dpatch, const int* __restrict__ coords, float* __restrict__ dx, int B, int H, int W, int cutn,
                         int cs, int P, int Kpad, float3 stdv, float scale) {
-  // per cutout, for image row yg: window geometry + the (at most CUT_MAX_ROWS) output rows whose bins contain it, with their bin heights
-  __shared__ int c_offx[CUT_MAX_CUTN], c_Sx[CUT_MAX_CUTN], r_n[CUT_MAX_CUTN], r_oy[CUT_MAX_CUTN][CUT_MAX_ROWS], r_h[CUT_MAX_CUTN][CUT_MAX_ROWS];
+  // per cutout, for image row yg: window geometry, the range [oy0, oy1] of output rows whose bins can contain it and, for the first
+  // CUT_MAX_ROWS of them, the bin height (0 = the bin does not contain the row); rows beyond that (a window clipped to a sliver at
+  // the border of a non-square image, quirk B3) are tested on the fly
+  __shared__ int c_offx[CUT_MAX_CUTN], c_Sx[CUT_MAX_CUTN], c_Sy[CUT_MAX_CUTN], c_ry[CUT_MAX_CUTN], r_oy0[CUT_MAX_CUTN], r_oy1[CUT_MAX_CUTN],
+      r_h[CUT_MAX_CUTN][CUT_MAX_ROWS];
   pdl_wait();
   pdl_launch_dependents();
   const int yg = blockIdx.x % H, b = blockIdx.x / H;
@@ -188,21 +191,21 @@ cutouts_bwd_rows_kernel(const __half* __restrict__ dpatch, const int* __restrict
     const int Sy = min(S, H - offy), Sx = min(S, W - offx);
     c_offx[k] = offx;
     c_Sx[k] = Sx;
+    c_Sy[k] = Sy;
     const int ry = yg - offy;
-    int n = 0;
+    c_ry[k] = ry;
+    int oy0 = 0, oy1 = -1;
     if (ry >= 0 && ry < Sy) {
-      const int oy0 = (int)(((unsigned)ry * (unsigned)cs) / (unsigned)Sy);
-      const int oy1 = min(cs - 1, (int)((((unsigned)(ry + 1)) * (unsigned)cs + Sy - 1) / (unsigned)Sy) - 1);
-      for (int oy = oy0; oy <= oy1 && n < CUT_MAX_ROWS; ++oy) {
+      oy0 = (int)(((unsigned)ry * (unsigned)cs) / (unsigned)Sy);
+      oy1 = min(cs - 1, (int)((((unsigned)(ry + 1)) * (unsigned)cs + Sy - 1) / (unsigned)Sy) - 1);
+      for (int i = 0; i < CUT_MAX_ROWS && oy0 + i <= oy1; ++i) {
         int ys, ye;
-        pool_bin(oy, Sy, cs, ys, ye);
-        if (ry < ys || ry >= ye) continue;
-        r_oy[k][n] = oy;
-        r_h[k][n] = ye - ys;
-        ++n;
+        pool_bin(oy0 + i, Sy, cs, ys, ye);
+        r_h[k][i] = (ry >= ys && ry < ye) ? ye - ys : 0;
       }
     }
-    r_n[k] = n;
+    r_oy0[k] = oy0;
+    r_oy1[k] = oy1;
   }
   __syncthreads();
   const int g = cs / P, G2 = g * g, PP = P * P;
@@ -210,15 +213,23 @@ cutouts_bwd_rows_kernel(const __half* __restrict__ dpatch, const int* __restrict
   for (int xg = threadIdx.x; xg < W; xg += blockDim.x) {
     float acc[3] = {0.f, 0.f, 0.f};
     for (int k = 0; k < cutn; ++k) {
-      const int nr = r_n[k];
-      if (nr == 0) continue;
+      const int oy0 = r_oy0[k], oy1 = r_oy1[k];
+      if (oy1 < oy0) continue;
       const int Sx = c_Sx[k], rx = xg - c_offx[k];
       if (rx < 0 || rx >= Sx) continue;
       const int ox0 = (int)(((unsigned)rx * (unsigned)cs) / (unsigned)Sx);
       const int ox1 = min(cs - 1, (int)((((unsigned)(rx + 1)) * (unsigned)cs + Sx - 1) / (unsigned)Sx) - 1);
       const __half* dp = dpatch + ((int64_t)k * B + b) * G2 * Kpad;
-      for (int i = 0; i < nr; ++i) {
-        const int oy = r_oy[k][i], bh = r_h[k][i];
+      for (int oy = oy0; oy <= oy1; ++oy) {
+        int bh;
+        if (oy - oy0 < CUT_MAX_ROWS) {
+          bh = r_h[k][oy - oy0];
+        } else {
+          int ys, ye;
+          pool_bin(oy, c_Sy[k], cs, ys, ye);
+          bh = (c_ry[k] >= ys && c_ry[k] < ye) ? ye - ys : 0;
+        }
+        if (bh == 0) continue;
         const int py = oy / P, ky = oy - py * P;
         for (int ox = ox0; ox <= ox1; ++ox) {
           int xs, xe;
@@ -373,8 +384,7 @@ int launch_cutouts_fwd(const CgdOp& op, cudaStream_t st) {
 int launch_cutouts_bwd(const CgdOp& op, cudaStream_t st) {
   if (int rc = cutout_check(op)) return rc;
   const int64_t B = op.i[0], H = op.i[1], W = op.i[2];
-  const int64_t s_min = std::min<int64_t>(std::min(H, W), op.i[4]);  // smallest window the reference draws (cgd/modules.py:40-41)
-  if (op.i[3] <= CUT_MAX_CUTN && op.i[4] <= 32768 && ceil_div(op.i[4], s_min) + 1 <= CUT_MAX_ROWS) {  // row-per-block gather, shared row tables
+  if (op.i[3] <= CUT_MAX_CUTN && op.i[4] <= 32768) {  // row-per-block gather with shared per-cutout row tables
     CGD_CUDA(launch_pdl(cutouts_bwd_rows_kernel, dim3((unsigned)(B * H)), dim3(256), 0, st, (const __half*)op.p[0], (const int*)op.p[1], (float*)op.p[2],
                         (int)B, (int)H, (int)W, (int)op.i[3], (int)op.i[4], (int)op.i[5], (int)op.i[6], make_float3(op.f[3], op.f[4], op.f[5]), op.f[6]));
     CGD_LAUNCH_CHECK();
