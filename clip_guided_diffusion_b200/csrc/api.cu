@@ -100,6 +100,9 @@ static int op_launches(const CgdOp& op, const ConvTcLaunch* conv) {
     case CGD_OP_CONV: return conv_tc_num_launches(*conv);
     case CGD_OP_ATTN_BWD: return attn_bwd_num_launches(op);
     case CGD_OP_FINAL_GRAD: return ((op.flags & 1) && !(op.flags & 4)) ? 2 : 1;
+    case CGD_OP_GN_FWD_GRID:
+    case CGD_OP_GN_BWD_GRID: return gn_grid_num_launches(op);
+    case CGD_OP_GN_APPLY_EPI: return gn_apply_epi_num_launches(op);
     default: return 1;
   }
 }

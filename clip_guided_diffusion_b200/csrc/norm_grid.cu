@@ -434,19 +434,34 @@ static int gng_check(const char* what, int64_t N, int64_t HW, int64_t C, int64_t
 bool gn_grid2_supports(int64_t C);
 int launch_gn_fwd_grid2(const CgdOp& op, cudaStream_t st);
 int launch_gn_bwd_grid2(const CgdOp& op, cudaStream_t st);
-// Measured (profiles/r01_gn_microbench_v4.txt): the direct-load engine wins the backward of the 256x256 level (51 vs 57 us at
-// C = 256, 86 vs 104 us at C = 512: two input streams, SiLU' recomputed twice -- the ring's 16 consumer warps are issue-bound
-// there), ties at 128x128 x 512 and loses 3 - 5 us everywhere else (its 1024-thread CTAs start and synchronise more slowly).
-// CGD_GN_GRID_ENGINE = ring | direct forces one engine for A/B runs.
-static bool gng_use_direct(bool backward, int64_t HW, int64_t C) {
+// norm_stream.cu: the streaming engine (three short launches: partial statistics, fold, apply; C % 256 == 0)
+bool gn_stream_supports(int64_t C);
+int gn_stream_partial_floats(int64_t N, int64_t HW, int64_t C);
+int launch_gn_fwd_stream(const CgdOp& op, cudaStream_t st);
+int launch_gn_bwd_stream(const CgdOp& op, cudaStream_t st);
+// Engines behind GN_FWD_GRID / GN_BWD_GRID.  Measured: persistent ring vs persistent direct (profiles/r01_gn_microbench_v4.txt): direct
+// wins the backward of the 256x256 level (51 vs 57 us at C = 256, 86 vs 104 us at C = 512), ties at 128x128 x 512, loses 3 - 5 us
+// elsewhere.  Both are schedule-bound, not traffic-bound (profiles/r02_launches_v1*: the one-trip GN_APPLY_EPI took as long as the
+// two-trip kernel), which the streaming engine fixes; it is the default where it applies (C % 256 == 0 and the op's partials buffer
+// has room for its per-CTA partial sums: i6 forward / i7 backward = capacity in floats, 0 = the persistent engines' N * Gn * 64).
+// CGD_GN_GRID_ENGINE = ring | direct | stream forces one engine for A/B runs.
+enum { kEngRing = 0, kEngDirect = 1, kEngStream = 2 };
+static int gng_engine(bool backward, int64_t N, int64_t HW, int64_t C, int64_t cap_floats) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("CGD_GN_GRID_ENGINE");
-    forced = !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'd' ? 2 : 0));
+    forced = !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'd' ? 2 : (e[0] == 's' ? 3 : 0)));
   }
-  if (!gn_grid2_supports(C) || forced == 1) return false;
-  if (forced == 2) return true;
-  return backward && HW * C >= (int64_t(1) << 23);
+  const bool stream_ok = gn_stream_supports(C) && cap_floats >= gn_stream_partial_floats(N, HW, C);
+  if (forced == 3) return stream_ok ? kEngStream : (gn_grid2_supports(C) ? kEngDirect : kEngRing);
+  if (forced == 1 || !gn_grid2_supports(C)) return kEngRing;
+  if (forced == 2) return kEngDirect;
+  if (stream_ok) return kEngStream;
+  return (backward && HW * C >= (int64_t(1) << 23)) ? kEngDirect : kEngRing;
+}
+int gn_grid_num_launches(const CgdOp& op) {  // for cgd_plan_num_launches
+  const bool bwd = op.code == CGD_OP_GN_BWD_GRID;
+  return gng_engine(bwd, op.i[0], op.i[1], op.i[2], bwd ? op.i[7] : op.i[6]) == kEngStream ? 3 : 1;
 }
 
 template <typename K>
@@ -462,7 +477,9 @@ int launch_gn_fwd_grid(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], HW = op.i[1], C = op.i[2], ldx = op.i[3], ldy = op.i[4], Gn = op.i[5];
   if (int rc = gng_check("gn_fwd_grid", N, HW, C, Gn)) return rc;
   CGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[4] && op.p[5] && op.p[6] && op.p[7], "gn_fwd_grid: bad args");
-  if (gng_use_direct(false, HW, C)) return launch_gn_fwd_grid2(op, st);
+  const int eng = gng_engine(false, N, HW, C, op.i[6]);
+  if (eng == kEngStream) return launch_gn_fwd_stream(op, st);
+  if (eng == kEngDirect) return launch_gn_fwd_grid2(op, st);
   static DeviceOnce set;
   if (set.needed()) {
     if (int rc = gng_prepare(gn_fwd_grid_kernel)) return rc;
@@ -480,7 +497,9 @@ int launch_gn_bwd_grid(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(ld_dy % 8 == 0 && ldx % 8 == 0 && ld_dx % 8 == 0 && op.p[0] && op.p[1] && op.p[2] && op.p[3] && op.p[4] && op.p[6] && op.p[7] &&
                     op.p[8],
                 "gn_bwd_grid: bad args");
-  if (gng_use_direct(true, HW, C)) return launch_gn_bwd_grid2(op, st);
+  const int eng = gng_engine(true, N, HW, C, op.i[7]);
+  if (eng == kEngStream) return launch_gn_bwd_stream(op, st);
+  if (eng == kEngDirect) return launch_gn_bwd_grid2(op, st);
   static DeviceOnce set;
   if (set.needed()) {
     if (int rc = gng_prepare(gn_bwd_grid_kernel)) return rc;

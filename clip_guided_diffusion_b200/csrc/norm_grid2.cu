@@ -410,11 +410,23 @@ constexpr int kG2FwdU = 4, kG2BwdU = 2;
 
 bool gn_grid2_supports(int64_t C) { return C % 256 == 0 && C <= 2048; }
 
+int launch_gn_apply_epi_stream(const CgdOp& op, cudaStream_t st);  // norm_stream.cu: fold launch + streaming apply launch
+static bool epi_use_stream(const CgdOp& op) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("CGD_GN_GRID_ENGINE");
+    off = (e && (e[0] == 'r' || e[0] == 'd')) ? 1 : 0;
+  }
+  return !off && op.p[7] != nullptr;
+}
+int gn_apply_epi_num_launches(const CgdOp& op) { return epi_use_stream(op) ? 2 : 1; }
+
 int launch_gn_apply_epi(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], HW = op.i[1], C = op.i[2], ldx = op.i[3], ldy = op.i[4], Gn = op.i[5], octs = op.i[6], oct0 = op.i[7];
   CGD_CHECK_ARG(N > 0 && HW > 0 && HW % 128 == 0 && gn_grid2_supports(C) && Gn >= 1 && ldx % 8 == 0 && ldy % 8 == 0 && octs >= oct0 + C / 8 && oct0 >= 0,
                 "gn_apply_epi: bad dims (HW %% 128, C %% 256, octets)");
   CGD_CHECK_ARG(op.p[0] && op.p[1] && op.p[2] && op.p[4] && op.p[5] && op.p[6], "gn_apply_epi: null pointer");
+  if (epi_use_stream(op)) return launch_gn_apply_epi_stream(op, st);
   CGD_CUDA(launch_pdl(gn_apply_epi_kernel<kG2FwdU>, dim3((unsigned)(N * Gn)), dim3(kG2Threads), 0, st, (const __half*)op.p[0], (const float*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (const float*)op.p[6], (int)HW, (int)C, ldx, ldy,
                       (int)Gn, (int)octs, (int)oct0, op.f[0], (int)(op.flags & 1)));

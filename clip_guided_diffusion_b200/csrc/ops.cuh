@@ -50,6 +50,8 @@ int launch_mag_clamp(const CgdOp& op, cudaStream_t st);
 int launch_attnpool_embed_fwd(const CgdOp& op, cudaStream_t st);
 int launch_attnpool_embed_bwd(const CgdOp& op, cudaStream_t st);
 int launch_gn_apply_epi(const CgdOp& op, cudaStream_t st);
+int gn_grid_num_launches(const CgdOp& op);
+int gn_apply_epi_num_launches(const CgdOp& op);
 int launch_spherical(const CgdOp& op, cudaStream_t st);
 int launch_pmv_blend(const CgdOp& op, cudaStream_t st);
 int launch_guide_grad(const CgdOp& op, cudaStream_t st);

@@ -215,6 +215,13 @@ def gn_fused_cluster(N: int, HW: int, C: int, maxv: int) -> int:
 
 
 N_SMS = 148  # B200
+GN_STREAM_CTAS = 148 * 8  # partial-sum slots of the streaming GroupNorm engine (csrc/norm_stream.cu: kGsMaxCtas)
+
+
+def gn_partial_floats(N: int, gn_g: int) -> int:
+    """partials buffer of a GN_*_GRID op: room for the persistent engines (N * Gn rows of 64 floats) and for the streaming engine
+    (up to GN_STREAM_CTAS rows + the folded sums)"""
+    return max(N * gn_g, GN_STREAM_CTAS) * 64 + N * 64
 
 
 def gn_grid_ctas(N: int, HW: int, C: int) -> int:
@@ -411,15 +418,16 @@ class Plan:
         gn_g = gn_grid_ctas(N, HW, C) if self.grid_gn else 0
         epi = self._epi_stats.get(x.key()) if self.gn_epi_stats else None
         if epi is not None and not cs_f and gn_g and HW % 128 == 0 and C % 256 == 0:
+            sums = self.new(N * 64, "f", name + "_sums")  # folded group sums (streaming engine: fold launch -> apply launch)
             self.emit("GN_APPLY_EPI", flags=1 if silu else 0, i=[N, HW, C, x.ld, y.ld, gn_g, epi[1], 0], f=[eps],
-                      p=[self._ap(x), self._bp(gamma), self._bp(beta), embp, self._ap(y), self._bp(stats), self._bp(epi[0])], tag=name)
+                      p=[self._ap(x), self._bp(gamma), self._bp(beta), embp, self._ap(y), self._bp(stats), self._bp(epi[0]), self._bp(sums)], tag=name)
         elif cs_f:
             self.emit("GN_FWD_FUSED", flags=1 if silu else 0, i=[N, HW, C, x.ld, y.ld, cs_f], f=[eps],
                       p=[self._ap(x), self._bp(gamma), self._bp(beta), embp, self._ap(y), self._bp(stats)], tag=name)
         elif gn_g:
-            partials = self.new(N * gn_g * 64, "f", name + "_part")
+            partials = self.new(gn_partial_floats(N, gn_g), "f", name + "_part")
             bar = self.new(2, "u32", name + "_bar")
-            self.emit("GN_FWD_GRID", flags=1 if silu else 0, i=[N, HW, C, x.ld, y.ld, gn_g], f=[eps],
+            self.emit("GN_FWD_GRID", flags=1 if silu else 0, i=[N, HW, C, x.ld, y.ld, gn_g, gn_partial_floats(N, gn_g)], f=[eps],
                       p=[self._ap(x), self._bp(gamma), self._bp(beta), embp, self._ap(y), self._bp(stats), self._bp(partials), self._bp(bar)], tag=name)
         else:
             pp = max(1, 256 // (C // 8))
@@ -442,12 +450,12 @@ class Plan:
             if cs_b:
                 self.emit("GN_BWD_FUSED", flags=fl, i=[N, HW, C, dy.ld, x.ld, dx.ld, cs_b], f=[eps], p=common + [self._ap(dx)], tag="d_" + name)
             elif gn_g:
-                bpart = self.new(N * gn_g * 64, "f", name + "_bpart")
+                bpart = self.new(gn_partial_floats(N, gn_g), "f", name + "_bpart")
                 bbar = self.new(2, "u32", name + "_bbar")
                 # one scratch tensor shared by every GroupNorm backward of the plan (they run one after the other)
                 if self._gn_scratch is None or self._gn_scratch.numel < N * HW * C:
                     self._gn_scratch = self.new(N * HW * C, "h", "gn_bwd_dxhat")
-                self.emit("GN_BWD_GRID", flags=fl, i=[N, HW, C, dy.ld, x.ld, dx.ld, gn_g], f=[eps],
+                self.emit("GN_BWD_GRID", flags=fl, i=[N, HW, C, dy.ld, x.ld, dx.ld, gn_g, gn_partial_floats(N, gn_g)], f=[eps],
                           p=common + [self._ap(dx), self._bp(bpart), self._bp(bbar), self._bp(self._gn_scratch)], tag="d_" + name)
             else:
                 pp = max(1, 256 // (C // 8))

@@ -187,11 +187,14 @@ enum {
   /* single persistent launch for LARGE activations: statistics pass, grid-wide barrier (generation counted, no reset needed),
    * apply pass over the same pixel range (L2 hit).  One 512-thread CTA per SM: N * Gn must not exceed the SM count.
    * p0 x(h) p1 gamma p2 beta p3 emb|0 p4 y(h) p5 stats(f [N,32,2]) p6 partials(f [N,Gn,32,2]) p7 barrier(u32 [2], zero-initialised)
-   * i0 N i1 HW i2 C i3 ldx i4 ldy i5 Gn (CTAs per image) ; f0 eps ; flags 1 = SiLU.  C % 64 == 0 */
+   * i0 N i1 HW i2 C i3 ldx i4 ldy i5 Gn (CTAs per image) ; f0 eps ; flags 1 = SiLU.  C % 64 == 0
+   * i6 = capacity of p6 in floats (0 = N * Gn * 64).  With C % 256 == 0 and room for N * min(1184 / N, HW / (2 * rows per CTA)) * 64
+   * + N * 64 floats the op runs as three streaming launches instead (csrc/norm_stream.cu: per-CTA partial sums, fold, apply) */
   CGD_OP_GN_FWD_GRID = 35,
   /* backward of the above: p0 dy p1 x p2 stats p3 gamma p4 beta p5 emb|0 p6 dx(h) p7 partials p8 barrier
    * p9 scratch(h, dense [N,HW,C])|0: d xhat is stored once and streamed back instead of recomputing SiLU' in the apply pass
-   * i0 N i1 HW i2 C i3 ld_dy i4 ldx i5 ld_dx i6 Gn ; flags 1 = SiLU, 2 = accumulate into dx */
+   * i0 N i1 HW i2 C i3 ld_dy i4 ldx i5 ld_dx i6 Gn i7 capacity of p7 in floats (see GN_FWD_GRID i6) ; flags 1 = SiLU,
+   * 2 = accumulate into dx */
   CGD_OP_GN_BWD_GRID = 36,
   /* y = max(x, 0) on n fp16 elements (n % 8 == 0; in place allowed): p0 x p1 y ; i0 n.  [3P] VGG16 ReLU of lpips.LPIPS (K21) */
   CGD_OP_RELU_FWD = 37,
@@ -229,7 +232,8 @@ enum {
    * p7 = partials(f [m_tiles][Npad/8][2]): sum / sum of squares of the fp16 output per 128-pixel tile and 8-channel octet).
    * p0 x(h) p1 gamma p2 beta p3 emb|0 p4 y(h) p5 stats(f [N,32,2] = mean, rstd, for the backward) p6 partials
    * i0 N i1 HW (% 128 == 0) i2 C (% 256 == 0) i3 ldx i4 ldy i5 CTAs per image i6 octets per tile row of the partials (producer Npad / 8)
-   * i7 first octet of x's channels in the producer's output ; f0 eps ; flags 1 = SiLU */
+   * i7 first octet of x's channels in the producer's output ; f0 eps ; flags 1 = SiLU
+   * p7 scratch(f [N * 64])|0: when given, the op runs as a fold launch (partials -> group sums) + a streaming apply launch */
   CGD_OP_GN_APPLY_EPI = 49,
   /* MakeCutouts with use_augs=True (cgd/modules.py:12-24, 60-64): crop -> RandomHorizontalFlip -> +noise -> RandomAffine (nearest,
    * fill 0) -> +noise -> RandomPerspective (bilinear, fill 0) -> +noise -> RandomGrayscale -> +noise -> adaptive_avg_pool2d ->

@@ -115,9 +115,10 @@ def test_all_paths_agree_on_statistics():
     assert th.allclose(outs[1], outs[2], rtol=2e-5, atol=2e-6), float((outs[1] - outs[2]).abs().max())
 
 
-@pytest.mark.parametrize("engine", ["ring", "direct"])
+@pytest.mark.parametrize("engine", ["ring", "direct", "stream"])
 def test_grid_engines_forced(engine):
-    """The dispatch picks the ring or the direct-load engine by shape (norm_grid.cu: gng_use_direct); the choice is read from the
+    """The dispatch picks the streaming engine where it applies, else the ring or the direct-load persistent engine (norm_grid.cu:
+    gng_engine); the choice is read from the
     environment once per process, so every grid case is re-run with each engine forced in a child process."""
     import os, subprocess, sys
     env = dict(os.environ, CGD_GN_GRID_ENGINE=engine)
