@@ -478,6 +478,29 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
       L.tail_units = sched_total_units(total, 74);
     }
   }
+  // co-resident instantiation of the pair kernel for latency-bound launches (conv_tc2.cu, CO): at most one wave of tiles, or a short
+  // K loop per tile.  Ring depth so that two CTAs fit an SM's 227 KB.  CGD_CONV_CO = 0 | 1 (default off until measured: DESIGN.md).
+  p.nstages = 0;
+  L.co_resident = 0;
+  {
+    static int co_on = -1;
+    if (co_on < 0) {
+      const char* e = getenv("CGD_CONV_CO");
+      co_on = (e && e[0] == '1') ? 1 : 0;
+    }
+    const int64_t units = (int64_t)((L.m_tiles + 1) / 2) * L.n_tiles * p.splits;
+    const int kb_tile = p.kb_per_split > 0 ? p.kb_per_split : p.kblocks;
+    if (co_on && !L.cluster_split && conv_use_pair_kernel(L) && L.tail_units == 0 && !(op.flags & 2) && (units <= 74 || kb_tile <= 16)) {
+      const int stage_bytes = 128 * 64 * 2 + (BN / 2) * 64 * 2;
+      const int fixed = (BN >= 64 ? 2 * 128 * 64 * 2 : 0) + 1024 + 512 + 1024 /* per-CTA reservation */;
+      int ns = ((227 * 1024) / 2 - fixed) / stage_bytes;
+      ns = std::min(ns, 6);
+      if (ns >= 2) {
+        p.nstages = ns;
+        L.co_resident = 1;
+      }
+    }
+  }
   // flags 2: the epilogue also reduces its output tile to per-octet sums for the GroupNorm that follows (GN_APPLY_EPI): needs the
   // TMA-store epilogue and tiles that are full and are 128 consecutive pixels of one image
   p.epi_stats = nullptr;

@@ -30,6 +30,8 @@ struct ConvTcParams {
   void* out;
   float* ws;                         // split-K partials [splits][m_tiles*128][Npad]
   int tail_full;                     // pair kernel, TAIL instantiation: tiles kept whole (conv_sched.cuh); the rest is split in halves
+  int nstages;                       // pair kernel: operand-ring depth of this launch (<= Tc2Cfg::kStages); fewer stages = less shared memory, so that
+                                     // the next kernel's CTAs can become resident (programmatic dependent launch) while this one drains
   float* epi_stats;                  // flags 2: per (128-pixel tile, 8-channel octet) sum / sum of squares of the fp16 OUTPUT, [m_tiles][Npad/8][2]
 };
 
@@ -41,6 +43,7 @@ struct ConvTcLaunch {
   int tail_units;                    // > 0: launch the TAIL instantiation over this many schedule units
   ConvTcParams p;
   int BN, impl, m_tiles, n_tiles;
+  int co_resident;                   // pair kernel: launch the 2-CTAs-per-SM instantiation with a short operand ring (latency-bound layers)
   int cluster_split;                 // split-K inside a 2*splits-CTA cluster, reduced through DSMEM (conv_tc3.cu): no workspace, one launch
   const __half* A;
   const __half* Wp;

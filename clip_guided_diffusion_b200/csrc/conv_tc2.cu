@@ -67,20 +67,24 @@ __device__ __forceinline__ Tile2 decode_tile(const ConvTcParams& p, int t, int n
 // separate instantiation so that the default kernel's code and shared-memory layout are untouched
 // TAIL: the tiles of the last partial wave are cut in two BN/2-wide halves (conv_sched.cuh); `total_tiles` then counts schedule units
 // (p.tail_full whole tiles first, then the halves) and tmB4 loads a quarter of the weight tile per CTA.  Also a separate instantiation.
-template <int BN, bool STATS = false, bool TAIL = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+// CO: "co-resident" instantiation for latency-bound launches (one wave of tiles or a short K loop): compiled for two CTAs per SM
+// (<= 168 registers) and launched with a short operand ring (p.nstages), so that with programmatic dependent launch the NEXT kernel's
+// CTAs are resident -- barriers initialised, descriptors prefetched, TMEM allocated where columns are free -- while this one drains.
+template <int BN, bool STATS = false, bool TAIL = false, bool CO = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, CO ? 2 : 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                 const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmB4, const ConvTcParams p, int n_tiles,
                 int pair_tiles, int total_tiles) {
   using Cfg = Tc2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NS = p.nstages;  // operand-ring depth of this launch (host: 2 <= nstages <= Cfg::kStages; shared memory sized for it)
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;  // [out 0][out 1], 1024-byte aligned tiles
+  uint8_t* smem_b = smem + NS * Cfg::kABytes;
+  uint8_t* smem_epi = smem + NS * Cfg::kStageBytes;  // [out 0][out 1], 1024-byte aligned tiles
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* tmem_full_bar = empty_bar + NS;
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
   uint64_t* res_full_bar = tmem_empty_bar + Cfg::kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 2);
@@ -98,7 +102,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tma_prefetch_desc(&tmOut);
       if (p.res) tma_prefetch_desc(&tmRes);
     }
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's copy is the one used: one arrive per CTA (+ the TMA transaction bytes)
       mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
     }
@@ -157,7 +161,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t tx_bytes = half_unit ? 2u * (Cfg::kABytes + Cfg::kBBytes / 2) : 2u * Cfg::kStageBytes;
           if (leader) mbar_expect_tx(&full_bar[stage], (p.dbg & 1) ? 0u : tx_bytes);
           else mbar_arrive_remote(&full_bar[stage], 0);
-          if (++stage == Cfg::kStages) {
+          if (++stage == NS) {
             stage = 0;
             phase ^= 1;
           }
@@ -193,7 +197,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc2_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > tl.kb0 || k > 0) ? 1u : 0u);
           tc2_commit_mc(&empty_bar[stage], 0x3);  // frees the stage in both CTAs
           if (kb == tl.kb1 - 1) tc2_commit_mc(&tmem_full_bar[acc], 0x3);
-          if (++stage == Cfg::kStages) {
+          if (++stage == NS) {
             stage = 0;
             phase ^= 1;
           }
@@ -468,13 +472,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BN, bool STATS, bool TAIL>
+template <int BN, bool STATS, bool TAIL, bool CO = false>
 static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   using Cfg = Tc2Cfg<BN>;
-  constexpr int kSmem = Cfg::kSmemBytes + (STATS ? Cfg::kStatBytes : 0);
+  constexpr int kSmemMax = Cfg::kSmemBytes + (STATS ? Cfg::kStatBytes : 0);
   static DeviceOnce attr_set;
   if (attr_set.needed()) {
-    CGD_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STATS, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    CGD_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STATS, TAIL, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_set.mark();
   }
   const int pair_tiles = (L.m_tiles + 1) / 2;
@@ -486,8 +490,10 @@ static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   }
   ConvTcParams prm = L.p;
   prm.dbg = dbg;
+  prm.nstages = (L.p.nstages >= 2 && L.p.nstages <= Cfg::kStages) ? L.p.nstages : Cfg::kStages;
+  const int smem = kSmemMax - (Cfg::kStages - prm.nstages) * Cfg::kStageBytes;
   const int clusters = std::min(total, 74);  // 148 SMs = 74 TPC pairs
-  CGD_CUDA(launch_pdl(conv_tc2_kernel<BN, STATS, TAIL>, dim3(2 * clusters), dim3(kThreads2), kSmem, st, L.tmA, L.tmB2, L.tmOut, L.tmRes, L.tmB4, prm,
+  CGD_CUDA(launch_pdl(conv_tc2_kernel<BN, STATS, TAIL, CO>, dim3(2 * clusters), dim3(kThreads2), smem, st, L.tmA, L.tmB2, L.tmOut, L.tmRes, L.tmB4, prm,
                       L.n_tiles, pair_tiles, total));
   return 0;
 }
@@ -510,6 +516,17 @@ int conv_tc2_launch(const ConvTcLaunch& L, cudaStream_t st) {
   if (stats && tail) return launch_tc2_wide<true, true>(L, st);
   if (stats) return launch_tc2_wide<true, false>(L, st);
   if (tail) return launch_tc2_wide<false, true>(L, st);
+  if (L.co_resident) {
+    switch (L.BN) {
+      case 16: return launch_tc2<16, false, false, true>(L, st);
+      case 32: return launch_tc2<32, false, false, true>(L, st);
+      case 64: return launch_tc2<64, false, false, true>(L, st);
+      case 128: return launch_tc2<128, false, false, true>(L, st);
+      case 192: return launch_tc2<192, false, false, true>(L, st);
+      case 256: return launch_tc2<256, false, false, true>(L, st);
+      default: set_error("conv: unsupported BN %d", L.BN); return -1;
+    }
+  }
   switch (L.BN) {
     case 16: return launch_tc2<16, false, false>(L, st);
     case 32: return launch_tc2<32, false, false>(L, st);

@@ -124,3 +124,15 @@ def test_conv_special_layouts(impl):
     gott = plan.view(tok, (n, T, wd)).float()
     assert float((gott[:, 1:] - reft).abs().max() / reft.abs().max()) < 3e-3
     assert float(gott[:, 0].abs().max()) == 0.0  # cls rows untouched
+
+
+def test_co_resident_pair_kernel_instantiation():
+    """CGD_CONV_CO=1: latency-bound launches (one wave of tiles or a short K loop) take the pair kernel's two-CTAs-per-SM
+    instantiation with a short operand ring (csrc/conv_tc2.cu, CO).  The switch is read once per process: every conv case is re-run
+    in a child process with it on."""
+    import os, subprocess, sys
+    env = dict(os.environ, CGD_CONV_CO="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_conv.py", "-q", "-x", "-m", "gpu", "-k", "(auto or tc2pair or special) and not co_resident",
+                        "-p", "no:cacheprovider"], cwd=root, env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
