@@ -3,7 +3,9 @@
 Third-party (clip-anytorch 2.6.0 ``clip/model.py``), absent from /root/reference; the reference
 calls ``clip_model.encode_image`` at ``cgd/cgd.py:194`` and reads ``visual.input_resolution`` at
 ``cgd/clip_util.py:61,66``.  Restated from SURVEY.md Appendix A.3 with upstream state_dict keys
-(``visual.*``).  PARITY UNPINNED; structural pins = parameter counts (87.8 / 86.2 / 304.0 M).
+(``visual.*``).  PARITY UNPINNED (no upstream vectors); structural pins = parameter counts (87.8 / 86.2 / 304.0 M);
+CROSS-CHECKED against the independent HuggingFace ``transformers`` CLIP vision tower with re-keyed seeded weights
+(tests/test_oracle_crosscheck.py: forward and input gradient agree to 2e-5 for a tiny tower, ViT-B/32 and ViT-B/16).
 """
 from __future__ import annotations
 

@@ -3,7 +3,9 @@
 The reference builds it lazily (cgd/cgd.py:147-148) and calls ``lpips_vgg(x_in, init_tensor).sum() * init_scale``
 (cgd/cgd.py:220-224) with inputs in [-1, 1].  The ``lpips`` package (pin 0.1.4, uv.lock:609-610) and torchvision's VGG16
 weights are NOT in /root/reference and cannot be installed here: this follows the published algorithm and the
-upstream state_dict key layout -- PARITY UNPINNED, structure only (14.7 M VGG16 feature parameters + 1472 lin weights).
+upstream state_dict key layout -- PARITY UNPINNED (14.7 M VGG16 feature parameters + 1472 lin weights); the VGG16 trunk and its
+five tap positions are CROSS-CHECKED against torchvision.models.vgg16().features (the network lpips wraps) with the same seeded weights
+(tests/test_oracle_crosscheck.py).
 
     ScalingLayer: (x - shift) / scale, shift = [-.030, -.088, -.188], scale = [.458, .448, .450]
     VGG16 features, taps after relu1_2, relu2_2, relu3_3, relu4_3, relu5_3 (64, 128, 256, 512, 512 channels)
