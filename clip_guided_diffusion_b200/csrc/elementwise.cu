@@ -17,20 +17,24 @@ static inline int ew_blocks(int64_t work_items, int threads = 256) {
   return (int)b;
 }
 
+// Index arithmetic: these kernels decode a flat index into (n, y, x, vector).  With int64 operands every / and % is a ~100-instruction
+// software routine and the decode, not the memory system, bounded them (profiles/r02_launches_v1_warm.csv: UP2 128x128 -> 256x256 x 256
+// 16.6 us for 42 MB = 2.5 TB/s where ADD moves 100 MB at 6.3 TB/s).  IdxT = uint32_t whenever the element count allows (always, here).
 // ---- 2x2 pooling (sum * scale) on pixel-major [N,H,W,C]
+template <typename IdxT>
 __global__ void pool2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C, int64_t ldx,
                              int64_t ldy, float scale) {
   pdl_wait();
   pdl_launch_dependents();
-  const int V = C / 8, Ho = H / 2, Wo = W / 2;
-  const int64_t total = (int64_t)N * Ho * Wo * V;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % V);
-    int64_t pix = idx / V;
-    const int xo = (int)(pix % Wo);
-    pix /= Wo;
-    const int yo = (int)(pix % Ho);
-    const int n = (int)(pix / Ho);
+  const IdxT V = (IdxT)(C / 8), Ho = (IdxT)(H / 2), Wo = (IdxT)(W / 2);
+  const IdxT total = (IdxT)N * Ho * Wo * V;
+  for (IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IdxT)gridDim.x * blockDim.x) {
+    const IdxT pixv = idx / V;
+    const int v = (int)(idx - pixv * V);
+    const IdxT row = pixv / Wo;
+    const int xo = (int)(pixv - row * Wo);
+    const IdxT n_ = row / Ho;
+    const int yo = (int)(row - n_ * Ho), n = (int)n_;
     const __half* s = x + (((int64_t)n * H + 2 * yo) * W + 2 * xo) * ldx + v * 8;
     float a[8], b[8], c[8], d[8], o[8];
     unpack8(ld8(s), a);
@@ -42,27 +46,35 @@ __global__ void pool2_kernel(const __half* __restrict__ x, __half* __restrict__ 
     st8(y + (((int64_t)n * Ho + yo) * Wo + xo) * ldy + v * 8, pack8(o));
   }
 }
-// ---- nearest x2 up-sampling (* scale)
+// ---- nearest x2 up-sampling (* scale): one thread per INPUT vector, written to its four output pixels
+template <typename IdxT>
 __global__ void up2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C, int64_t ldx,
                            int64_t ldy, float scale) {
   pdl_wait();
   pdl_launch_dependents();
-  const int V = C / 8, Ho = H * 2, Wo = W * 2;
-  const int64_t total = (int64_t)N * Ho * Wo * V;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % V);
-    int64_t pix = idx / V;
-    const int xo = (int)(pix % Wo);
-    pix /= Wo;
-    const int yo = (int)(pix % Ho);
-    const int n = (int)(pix / Ho);
-    float a[8];
-    unpack8(ld8(x + (((int64_t)n * H + yo / 2) * W + xo / 2) * ldx + v * 8), a);
+  const IdxT V = (IdxT)(C / 8), Hi = (IdxT)H, Wi = (IdxT)W;
+  const int64_t Wo = 2 * (int64_t)W;
+  const IdxT total = (IdxT)N * Hi * Wi * V;
+  for (IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IdxT)gridDim.x * blockDim.x) {
+    const IdxT pixv = idx / V;
+    const int v = (int)(idx - pixv * V);
+    const IdxT row = pixv / Wi;
+    const int xi = (int)(pixv - row * Wi);
+    const IdxT n_ = row / Hi;
+    const int yi = (int)(row - n_ * Hi), n = (int)n_;
+    half8 h = ld8(x + (((int64_t)n * H + yi) * W + xi) * ldx + v * 8);
     if (scale != 1.f) {
+      float a[8];
+      unpack8(h, a);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] *= scale;
+      h = pack8(a);
     }
-    st8(y + (((int64_t)n * Ho + yo) * Wo + xo) * ldy + v * 8, pack8(a));
+    __half* o = y + (((int64_t)n * 2 * H + 2 * yi) * Wo + 2 * xi) * ldy + v * 8;
+    st8(o, h);
+    st8(o + ldy, h);
+    st8(o + Wo * ldy, h);
+    st8(o + Wo * ldy + ldy, h);
   }
 }
 __global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ c, int64_t rows, int C,
@@ -71,9 +83,10 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
   pdl_launch_dependents();
   const int V = C / 8;
   const int64_t total = rows * V;
+  const bool small = total + (int64_t)gridDim.x * blockDim.x < (int64_t(1) << 32);  // 32-bit decode (a 64-bit / and % cost ~200 instructions)
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % V);
-    const int64_t r = idx / V;
+    const int64_t r = small ? (int64_t)((uint32_t)idx / (uint32_t)V) : idx / V;
+    const int v = (int)(idx - r * V);
     float x[8], y[8];
     unpack8(ld8(a + r * lda + v * 8), x);
     unpack8(ld8(b + r * ldb + v * 8), y);
@@ -87,9 +100,10 @@ __global__ void copy_kernel(const __half* __restrict__ a, __half* __restrict__ c
   pdl_launch_dependents();
   const int V = C / 8;
   const int64_t total = rows * V;
+  const bool small = total + (int64_t)gridDim.x * blockDim.x < (int64_t(1) << 32);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % V);
-    const int64_t r = idx / V;
+    const int64_t r = small ? (int64_t)((uint32_t)idx / (uint32_t)V) : idx / V;
+    const int v = (int)(idx - r * V);
     st8(c + r * ldc + v * 8, ld8(a + r * lda + v * 8));
   }
 }
@@ -97,16 +111,26 @@ __global__ void copy_kernel(const __half* __restrict__ a, __half* __restrict__ c
 int launch_pool2(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], H = op.i[1], W = op.i[2], C = op.i[3], ldx = op.i[4], ldy = op.i[5];
   CGD_CHECK_ARG(N > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1], "pool2: bad args");
-  CGD_CUDA(launch_pdl(pool2_kernel, dim3(ew_blocks(N * (H / 2) * (W / 2) * (C / 8))), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W,
-                                                                        (int)C, ldx, ldy, op.f[0]));
+  const int64_t items = N * (H / 2) * (W / 2) * (C / 8);
+  if (items + (int64_t)148 * 8 * 256 < (int64_t(1) << 32))
+    CGD_CUDA(launch_pdl(pool2_kernel<uint32_t>, dim3(ew_blocks(items)), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W,
+                        (int)C, ldx, ldy, op.f[0]));
+  else
+    CGD_CUDA(launch_pdl(pool2_kernel<int64_t>, dim3(ew_blocks(items)), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W,
+                        (int)C, ldx, ldy, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
 int launch_up2(const CgdOp& op, cudaStream_t st) {
   const int64_t N = op.i[0], H = op.i[1], W = op.i[2], C = op.i[3], ldx = op.i[4], ldy = op.i[5];
   CGD_CHECK_ARG(N > 0 && H > 0 && W > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && op.p[0] && op.p[1], "up2: bad args");
-  CGD_CUDA(launch_pdl(up2_kernel, dim3(ew_blocks(N * H * W * 4 * (C / 8))), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W, (int)C,
-                                                                ldx, ldy, op.f[0]));
+  const int64_t items = N * H * W * (C / 8);  // one thread per input vector
+  if (items + (int64_t)148 * 8 * 256 < (int64_t(1) << 32))
+    CGD_CUDA(launch_pdl(up2_kernel<uint32_t>, dim3(ew_blocks(items)), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W, (int)C,
+                        ldx, ldy, op.f[0]));
+  else
+    CGD_CUDA(launch_pdl(up2_kernel<int64_t>, dim3(ew_blocks(items)), dim3(256), 0, st, (const __half*)op.p[0], (__half*)op.p[1], (int)N, (int)H, (int)W, (int)C,
+                        ldx, ldy, op.f[0]));
   CGD_LAUNCH_CHECK();
   return 0;
 }
