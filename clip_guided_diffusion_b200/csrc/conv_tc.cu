@@ -501,6 +501,13 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
       }
     }
   }
+  // flags 4: the "residual" operand is a QuickGELU pre-activation u and the epilogue computes acc * QuickGELU'(u) instead of acc + res
+  p.res_mode = 0;
+  if (op.flags & 4) {
+    CGD_CHECK_ARG(p.epi_tma && p.res != nullptr && p.bias == nullptr, "conv: flags 4 (QuickGELU' epilogue) needs the pair kernel's TMA-store epilogue, a res "
+                  "operand and no bias (BN=%d splits=%d Cout=%lld)", BN, p.splits, (long long)Cout);
+    p.res_mode = 1;
+  }
   // flags 2: the epilogue also reduces its output tile to per-octet sums for the GroupNorm that follows (GN_APPLY_EPI): needs the
   // TMA-store epilogue and tiles that are full and are 128 consecutive pixels of one image
   p.epi_stats = nullptr;

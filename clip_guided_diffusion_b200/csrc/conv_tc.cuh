@@ -30,6 +30,8 @@ struct ConvTcParams {
   void* out;
   float* ws;                         // split-K partials [splits][m_tiles*128][Npad]
   int tail_full;                     // pair kernel, TAIL instantiation: tiles kept whole (conv_sched.cuh); the rest is split in halves
+  int res_mode;                      // pair kernel, TMA-store epilogue: 0 = out = acc (+bias) + res ; 1 = out = acc * QuickGELU'(res) (CONV flags 4:
+                                     // the dgrad of the ViT's c_proj writes d(c_fc output) directly, `res` = the saved pre-activation)
   int nstages;                       // pair kernel: operand-ring depth of this launch (<= Tc2Cfg::kStages); fewer stages = less shared memory, so that
                                      // the next kernel's CTAs can become resident (programmatic dependent launch) while this one drains
   float* epi_stats;                  // flags 2: per (128-pixel tile, 8-channel octet) sum / sum of squares of the fp16 OUTPUT, [m_tiles][Npad/8][2]

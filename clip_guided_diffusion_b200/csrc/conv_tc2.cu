@@ -308,8 +308,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (has_res) {
                 float rr[8];
                 unpack8(*reinterpret_cast<const half8*>(rrow + unit), rr);
+                if (p.res_mode == 1) {  // CONV flags 4: out = acc * QuickGELU'(u), u = the tile TMA-loaded through the residual path
 #pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] += rr[e];
+                  for (int e = 0; e < 8; ++e) {
+                    const float sg = 1.f / (1.f + __expf(-1.702f * rr[e]));
+                    a[e] *= sg * (1.f + 1.702f * rr[e] * (1.f - sg));
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) a[e] += rr[e];
+                }
               }
               const half8 hv = pack8(a);
               *reinterpret_cast<half8*>(orow + unit) = hv;

@@ -253,6 +253,7 @@ class Plan:
         # instead of two.  Interpreter-verified, NOT yet run on the device: opt-in until it is (DESIGN.md "Next")
         self.gn_epi_stats = os.environ.get("CGD_GN_EPI_STATS", "0") == "1"
         self._epi_stats = {}  # output Act key -> (partials Buf, octets per tile row)
+        self._gelu_src = {}   # QuickGELU output Act key -> its pre-activation Act (dgrad-epilogue fusion, CONV flags 4)
         self.arena: Optional[th.Tensor] = None
         self.handle = None
         self._c_ops = None
@@ -329,7 +330,7 @@ class Plan:
 
     # ------------------------------------------------------------------ conv / GEMM
     def _emit_conv(self, x_ptr, x_strides, NB, H, W, Cin, wbuf, npad, Cout, taps, bias, res_ptr, res_strides, out_ptr, out_strides,
-                   out_f32=False, out_sc=1, tag="", b_ptr=None, b_batch=(0, 0), ldb=0, want_stats=False):
+                   out_f32=False, out_sc=1, tag="", b_ptr=None, b_batch=(0, 0), ldb=0, want_stats=False, res_gelu=False):
         """b_ptr / b_batch / ldb: batched-GEMM mode (attention): the B operand is a strided activation matrix selected by the
         tile's (h, n) instead of a packed weight."""
         m_tiles = conv_tile_count(NB, H, W)
@@ -360,10 +361,22 @@ class Plan:
                 and bn >= 64 and Cout % 64 == 0 and m_tiles >= 2 and m_tiles % 2 == 0 and tw * t_h == 128 and W % tw == 0 and H % t_h == 0
                 and (tw == W or t_h == 1)):
             stats = self.new(m_tiles * (npad // 8) * 2, "f", "epi_stats")
-        self.emit("CONV", flags=(1 if out_f32 else 0) | (2 if stats is not None else 0), i=i,
+        if res_gelu:
+            assert self.conv_gelu_epilogue_ok(NB, H, W, Cin, npad, Cout, taps), tag
+        self.emit("CONV", flags=(1 if out_f32 else 0) | (2 if stats is not None else 0) | (4 if res_gelu else 0), i=i,
                   p=[x_ptr, b_ptr if b_ptr is not None else self._bp(wbuf), self._bp(bias), res_ptr, out_ptr, self._bp(ws), self._bp(skbar)]
                   + ([self._bp(stats)] if stats is not None else []), tag=tag)
         return stats
+
+    def conv_gelu_epilogue_ok(self, NB, H, W, Cin, npad, Cout, taps) -> bool:
+        """would this conv run on the pair kernel with the TMA-store epilogue (the one that implements CONV flags 4)?  Mirrors the
+        choices of `_emit_conv` / conv_tc_prepare: tcgen05 path, >= 2 pixel tiles, no split-K, BN >= 64, whole 64-channel chunks."""
+        if self.conv_impl not in (0, 3) or os.environ.get("CGD_CONV_EPI_TMA", "1") == "0" or os.environ.get("CGD_QGELU_EPI", "1") == "0":
+            return False
+        m_tiles = conv_tile_count(NB, H, W)
+        kblocks = taps * Cin // 64
+        bn = pick_bn(npad, m_tiles, kblocks)
+        return (m_tiles >= 2 or self.conv_impl == 3) and pick_splits(m_tiles, npad // bn, kblocks, npad) == 1 and bn >= 64 and Cout % 64 == 0
 
     def _gn_would_use_epi(self, y: Act) -> bool:
         """would a GroupNorm over y take the statistics of the producing conv's epilogue?  (the large activations of the persistent
@@ -396,6 +409,16 @@ class Plan:
             if res is not None:
                 self.add_grad(res, dy)
             if w.bwd is None:
+                return
+            u = self._gelu_src.get(x.key())
+            if (u is not None and self.grad_of(x) is None and u.ld == u.C
+                    and self.conv_gelu_epilogue_ok(x.N, x.H, x.W, dy.C, w.bwd_npad, x.C, w.taps)):
+                # x = QuickGELU(u) feeds only this conv: its dgrad epilogue multiplies by QuickGELU'(u) (CONV flags 4) and writes
+                # d u directly -- no d a tensor, no QGELU_BWD launch (quick_gelu's own backward then finds no gradient and emits nothing)
+                du = self.act(u.N, u.H, u.W, u.C, "d_" + name + ".gelu")
+                self._emit_conv(self._ap(dy), self._strides(dy), x.N, x.H, x.W, dy.C, w.bwd, w.bwd_npad, x.C, w.taps, None,
+                                self._ap(u), self._strides(u), self._ap(du), self._strides(du), tag="d_" + name + "*gelu'", res_gelu=True)
+                self.add_grad(u, du)
                 return
             cur, has = self.writable_grad(x)
             dx = cur if has else self.act(x.N, x.H, x.W, x.C, "d_" + name)
@@ -743,6 +766,7 @@ class Plan:
         assert u.ld == u.C
         a = self.act(u.N, u.H, u.W, u.C, name)
         self.emit("QGELU_FWD", i=[u.rows * u.C], p=[self._ap(u), self._ap(a)], tag=name)
+        self._gelu_src[a.key()] = u
 
         def bwd():
             da = self.grad_of(a)

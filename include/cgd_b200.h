@@ -66,7 +66,8 @@ enum {
    *   i23 = 1: split-K inside a thread-block cluster of 2 * splits CTAs, reduced through distributed shared memory (one launch, no
    *   workspace; splits in 2..8, BN >= 64, BN / splits a multiple of 16, fp16 contiguous output, Cout % 8 == 0)
    *   flags: 1 = out is fp32 ; 2 = epilogue statistics for CGD_OP_GN_APPLY_EPI into p7 (pair kernel with the TMA-store epilogue, full
-   *   128-pixel tiles inside one image) */
+   *   128-pixel tiles inside one image) ; 4 = p3 is a QuickGELU pre-activation u and out = acc * QuickGELU'(u) instead of acc + res
+   *   (dgrad of the CLIP MLP's c_proj writing d c_fc directly; pair kernel with the TMA-store epilogue, no bias) */
   CGD_OP_CONV = 1,
   /* GroupNorm(32) statistics: per (image, chunk, group) partial sum / sum of squares; the last block per image
    * folds the chunks (fixed order, fp64) into (mean, rstd).  [3P] GroupNorm32.

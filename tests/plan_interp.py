@@ -76,7 +76,12 @@ class Interp:
         if op.p[2] is not None:
             y = y + self.flat(op.p[2], Cout)
         if op.p[3] is not None:
-            y = y + self.V(op.p[3], (NB, H, W, Cout), (rsn, rsh, rsw, 1)).float()
+            r = self.V(op.p[3], (NB, H, W, Cout), (rsn, rsh, rsw, 1)).float()
+            if op.flags & 4:  # out = acc * QuickGELU'(u)
+                sg = th.sigmoid(1.702 * r)
+                y = y * (sg * (1 + 1.702 * r * (1 - sg)))
+            else:
+                y = y + r
         out = self.V(op.p[4], (NB, H, W, Cout), (osn, osh, osw, osc))
         out.copy_(y)
         if op.flags & 2:  # epilogue statistics: per (128 consecutive pixels, 8-channel octet) sum / sum of squares of the STORED values

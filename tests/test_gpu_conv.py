@@ -136,3 +136,34 @@ def test_co_resident_pair_kernel_instantiation():
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_conv.py", "-q", "-x", "-m", "gpu", "-k", "(auto or tc2pair or special) and not co_resident",
                         "-p", "no:cacheprovider"], cwd=root, env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("rows", [800, 200])
+def test_quick_gelu_backward_fused_into_dgrad_epilogue(rows):
+    """CLIP MLP: a = QuickGELU(u), y = c_proj(a).  The dgrad of c_proj multiplies its accumulator by QuickGELU'(u) in the epilogue
+    (CONV flags 4: u arrives through the residual TMA path) and writes d u directly -- no d a tensor, no QGELU_BWD launch."""
+    from clip_guided_diffusion_b200._lib import OP
+    th.manual_seed(0)
+    Cin, Cout = 3072, 768
+    w = th.randn(Cout, Cin) * Cin ** -0.5
+    plan = Plan()
+    cw = pack_conv(plan, w, th.zeros(Cout), need_bwd=True, name="c_proj")
+    u = plan.act(1, 1, rows, Cin, "u")
+    a = plan.quick_gelu(u, "gelu")
+    y = plan.conv(a, cw, name="c_proj")
+    dy = plan.act(1, 1, rows, Cout, "dy")
+    plan._grads[y.key()] = dy
+    plan.backward()
+    plan.finalize("cuda")
+    codes = [op.code for op in plan.ops]
+    assert OP["QGELU_BWD"] not in codes and any(op.code == OP["CONV"] and op.flags & 4 for op in plan.ops)
+    uv = plan.view(u.buf, (rows, Cin)).normal_()
+    dv = plan.view(dy.buf, (rows, Cout)).normal_()
+    plan.run()
+    th.cuda.synchronize()
+    ug = uv.float().clone().requires_grad_()
+    yr = (ug * th.sigmoid(1.702 * ug)) @ w.cuda().t()
+    (gref,) = th.autograd.grad((yr * dv.float()).sum(), ug)
+    got = plan.view(plan.grad_of(u).buf, (rows, Cin)).float()
+    err = float((got - gref).abs().max() / gref.abs().max())
+    assert th.isfinite(got).all() and err < 3e-3, err
