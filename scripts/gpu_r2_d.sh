@@ -21,3 +21,17 @@ CGD_CONV_CO=1 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control n
 echo "=== launch list (stream + EPI)"
 CGD_GN_EPI_STATS=1 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02_launches_v2_stream_epi_warm.csv python scripts/profile_step.py eager > gpurun_out/ncu_launches.log 2>&1; tail -2 gpurun_out/ncu_launches.log
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02_launches_v2_stream_warm.csv python scripts/profile_step.py eager > gpurun_out/ncu_launches2.log 2>&1; tail -2 gpurun_out/ncu_launches2.log
+echo "=== ncu --set full, one launch per kernel family (raw page only: the .ncu-rep files exceed the 64 MiB return limit)"
+timeout 1200 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/r02_families python scripts/profile_families.py > gpurun_out/ncu_families.log 2>&1
+tail -3 gpurun_out/ncu_families.log
+ncu -i /tmp/r02_families.ncu-rep --page raw --csv > gpurun_out/r02_families_raw.csv 2>/dev/null; ls -la gpurun_out/r02_families_raw.csv
+CGD_GN_EPI_STATS=1 PF_ONLY=GN_APPLY_EPI,CONV_STATS timeout 600 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/r02_epi python scripts/profile_families.py > gpurun_out/ncu_epi.log 2>&1
+ncu -i /tmp/r02_epi.ncu-rep --page raw --csv > gpurun_out/r02_epi_raw.csv 2>/dev/null
+for tool in memcheck synccheck; do
+  echo "=== compute-sanitizer --tool $tool"
+  timeout 600 compute-sanitizer --tool $tool --error-exitcode 3 --log-file gpurun_out/r02_sanitizer_$tool.log \
+    python -m pytest tests/test_gpu_conv.py tests/test_gpu_norm.py tests/test_gpu_attention.py -q -m gpu -x -p no:cacheprovider \
+      -k "(conv3x3_64x64_c128 or conv3x3_32x32_c256_res or conv3x3_16x16_c512_splitk or conv1x1_skip or linear_m50 or cluster8 or special or norm or attention) and not simt and not tc1 and not forced and not co_resident" 2>&1 | tail -3
+  tail -3 gpurun_out/r02_sanitizer_$tool.log
+done
+du -sh gpurun_out
