@@ -537,6 +537,16 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
     L.tmOut = L.tmA;  // unused, but kernel parameters must be valid descriptors
     L.tmRes = L.tmA;
   }
+  // <= 8 output channels, fp32 output, 3x3 (UNet head, stem dgrad): halo-tile mma.sync kernel (conv_narrow.cu); CGD_CONV_NARROW=0 keeps
+  // the tcgen05 N = 16 tile for A/B runs
+  {
+    static int narrow_on = -1;
+    if (narrow_on < 0) {
+      const char* e = getenv("CGD_CONV_NARROW");
+      narrow_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    L.narrow = (narrow_on && conv_narrow_eligible(L)) ? 1 : 0;
+  }
   return 0;
 }
 
@@ -566,6 +576,7 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
     CGD_CUDA(launch_pdl(conv_simt_kernel, dim3(blocks), dim3(256), 0, st, L.A, L.Wp, p, L.a_sn, L.a_sh, L.a_sw, L.ldb, L.b_sh, L.b_sn));
     return 0;
   }
+  if (L.narrow) return conv_narrow_launch(L, st);
   if (L.cluster_split) return conv_tc3_launch(L, st);
   int rc = 0;
   if (conv_use_pair_kernel(L)) rc = conv_tc2_launch(L, st);

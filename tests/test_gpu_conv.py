@@ -167,3 +167,28 @@ def test_quick_gelu_backward_fused_into_dgrad_epilogue(rows):
     got = plan.view(plan.grad_of(u).buf, (rows, Cin)).float()
     err = float((got - gref).abs().max() / gref.abs().max())
     assert th.isfinite(got).all() and err < 3e-3, err
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 256, 256, 6), (1, 256, 256, 256, 3), (2, 37, 45, 128, 6), (1, 64, 64, 192, 6)],
+                         ids=["head_256x256", "stem_dgrad_256x256", "ragged_b2", "64px_c192"])
+def test_narrow_conv_halo_kernel(shape):
+    """3x3 conv with <= 8 output channels and an fp32 NCHW output (UNet head 256 -> 6, stem dgrad 256 -> 3): the halo-tile
+    mma.sync kernel (csrc/conv_narrow.cu) against F.conv2d, including image borders that cut the 4 x 32 tiles."""
+    NB, H, W, C, Cout = shape
+    th.manual_seed(2)
+    plan = Plan(conv_impl=0)
+    w = th.randn(Cout, C, 3, 3) * (9 * C) ** -0.5
+    b = th.randn(Cout) * 0.1
+    cw = pack_conv(plan, w, b, need_bwd=False, name="head")
+    x = plan.act(NB, H, W, C, "x")
+    out = plan.new(NB * Cout * H * W, "f", "out")
+    plan._emit_conv(plan._ap(x), plan._strides(x), NB, H, W, C, cw.fwd, cw.fwd_npad, Cout, 9, cw.bias, None, None, (out, 0), (Cout * H * W, W, 1),
+                    out_f32=True, out_sc=H * W, tag="head")
+    plan.finalize("cuda")
+    xv = plan.view(x.buf, (NB, H, W, C)).normal_()
+    plan.run()
+    th.cuda.synchronize()
+    ref = F.conv2d(xv.float().permute(0, 3, 1, 2), w.cuda().half().float(), b.cuda(), padding=1)
+    got = plan.view(out, (NB, Cout, H, W))
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert th.isfinite(got).all() and err < 2e-3, err
