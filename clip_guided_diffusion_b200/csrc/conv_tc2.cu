@@ -311,8 +311,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (p.res_mode == 1) {  // CONV flags 4: out = acc * QuickGELU'(u), u = the tile TMA-loaded through the residual path
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
-                    const float sg = 1.f / (1.f + __expf(-1.702f * rr[e]));
-                    a[e] *= sg * (1.f + 1.702f * rr[e] * (1.f - sg));
+                    const float sg = rcp_ftz(1.f + ex2_ftz(-1.702f * 1.4426950408889634f * rr[e]));  // sigmoid(1.702 u), MUFU ex2 + rcp
+                    a[e] *= sg * fmaf(1.702f * rr[e], 1.f - sg, 1.f);
                   }
                 } else {
 #pragma unroll

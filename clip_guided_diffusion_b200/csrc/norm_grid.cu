@@ -442,8 +442,8 @@ int launch_gn_bwd_stream(const CgdOp& op, cudaStream_t st);
 // Engines behind GN_FWD_GRID / GN_BWD_GRID.  Measured: persistent ring vs persistent direct (profiles/r01_gn_microbench_v4.txt): direct
 // wins the backward of the 256x256 level (51 vs 57 us at C = 256, 86 vs 104 us at C = 512), ties at 128x128 x 512, loses 3 - 5 us
 // elsewhere.  Both are schedule-bound, not traffic-bound (profiles/r02_launches_v1*: the one-trip GN_APPLY_EPI took as long as the
-// two-trip kernel), which the streaming engine fixes; it is the default where it applies (C % 256 == 0 and the op's partials buffer
-// has room for its per-CTA partial sums: i6 forward / i7 backward = capacity in floats, 0 = the persistent engines' N * Gn * 64).
+// two-trip kernel); the streaming engine (three launches, norm_stream.cu) is the attempt at that, opt-in until it measures faster
+// (needs C % 256 == 0 and room in the op's partials buffer: i6 forward / i7 backward = capacity in floats).
 // CGD_GN_GRID_ENGINE = ring | direct | stream forces one engine for A/B runs.
 enum { kEngRing = 0, kEngDirect = 1, kEngStream = 2 };
 static int gng_engine(bool backward, int64_t N, int64_t HW, int64_t C, int64_t cap_floats) {
@@ -456,8 +456,7 @@ static int gng_engine(bool backward, int64_t N, int64_t HW, int64_t C, int64_t c
   if (forced == 3) return stream_ok ? kEngStream : (gn_grid2_supports(C) ? kEngDirect : kEngRing);
   if (forced == 1 || !gn_grid2_supports(C)) return kEngRing;
   if (forced == 2) return kEngDirect;
-  if (stream_ok) return kEngStream;
-  return (backward && HW * C >= (int64_t(1) << 23)) ? kEngDirect : kEngRing;
+  return (backward && HW * C >= (int64_t(1) << 23)) ? kEngDirect : kEngRing;  // streaming engine: opt-in (see norm_stream.cu header)
 }
 int gn_grid_num_launches(const CgdOp& op) {  // for cgd_plan_num_launches
   const bool bwd = op.code == CGD_OP_GN_BWD_GRID;

@@ -415,7 +415,7 @@ static bool epi_use_stream(const CgdOp& op) {
   static int off = -1;
   if (off < 0) {
     const char* e = getenv("CGD_GN_GRID_ENGINE");
-    off = (e && (e[0] == 'r' || e[0] == 'd')) ? 1 : 0;
+    off = (e && e[0] == 's') ? 0 : 1;  // streaming engine opt-in
   }
   return !off && op.p[7] != nullptr;
 }

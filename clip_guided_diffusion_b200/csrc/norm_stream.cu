@@ -99,38 +99,53 @@ __device__ __forceinline__ void gs_block_partials(const GsMap& m, int vpg, float
 // ------------------------------------------------------------------------------------------------ fold
 // sums[n][g][2] = sum over the partials of image n, group g.  mode 0: partials [n][G][32][2] (one row per CTA of a *_stats_stream
 // launch); mode 1: conv-epilogue partials [n * tpi + tile][octs][2] (CONV flags 2), group g = octets [oct0 + g * vpg, + vpg) of each
-// of the image's tpi tiles.  grid = N, 1024 threads: warp g folds group g, lanes stride over the partials (independent loads,
-// double accumulation, fixed order), five shuffles.
-__global__ void __launch_bounds__(1024)
+// of the image's tpi tiles.  grid (32 groups, N), 256 threads: every thread takes a few partials with INDEPENDENT loads (a first
+// version -- one CTA per image, each lane adding ~37 partials in a load -> add chain -- spent 22 us per call waiting for one L2 round
+// trip per addend), then a fixed-order reduction: lanes by shuffle, the eight warps through shared memory.  Deterministic.
+constexpr int kFoldThreads = 256;
+__global__ void __launch_bounds__(kFoldThreads)
 gn_fold_kernel(const float* __restrict__ partials, float* __restrict__ sums, int mode, int G, int tpi, int octs, int oct0, int vpg) {
+  __shared__ float2 wsum[kFoldThreads / 32];
   pdl_wait();
   pdl_launch_dependents();
-  const int n = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double s = 0.0, q = 0.0;
-  if (mode == 0) {
-    const float* p = partials + ((int64_t)n * G) * 64 + g * 2;
-    for (int j = lane; j < G; j += 32) {
-      const float2 v = __ldcg(reinterpret_cast<const float2*>(p + (int64_t)j * 64));
-      s += (double)v.x;
-      q += (double)v.y;
-    }
-  } else {
-    const int cnt = tpi * vpg;
-    for (int m = lane; m < cnt; m += 32) {
-      const int tile = m / vpg, o = m - tile * vpg;
-      const float2 v = __ldcg(reinterpret_cast<const float2*>(partials + (((int64_t)n * tpi + tile) * octs + oct0 + g * vpg + o) * 2));
-      s += (double)v.x;
-      q += (double)v.y;
-    }
+  const int g = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
+  const int cnt = mode == 0 ? G : tpi * vpg;
+  auto addr = [&](int m) -> const float2* {
+    if (mode == 0) return reinterpret_cast<const float2*>(partials + (((int64_t)n * G + m) * 32 + g) * 2);
+    const int tile = m / vpg, o = m - tile * vpg;
+    return reinterpret_cast<const float2*>(partials + (((int64_t)n * tpi + tile) * octs + oct0 + g * vpg + o) * 2);
+  };
+  float s = 0.f, q = 0.f;
+  int m = t;
+  for (; m + 3 * kFoldThreads < cnt; m += 4 * kFoldThreads) {
+    const float2 v0 = __ldcg(addr(m)), v1 = __ldcg(addr(m + kFoldThreads)), v2 = __ldcg(addr(m + 2 * kFoldThreads)),
+                 v3 = __ldcg(addr(m + 3 * kFoldThreads));
+    s += (v0.x + v1.x) + (v2.x + v3.x);
+    q += (v0.y + v1.y) + (v2.y + v3.y);
+  }
+  float2 r[3];
+  int nr = 0;
+  for (; m < cnt && nr < 3; m += kFoldThreads) r[nr++] = __ldcg(addr(m));
+  for (int i = 0; i < nr; ++i) {
+    s += r[i].x;
+    q += r[i].y;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
-  if (lane == 0) {
-    sums[((int64_t)n * 32 + g) * 2] = (float)s;
-    sums[((int64_t)n * 32 + g) * 2 + 1] = (float)q;
+  if ((t & 31) == 0) wsum[t >> 5] = make_float2(s, q);
+  __syncthreads();
+  if (t == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < kFoldThreads / 32; ++w) {
+      a += wsum[w].x;
+      b += wsum[w].y;
+    }
+    sums[((int64_t)n * 32 + g) * 2] = a;
+    sums[((int64_t)n * 32 + g) * 2 + 1] = b;
   }
 }
 
@@ -147,16 +162,28 @@ gn_stats_stream_kernel(const __half* __restrict__ x, float* __restrict__ partial
   float2 s[4], q[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) s[j] = q[j] = make_float2(0.f, 0.f);
-  if (m.active)
-    for (int r = blockIdx.x * m.RP + m.slot; r < HW; r += G * m.RP) {
-      float2 f[4];
-      gs_unpack(gs_ld(xb + (int64_t)r * ldx), f);
+  auto acc = [&](const uint4& v) {
+    float2 f[4];
+    gs_unpack(v, f);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s[j] = add2(s[j], f[j]);
-        q[j] = fma2(f[j], f[j], q[j]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      s[j] = add2(s[j], f[j]);
+      q[j] = fma2(f[j], f[j], q[j]);
     }
+  };
+  if (m.active) {  // four independent 16-byte loads in flight per thread: one per trip left the kernel at 3 TB/s (latency-bound)
+    const int st = G * m.RP;
+    int r = blockIdx.x * m.RP + m.slot;
+    for (; r + 3 * st < HW; r += 4 * st) {
+      const uint4 v0 = gs_ld(xb + (int64_t)r * ldx), v1 = gs_ld(xb + (int64_t)(r + st) * ldx), v2 = gs_ld(xb + (int64_t)(r + 2 * st) * ldx),
+                  v3 = gs_ld(xb + (int64_t)(r + 3 * st) * ldx);
+      acc(v0);
+      acc(v1);
+      acc(v2);
+      acc(v3);
+    }
+    for (; r < HW; r += st) acc(gs_ld(xb + (int64_t)r * ldx));
+  }
   const float ts = ((s[0].x + s[0].y) + (s[1].x + s[1].y)) + ((s[2].x + s[2].y) + (s[3].x + s[3].y));
   const float tq = ((q[0].x + q[0].y) + (q[1].x + q[1].y)) + ((q[2].x + q[2].y) + (q[3].x + q[3].y));
   gs_block_partials(m, C / 256, ts, tq, red, partials + ((int64_t)n * G + blockIdx.x) * 64);
@@ -191,9 +218,9 @@ gn_apply_stream_kernel(const __half* __restrict__ x, const float* __restrict__ g
   gs_coef(n, m.col, C, gamma, beta, emb, mu, rs, A, B, Gn);
   const __half* xb = x + (int64_t)n * HW * ldx + m.col * 8;
   __half* yb = y + (int64_t)n * HW * ldy + m.col * 8;
-  for (int r = blockIdx.x * m.RP + m.slot; r < HW; r += G * m.RP) {
+  auto apply = [&](const uint4& v, int r) {
     float2 f[4];
-    gs_unpack(gs_ld(xb + (int64_t)r * ldx), f);
+    gs_unpack(v, f);
     uint4 o;
     uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
@@ -203,7 +230,18 @@ gn_apply_stream_kernel(const __half* __restrict__ x, const float* __restrict__ g
       ow[j] = gs_f2h(t);
     }
     *reinterpret_cast<uint4*>(yb + (int64_t)r * ldy) = o;
+  };
+  const int st = G * m.RP;
+  int r = blockIdx.x * m.RP + m.slot;
+  for (; r + 3 * st < HW; r += 4 * st) {
+    const uint4 v0 = gs_ld(xb + (int64_t)r * ldx), v1 = gs_ld(xb + (int64_t)(r + st) * ldx), v2 = gs_ld(xb + (int64_t)(r + 2 * st) * ldx),
+                v3 = gs_ld(xb + (int64_t)(r + 3 * st) * ldx);
+    apply(v0, r);
+    apply(v1, r + st);
+    apply(v2, r + 2 * st);
+    apply(v3, r + 3 * st);
   }
+  for (; r < HW; r += st) apply(gs_ld(xb + (int64_t)r * ldx), r);
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -227,19 +265,31 @@ gn_bwd_stats_stream_kernel(const __half* __restrict__ dy, const __half* __restri
   float2 s[4], q[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) s[j] = q[j] = make_float2(0.f, 0.f);
-  if (m.active)
-    for (int r = blockIdx.x * m.RP + m.slot; r < HW; r += G * m.RP) {
-      float2 d[4], a[4];
-      gs_unpack(gs_ld(db + (int64_t)r * ld_dy), d);
-      gs_unpack(gs_ld(xb + (int64_t)r * ldx), a);
+  auto acc = [&](const uint4& vd, const uint4& vx) {
+    float2 d[4], a[4];
+    gs_unpack(vd, d);
+    gs_unpack(vx, a);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 e = silu ? mul2(d[j], silu_grad2(fma2(a[j], A[j], B[j]))) : d[j];
-        const float2 xh = fma2(a[j], rs2, nmr2);
-        s[j] = add2(s[j], e);
-        q[j] = fma2(e, xh, q[j]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 e = silu ? mul2(d[j], silu_grad2(fma2(a[j], A[j], B[j]))) : d[j];
+      const float2 xh = fma2(a[j], rs2, nmr2);
+      s[j] = add2(s[j], e);
+      q[j] = fma2(e, xh, q[j]);
     }
+  };
+  if (m.active) {
+    const int st = G * m.RP;
+    int r = blockIdx.x * m.RP + m.slot;
+    for (; r + 2 * st < HW; r += 3 * st) {  // six independent loads in flight
+      const uint4 d0 = gs_ld(db + (int64_t)r * ld_dy), x0 = gs_ld(xb + (int64_t)r * ldx);
+      const uint4 d1 = gs_ld(db + (int64_t)(r + st) * ld_dy), x1 = gs_ld(xb + (int64_t)(r + st) * ldx);
+      const uint4 d2 = gs_ld(db + (int64_t)(r + 2 * st) * ld_dy), x2 = gs_ld(xb + (int64_t)(r + 2 * st) * ldx);
+      acc(d0, x0);
+      acc(d1, x1);
+      acc(d2, x2);
+    }
+    for (; r < HW; r += st) acc(gs_ld(db + (int64_t)r * ld_dy), gs_ld(xb + (int64_t)r * ldx));
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {  // the channel gains are constant over pixels: applied once
     s[j] = mul2(s[j], Gn[j]);
@@ -274,13 +324,11 @@ gn_bwd_apply_stream_kernel(const __half* __restrict__ dy, const __half* __restri
   const __half* db = dy + (int64_t)n * HW * ld_dy + m.col * 8;
   const __half* xb = x + (int64_t)n * HW * ldx + m.col * 8;
   __half* ob = dx + (int64_t)n * HW * ld_dx + m.col * 8;
-  for (int r = blockIdx.x * m.RP + m.slot; r < HW; r += G * m.RP) {
+  auto apply = [&](const uint4& vd, const uint4& vx, uint4 o, int r) {
     float2 d[4], a[4];
-    gs_unpack(gs_ld(db + (int64_t)r * ld_dy), d);
-    gs_unpack(gs_ld(xb + (int64_t)r * ldx), a);
-    uint4 o;
+    gs_unpack(vd, d);
+    gs_unpack(vx, a);
     uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-    if (accumulate) o = *reinterpret_cast<const uint4*>(ob + (int64_t)r * ld_dx);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 e = silu ? mul2(d[j], silu_grad2(fma2(a[j], A[j], B[j]))) : d[j];
@@ -289,7 +337,18 @@ gn_bwd_apply_stream_kernel(const __half* __restrict__ dy, const __half* __restri
       ow[j] = gs_f2h(v);
     }
     *reinterpret_cast<uint4*>(ob + (int64_t)r * ld_dx) = o;
+  };
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  auto ld_acc = [&](int r) { return accumulate ? *reinterpret_cast<const uint4*>(ob + (int64_t)r * ld_dx) : zero; };
+  const int st = G * m.RP;
+  int r = blockIdx.x * m.RP + m.slot;
+  for (; r + st < HW; r += 2 * st) {  // four to six independent loads in flight
+    const uint4 d0 = gs_ld(db + (int64_t)r * ld_dy), x0 = gs_ld(xb + (int64_t)r * ldx), o0 = ld_acc(r);
+    const uint4 d1 = gs_ld(db + (int64_t)(r + st) * ld_dy), x1 = gs_ld(xb + (int64_t)(r + st) * ldx), o1 = ld_acc(r + st);
+    apply(d0, x0, o0, r);
+    apply(d1, x1, o1, r + st);
   }
+  for (; r < HW; r += st) apply(gs_ld(db + (int64_t)r * ld_dy), gs_ld(xb + (int64_t)r * ldx), ld_acc(r), r);
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -309,7 +368,7 @@ int launch_gn_fwd_stream(const CgdOp& op, cudaStream_t st) {
   float* partials = (float*)op.p[6];
   float* sums = partials + (int64_t)N * G * 64;
   CGD_CUDA(launch_pdl(gn_stats_stream_kernel, dim3(G, (unsigned)N), dim3(kGsThreads), 0, st, (const __half*)op.p[0], partials, (int)HW, (int)C, ldx));
-  CGD_CUDA(launch_pdl(gn_fold_kernel, dim3((unsigned)N), dim3(1024), 0, st, (const float*)partials, sums, 0, G, 0, 0, 0, (int)(C / 256)));
+  CGD_CUDA(launch_pdl(gn_fold_kernel, dim3(32, (unsigned)N), dim3(kFoldThreads), 0, st, (const float*)partials, sums, 0, G, 0, 0, 0, (int)(C / 256)));
   CGD_CUDA(launch_pdl(gn_apply_stream_kernel, dim3(G, (unsigned)N), dim3(kGsThreads), 0, st, (const __half*)op.p[0], (const float*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (const float*)sums, (int)HW, (int)C, ldx, ldy,
                       op.f[0], (int)(op.flags & 1)));
@@ -326,7 +385,7 @@ int launch_gn_bwd_stream(const CgdOp& op, cudaStream_t st) {
   CGD_CUDA(launch_pdl(gn_bwd_stats_stream_kernel, dim3(G, (unsigned)N), dim3(kGsThreads), 0, st, (const __half*)op.p[0], (const __half*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (const float*)op.p[4], (const float*)op.p[5], partials, (int)HW, (int)C, ld_dy, ldx,
                       silu));
-  CGD_CUDA(launch_pdl(gn_fold_kernel, dim3((unsigned)N), dim3(1024), 0, st, (const float*)partials, sums, 0, G, 0, 0, 0, (int)(C / 256)));
+  CGD_CUDA(launch_pdl(gn_fold_kernel, dim3(32, (unsigned)N), dim3(kFoldThreads), 0, st, (const float*)partials, sums, 0, G, 0, 0, 0, (int)(C / 256)));
   CGD_CUDA(launch_pdl(gn_bwd_apply_stream_kernel, dim3(G, (unsigned)N), dim3(kGsThreads), 0, st, (const __half*)op.p[0], (const __half*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (const float*)op.p[4], (const float*)op.p[5], (__half*)op.p[6], (const float*)sums,
                       (int)HW, (int)C, ld_dy, ldx, ld_dx, silu, acc));
@@ -342,7 +401,7 @@ int launch_gn_apply_epi_stream(const CgdOp& op, cudaStream_t st) {
   CGD_CHECK_ARG(op.p[7] != nullptr, "gn_apply_epi (stream engine): p7 (scratch for the folded sums, N * 64 floats) missing");
   const int G = gs_ctas(N, HW, C);
   float* sums = (float*)op.p[7];
-  CGD_CUDA(launch_pdl(gn_fold_kernel, dim3((unsigned)N), dim3(1024), 0, st, (const float*)op.p[6], sums, 1, 0, (int)(HW / 128), (int)octs, (int)oct0,
+  CGD_CUDA(launch_pdl(gn_fold_kernel, dim3(32, (unsigned)N), dim3(kFoldThreads), 0, st, (const float*)op.p[6], sums, 1, 0, (int)(HW / 128), (int)octs, (int)oct0,
                       (int)(C / 256)));
   CGD_CUDA(launch_pdl(gn_apply_stream_kernel, dim3(G, (unsigned)N), dim3(kGsThreads), 0, st, (const __half*)op.p[0], (const float*)op.p[1],
                       (const float*)op.p[2], (const float*)op.p[3], (__half*)op.p[4], (float*)op.p[5], (const float*)sums, (int)HW, (int)C, ldx, ldy,

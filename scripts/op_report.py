@@ -47,7 +47,7 @@ def shape_of(kind, op):
 
 
 # the launch list was taken with the streaming GroupNorm engine unless CGD_GN_GRID_ENGINE said otherwise (same variable as the library)
-STREAM = os.environ.get("CGD_GN_GRID_ENGINE", "stream")[0] == "s"
+STREAM = os.environ.get("CGD_GN_GRID_ENGINE", "direct")[0] == "s"
 
 
 def main():
