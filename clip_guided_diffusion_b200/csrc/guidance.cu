@@ -114,7 +114,8 @@ __global__ void cutouts_bwd_kernel(const __half* __restrict__ dpatch, const int*
 // every element: 43 us forward / 108 us backward at cfg2 for ~15 MB of (mostly L2-resident) traffic.  Here the bin tables are built
 // once per block in shared memory, a warp owns one output row (forward) or one image row (backward), lanes walk consecutive x --
 // coalesced reads of the source row(s), contiguous fp16 writes per patch row -- and nothing is divided in the inner loops.
-// Same arithmetic in the same order as the kernels above (bit-identical results: tests/test_gpu_guidance.py goldens).
+// Same sums in the same order as the kernels above; the bin mean / normalisation use reciprocals instead of IEEE divisions (<= 1 fp32
+// ulp apart, far inside the fp16 output's rounding; checked against the reference-generated goldens, tests/test_gpu_guidance.py).
 constexpr int CUT_MAX_CS = 1024;   // shared tables: output extent
 constexpr int CUT_FWD_ROWS = 8;    // output rows (= warps) per block
 
@@ -122,7 +123,9 @@ constexpr int CUT_FWD_ROWS = 8;    // output rows (= warps) per block
 __global__ void __launch_bounds__(32 * CUT_FWD_ROWS)
 cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coords, __half* __restrict__ out, int B, int H, int W, int cutn,
                         int cs, int P, int Kpad, float3 mean, float3 stdv) {
-  __shared__ short xs_t[CUT_MAX_CS], xe_t[CUT_MAX_CS];
+  // per output column: first source column, bin width, offset of (patch column, kx) inside a patch row of the output
+  __shared__ short xs_t[CUT_MAX_CS], xw_t[CUT_MAX_CS];
+  __shared__ int xo_t[CUT_MAX_CS];
   pdl_wait();
   pdl_launch_dependents();
   const int rb = cs / CUT_FWD_ROWS + (cs % CUT_FWD_ROWS ? 1 : 0);  // row blocks per (k, b)
@@ -134,7 +137,9 @@ cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coo
     int s0, e0;
     pool_bin(o, Sx, cs, s0, e0);
     xs_t[o] = (short)s0;
-    xe_t[o] = (short)e0;
+    xw_t[o] = (short)(e0 - s0);
+    const int px = o / P;
+    xo_t[o] = px * Kpad + (o - px * P);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,18 +150,24 @@ cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coo
     int ys, ye;
     pool_bin(oy, Sy, cs, ys, ye);
     const int py = oy / P, ky = oy - py * P;
+    const int bh = ye - ys;
+    // mean over the bin and CLIP normalisation as one affine map per bin width: ((acc / n + 1) / 2 - mu) / sd = acc * a_w + c
+    // (reciprocals instead of two IEEE divisions per element: the result differs from the division form by <= 1 fp32 ulp, far inside
+    // the fp16 output's rounding; the element-per-thread fallback keeps the divisions)
     for (int c = 0; c < 3; ++c) {
-      const float* src = x + ((int64_t)b * 3 + c) * H * W + (int64_t)offy * W + offx;
+      const float* src = x + ((int64_t)b * 3 + c) * H * W + (int64_t)(offy + ys) * W + offx;
       const float mu = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
-      const float sd = c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z);
+      const float rsd = 1.f / (c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z));
+      const float cc = (0.5f - mu) * rsd;
+      __half* oc = orow + (int64_t)py * g * Kpad + c * PP + ky * P;
       for (int ox = lane; ox < cs; ox += 32) {
-        const int xs = xs_t[ox], xe = xe_t[ox];
+        const int xs = xs_t[ox], xw = xw_t[ox];
+        const float* q = src + xs;
         float acc = 0.f;
-        for (int yy = ys; yy < ye; ++yy)
-          for (int xx = xs; xx < xe; ++xx) acc += src[(int64_t)yy * W + xx];
-        acc /= (float)((ye - ys) * (xe - xs));
-        const int px = ox / P, kx = ox - px * P;
-        orow[(int64_t)(py * g + px) * Kpad + c * PP + ky * P + kx] = __float2half_rn(((acc + 1.f) * 0.5f - mu) / sd);
+        for (int yy = 0; yy < bh; ++yy, q += W)
+          for (int xx = 0; xx < xw; ++xx) acc += q[xx];
+        const float aw = 0.5f * rsd / (float)(bh * xw);
+        oc[xo_t[ox]] = __float2half_rn(fmaf(acc, aw, cc));
       }
     }
   }
@@ -174,8 +185,9 @@ cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coo
 // block = (image b, image row yg); thread -> xg = tid, tid + blockDim, ...; per cutout the row's output-row range is found once per
 // block (thread 0 .. cutn-1 fill the shared table), the column range once per (thread, cutout) and shared by the 3 channels
 constexpr int CUT_MAX_CUTN = 128;
+constexpr int CUT_BWD_THREADS = 128;  // columns per block: H * ceil(W / 128) blocks per image keep >= 3 CTAs per SM at 256 x 256
 constexpr int CUT_MAX_ROWS = 8;  // output rows whose bins contain one input row: <= ceil(cs / S) + 1 (up-sampling 64 -> 224: 5)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CUT_BWD_THREADS)
 cutouts_bwd_rows_kernel(const __half* __restrict__ dpatch, const int* __restrict__ coords, float* __restrict__ dx, int B, int H, int W, int cutn,
                         int cs, int P, int Kpad, float3 stdv, float scale) {
   // per cutout, for image row yg: window geometry, the range [oy0, oy1] of output rows whose bins can contain it and, for the first
@@ -185,7 +197,8 @@ cutouts_bwd_rows_kernel(const __half* __restrict__ dpatch, const int* __restrict
       r_h[CUT_MAX_CUTN][CUT_MAX_ROWS];
   pdl_wait();
   pdl_launch_dependents();
-  const int yg = blockIdx.x % H, b = blockIdx.x / H;
+  const int xblocks = (W + CUT_BWD_THREADS - 1) / CUT_BWD_THREADS;
+  const int xb = blockIdx.x % xblocks, yg = (blockIdx.x / xblocks) % H, b = blockIdx.x / (xblocks * H);
   for (int k = threadIdx.x; k < cutn; k += blockDim.x) {
     const int offx = coords[k * 3 + 0], offy = coords[k * 3 + 1], S = coords[k * 3 + 2];
     const int Sy = min(S, H - offy), Sx = min(S, W - offx);
@@ -210,7 +223,7 @@ cutouts_bwd_rows_kernel(const __half* __restrict__ dpatch, const int* __restrict
   __syncthreads();
   const int g = cs / P, G2 = g * g, PP = P * P;
   const float sd3[3] = {stdv.x, stdv.y, stdv.z};
-  for (int xg = threadIdx.x; xg < W; xg += blockDim.x) {
+  for (int xg = xb * CUT_BWD_THREADS + threadIdx.x; xg < min(W, (xb + 1) * CUT_BWD_THREADS); xg += blockDim.x) {
     float acc[3] = {0.f, 0.f, 0.f};
     for (int k = 0; k < cutn; ++k) {
       const int oy0 = r_oy0[k], oy1 = r_oy1[k];
@@ -237,10 +250,10 @@ cutouts_bwd_rows_kernel(const __half* __restrict__ dpatch, const int* __restrict
           if (rx < xs || rx >= xe) continue;
           const int px = ox / P, kx = ox - px * P;
           const __half* q = dp + (int64_t)(py * g + px) * Kpad + ky * P + kx;
-          const float inv = (float)(bh * (xe - xs));
-          acc[0] += __half2float(q[0]) / inv;
-          acc[1] += __half2float(q[PP]) / inv;
-          acc[2] += __half2float(q[2 * PP]) / inv;
+          const float rinv = 1.f / (float)(bh * (xe - xs));  // one reciprocal per tap instead of three divisions (<= 1 ulp apart)
+          acc[0] = fmaf(__half2float(q[0]), rinv, acc[0]);
+          acc[1] = fmaf(__half2float(q[PP]), rinv, acc[1]);
+          acc[2] = fmaf(__half2float(q[2 * PP]), rinv, acc[2]);
         }
       }
     }
@@ -385,7 +398,7 @@ int launch_cutouts_bwd(const CgdOp& op, cudaStream_t st) {
   if (int rc = cutout_check(op)) return rc;
   const int64_t B = op.i[0], H = op.i[1], W = op.i[2];
   if (op.i[3] <= CUT_MAX_CUTN && op.i[4] <= 32768) {  // row-per-block gather with shared per-cutout row tables
-    CGD_CUDA(launch_pdl(cutouts_bwd_rows_kernel, dim3((unsigned)(B * H)), dim3(256), 0, st, (const __half*)op.p[0], (const int*)op.p[1], (float*)op.p[2],
+    CGD_CUDA(launch_pdl(cutouts_bwd_rows_kernel, dim3((unsigned)(B * H * ceil_div(W, CUT_BWD_THREADS))), dim3(CUT_BWD_THREADS), 0, st, (const __half*)op.p[0], (const int*)op.p[1], (float*)op.p[2],
                         (int)B, (int)H, (int)W, (int)op.i[3], (int)op.i[4], (int)op.i[5], (int)op.i[6], make_float3(op.f[3], op.f[4], op.f[5]), op.f[6]));
     CGD_LAUNCH_CHECK();
     return 0;
