@@ -104,7 +104,22 @@ __device__ __forceinline__ float rcp_ftz(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// sigmoid(v) = 1/2 + 1/2 tanh(v / 2): ONE MUFU op (tanh.approx.f32, relative error 2^-11) instead of two (ex2 + rcp).  Why it matters
+// (ncu, profiles/r02_families_summary.txt): the XU (SFU) pipe was 56 % busy in the streaming GroupNorm-apply kernel -- two MUFU per
+// element at 16 lanes / clk / SM put a ~20 us floor under a kernel whose 67 MB of traffic need ~12 us; every SiLU / SiLU' in the
+// GroupNorm kernels is XU-bound the same way.  Accuracy: |sigmoid error| <= 2.5e-4 absolute, i.e. |silu error| <= 2.5e-4 |v| -- the
+// size of the fp16 rounding of the output itself; the full-size parity tests (tests/test_gpu_baseline_configs.py) bound the effect.
+// -DCGD_SIGMOID_EX2RCP restores the two-MUFU form (A/B builds).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#ifdef CGD_SIGMOID_EX2RCP
 __device__ __forceinline__ float sigmoid_fast(float v) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * v)); }
+#else
+__device__ __forceinline__ float sigmoid_fast(float v) { return fmaf(0.5f, tanh_approx(0.5f * v), 0.5f); }
+#endif
 __device__ __forceinline__ float silu_f(float v) { return v * sigmoid_fast(v); }
 // d silu(v)/dv
 __device__ __forceinline__ float silu_grad_f(float v) {
@@ -135,6 +150,7 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
+#ifdef CGD_SIGMOID_EX2RCP
 // silu on a pair: t * 1 / (1 + 2^(-log2e * t))
 __device__ __forceinline__ float2 silu2(float2 t) {
   const float2 u = mul2(t, make_float2(-1.4426950408889634f, -1.4426950408889634f));
@@ -150,6 +166,21 @@ __device__ __forceinline__ float2 silu_grad2(float2 t) {
   const float2 w = fma2(t, fma2(s, make_float2(-1.f, -1.f), one), one);  // 1 + t * (1 - s)
   return mul2(s, w);
 }
+#else
+// silu on a pair: with h = t / 2, t * sigmoid(t) = h * tanh(h) + h  (one MUFU and two packed ops per pair element)
+__device__ __forceinline__ float2 silu2(float2 t) {
+  const float2 h = mul2(t, make_float2(0.5f, 0.5f));
+  return fma2(h, make_float2(tanh_approx(h.x), tanh_approx(h.y)), h);
+}
+// d silu / dt on a pair: s * (1 + t * (1 - s)), s = 1/2 + 1/2 tanh(t / 2)
+__device__ __forceinline__ float2 silu_grad2(float2 t) {
+  const float2 half2v = make_float2(0.5f, 0.5f), one = make_float2(1.f, 1.f);
+  const float2 h = mul2(t, half2v);
+  const float2 s = fma2(make_float2(tanh_approx(h.x), tanh_approx(h.y)), half2v, half2v);
+  const float2 w = fma2(t, fma2(s, make_float2(-1.f, -1.f), one), one);  // 1 + t * (1 - s)
+  return mul2(s, w);
+}
+#endif
 
 // ---------------------------------------------------------------- global-memory barrier among co-resident CTAs
 // bar[0] = arrival count (returns to 0), bar[1] = generation (only ever incremented): reusable across launches / graph replays
