@@ -120,8 +120,13 @@ constexpr int CUT_MAX_CS = 1024;   // shared tables: output extent
 constexpr int CUT_FWD_ROWS = 8;    // output rows (= warps) per block
 
 // block = (cutout k, image b, 8 output rows); warp = one output row oy, all 3 channels; lane -> ox = lane, lane + 32, ...
+template <typename OutT> __device__ __forceinline__ OutT cut_out(float v);
+template <> __device__ __forceinline__ __half cut_out<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ float cut_out<float>(float v) { return v; }
+// OutT = __half: the CLIP tower's input; float: the stand-alone MakeCutouts surface (the reference returns fp32 from adaptive_avg_pool2d)
+template <typename OutT>
 __global__ void __launch_bounds__(32 * CUT_FWD_ROWS)
-cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coords, __half* __restrict__ out, int B, int H, int W, int cutn,
+cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coords, OutT* __restrict__ out, int B, int H, int W, int cutn,
                         int cs, int P, int Kpad, float3 mean, float3 stdv) {
   // per output column: first source column, bin width, offset of (patch column, kx) inside a patch row of the output
   __shared__ short xs_t[CUT_MAX_CS], xw_t[CUT_MAX_CS];
@@ -145,7 +150,7 @@ cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int oy = rblk * CUT_FWD_ROWS + warp;
   const int g = cs / P, G2 = g * g, PP = P * P;
-  __half* orow = out + ((int64_t)k * B + b) * G2 * Kpad;
+  OutT* orow = out + ((int64_t)k * B + b) * G2 * Kpad;
   if (oy < cs) {
     int ys, ye;
     pool_bin(oy, Sy, cs, ys, ye);
@@ -159,7 +164,7 @@ cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coo
       const float mu = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
       const float rsd = 1.f / (c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z));
       const float cc = (0.5f - mu) * rsd;
-      __half* oc = orow + (int64_t)py * g * Kpad + c * PP + ky * P;
+      OutT* oc = orow + (int64_t)py * g * Kpad + c * PP + ky * P;
       for (int ox = lane; ox < cs; ox += 32) {
         const int xs = xs_t[ox], xw = xw_t[ox];
         const float* q = src + xs;
@@ -167,7 +172,7 @@ cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coo
         for (int yy = 0; yy < bh; ++yy, q += W)
           for (int xx = 0; xx < xw; ++xx) acc += q[xx];
         const float aw = 0.5f * rsd / (float)(bh * xw);
-        oc[xo_t[ox]] = __float2half_rn(fmaf(acc, aw, cc));
+        oc[xo_t[ox]] = cut_out<OutT>(fmaf(acc, aw, cc));
       }
     }
   }
@@ -177,7 +182,7 @@ cutouts_fwd_rows_kernel(const float* __restrict__ x, const int* __restrict__ coo
     for (int r = 0; r < CUT_FWD_ROWS; ++r) {
       const int oyr = rblk * CUT_FWD_ROWS + r;
       if (oyr >= cs || oyr % P) continue;
-      for (int i = threadIdx.x; i < g * pad; i += blockDim.x) orow[(int64_t)((oyr / P) * g + i / pad) * Kpad + 3 * PP + i % pad] = __float2half_rn(0.f);
+      for (int i = threadIdx.x; i < g * pad; i += blockDim.x) orow[(int64_t)((oyr / P) * g + i / pad) * Kpad + 3 * PP + i % pad] = cut_out<OutT>(0.f);
     }
   }
 }
@@ -380,14 +385,21 @@ int launch_cutouts_fwd(const CgdOp& op, cudaStream_t st) {
   if (int rc = cutout_check(op)) return rc;
   const int64_t B = op.i[0], cutn = op.i[3], cs = op.i[4], P = op.i[5], Kpad = op.i[6];
   const int64_t total = cutn * B * (cs / P) * (cs / P) * Kpad;
+  const bool f32_out = op.flags & 1;  // stand-alone MakeCutouts surface: fp32 pooled cutouts like the reference's
   if (cs <= CUT_MAX_CS && op.i[1] < 32768 && op.i[2] < 32768) {  // row-per-warp kernel: bin tables in shared memory
     const int64_t rb = ceil_div(cs, CUT_FWD_ROWS);
-    CGD_CUDA(launch_pdl(cutouts_fwd_rows_kernel, dim3((unsigned)(cutn * B * rb)), dim3(32 * CUT_FWD_ROWS), 0, st, (const float*)op.p[0], (const int*)op.p[1],
-                        (__half*)op.p[2], (int)B, (int)op.i[1], (int)op.i[2], (int)cutn, (int)cs, (int)P, (int)Kpad,
-                        make_float3(op.f[0], op.f[1], op.f[2]), make_float3(op.f[3], op.f[4], op.f[5])));
+    if (f32_out)
+      CGD_CUDA(launch_pdl(cutouts_fwd_rows_kernel<float>, dim3((unsigned)(cutn * B * rb)), dim3(32 * CUT_FWD_ROWS), 0, st, (const float*)op.p[0],
+                          (const int*)op.p[1], (float*)op.p[2], (int)B, (int)op.i[1], (int)op.i[2], (int)cutn, (int)cs, (int)P, (int)Kpad,
+                          make_float3(op.f[0], op.f[1], op.f[2]), make_float3(op.f[3], op.f[4], op.f[5])));
+    else
+      CGD_CUDA(launch_pdl(cutouts_fwd_rows_kernel<__half>, dim3((unsigned)(cutn * B * rb)), dim3(32 * CUT_FWD_ROWS), 0, st, (const float*)op.p[0],
+                          (const int*)op.p[1], (__half*)op.p[2], (int)B, (int)op.i[1], (int)op.i[2], (int)cutn, (int)cs, (int)P, (int)Kpad,
+                          make_float3(op.f[0], op.f[1], op.f[2]), make_float3(op.f[3], op.f[4], op.f[5])));
     CGD_LAUNCH_CHECK();
     return 0;
   }
+  CGD_CHECK_ARG(!f32_out, "cutouts_fwd: fp32 output (flags 1) needs cut_size <= %d", CUT_MAX_CS);
   CGD_CUDA(launch_pdl(cutouts_fwd_kernel, dim3(gw_blocks(total)), dim3(256), 0, st, (const float*)op.p[0], (const int*)op.p[1], (__half*)op.p[2], (int)B, (int)op.i[1],
                                                       (int)op.i[2], (int)cutn, (int)cs, (int)P, (int)Kpad,
                                                       make_float3(op.f[0], op.f[1], op.f[2]), make_float3(op.f[3], op.f[4], op.f[5])));

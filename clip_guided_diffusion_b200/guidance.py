@@ -70,10 +70,10 @@ class MakeCutouts(th.nn.Module):
         cs = self.cut_size
         x = input.detach().float().contiguous()
         cdev = th.tensor(coords, dtype=th.int32, device=x.device)
-        out = th.empty(len(coords) * B, 1, 3 * cs * cs, dtype=th.float16, device=x.device)
         lib = _lib.load()
         if self.use_augs:  # the reference applies its augmentations to the raw cutout values: feed 2x - 1, mean 0 / std 1
             from . import augs
+            out = th.empty(len(coords) * B, 1, 3 * cs * cs, dtype=th.float16, device=x.device)
             Smax = min(H, W)
             noise = th.zeros(len(coords), 4, B, 3, Smax, Smax, device=x.device)
             prm = augs.draw_aug_params(coords, B, H, W, noise_device=x.device, noise_out=noise).to(x.device)
@@ -88,15 +88,19 @@ class MakeCutouts(th.nn.Module):
                 op.p[j] = t.data_ptr()
             _lib.check(lib.cgd_run_op(ctypes.byref(op), ctypes.c_void_p(th.cuda.current_stream().cuda_stream)), "cutouts_aug_fwd")
             return out.view(len(coords) * B, 3, cs, cs).float()
-        mean = (ctypes.c_float * 3)(0.5, 0.5, 0.5)  # with std 0.5 and the kernel's (x+1)/2 this yields the raw pooled value
-        std = (ctypes.c_float * 3)(0.5, 0.5, 0.5)
-        # patch = cut_size -> a single "patch" per cutout whose (c, ky, kx) order is exactly CHW
-        rc = lib.cgd_cutouts_fwd(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(cdev.data_ptr()), ctypes.c_void_p(out.data_ptr()),
-                                 ctypes.c_int64(B), ctypes.c_int64(H), ctypes.c_int64(W), ctypes.c_int64(len(coords)),
-                                 ctypes.c_int64(cs), ctypes.c_int64(cs), ctypes.c_int64(3 * cs * cs), mean, std,
-                                 ctypes.c_void_p(th.cuda.current_stream().cuda_stream))
-        _lib.check(rc, "cgd_cutouts_fwd")
-        return out.view(len(coords) * B, 3, cs, cs).float()
+        # mean 0.5 / std 0.5 with the kernel's (x + 1) / 2 yield the raw pooled value; flags 1 = fp32 output like the reference's
+        # adaptive_avg_pool2d (the fused step writes fp16 straight into the CLIP tower's patch buffer instead)
+        out32 = th.empty(len(coords) * B, 3, cs, cs, dtype=th.float32, device=x.device)
+        op = _lib.CgdOp()
+        op.code, op.flags = _lib.OP["CUTOUTS_FWD"], 1
+        for j, v in enumerate([B, H, W, len(coords), cs, cs, 3 * cs * cs]):
+            op.i[j] = v
+        for j, v in enumerate([0.5, 0.5, 0.5, 0.5, 0.5, 0.5]):
+            op.f[j] = v
+        for j, t in enumerate([x, cdev, out32]):
+            op.p[j] = t.data_ptr()
+        _lib.check(lib.cgd_run_op(ctypes.byref(op), ctypes.c_void_p(th.cuda.current_stream().cuda_stream)), "cgd_cutouts_fwd")
+        return out32
 
 
 class EngineModel:
@@ -232,6 +236,11 @@ class GuidedStepB200:
                 if H != W or cutn_variants:
                     raise NotImplementedError("ResizeRight cutouts: square images and a single cutout count only")
                 from .resize_right import T_MAX
+                # the device tables hold T_MAX = 16 taps per output: lanczos3 with antialiasing needs ceil(6 * S / cs) of them, and the
+                # largest window the reference draws is min(H, W) (cgd/modules.py:40) -- checked here, once, not in the middle of a run
+                if -(-6 * min(H, W) // cs) > T_MAX:
+                    raise ValueError(f"cutout_resize='lanczos3': windows up to {min(H, W)} px down to {cs} px need {-(-6 * min(H, W) // cs)} taps, "
+                                     f"the device tables hold {T_MAX} (images up to {T_MAX * cs // 6} px)")
                 self.rr_left = p.new(cutn * cs, "i32", "rr_left")
                 self.rr_w = p.new(cutn * cs * T_MAX, "f", "rr_weights")
                 self.rr_taps = p.new(cutn, "i32", "rr_taps")

@@ -131,6 +131,7 @@ enum {
    * Output is written directly in ViT patch order: [cutn*B (row k*B+b), g*g, Kpad] with k = (c, ky, kx).
    * p0 x_in(f NCHW [B,3,H,W]) p1 coords(int32 [cutn,3] = offsetx, offsety, size) p2 patches(h)
    * i0 B i1 H i2 W i3 cutn i4 cut_size i5 patch i6 Kpad ; f0..2 mean f3..5 std */
+  /* (CUTOUTS_FWD flags 1: p2 is fp32 instead of fp16 -- the stand-alone MakeCutouts surface returns fp32 like the reference) */
   CGD_OP_CUTOUTS_FWD = 21,
   /* gather-style backward (no atomics): p0 dpatches(h) p1 coords p2 dx_in(f NCHW) ; i as fwd ; f3..5 std ; f6 scale */
   CGD_OP_CUTOUTS_BWD = 22,
