@@ -453,7 +453,7 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   // the image are clipped by the TMA unit; needs fp16 channel-contiguous output and whole 64-channel chunks
   p.epi_tma = (!L.cluster_split && conv_use_pair_kernel(L) && !p.out_f32 && p.out_sc == 1 && p.splits == 1 && BN >= 64 && Cout % 64 == 0) ? 1 : 0;
   if (const char* e = getenv("CGD_CONV_EPI_TMA")) if (e[0] == '0') p.epi_tma = 0;
-  // split last wave (opt-in: CGD_CONV_TAIL=1, device run pending): pair kernel with the TMA-store epilogue, no split-K, tail halves fit a wave
+  // split last wave (opt-in: CGD_CONV_TAIL=1; device-validated, measured no gain -- DESIGN.md): pair kernel with the TMA-store epilogue, no split-K, tail halves fit a wave
   L.tail_units = 0;
   p.tail_full = 0;
   L.tmB4 = L.tmB2;

@@ -1,7 +1,6 @@
 """GPU: the pair conv kernel with a split last wave (CGD_CONV_TAIL=1; csrc/conv_sched.cuh, TAIL instantiation of conv_tc2_kernel).
-Written after the round's GPU budget was spent: the schedule arithmetic is verified exhaustively on the host
-(tests/test_conv_sched.py), the device code is not yet run, so this file is opt-in (CGD_TEST_TAIL=1); scripts/gpu_round2_first.sh
-runs it and times the dominant layer both ways."""
+The schedule arithmetic is verified exhaustively on the host
+(tests/test_conv_sched.py); device-validated in round 2, the path stays opt-in (no measured gain)."""
 import os
 import subprocess
 import sys
