@@ -128,4 +128,151 @@ int conv_narrow_launch(const ConvTcLaunch& L, cudaStream_t st) {
   return 0;
 }
 
+
+// ================================================================================================ 8 x 8 images: weight-streaming kernel
+// conv_small_kernel -- 3x3 / 1x1 convolution of an 8 x 8 image (M = 64 pixels): the UNet's deepest level and its attention 1x1s.
+//
+// Why (profiles/r02_launches_v3_warm.csv): on the tcgen05 tiles these layers are 64 pixels in a 128- / 256-row tile, split 8 - 16 ways
+// along K with an fp32 workspace and a reduce launch (or a 16-CTA cluster): 18.6 us for the 1024 -> 1024 3x3 (18.9 MB of weights =
+// 4 us at HBM speed), 10 - 18 us for the 1x1s -- 56 launches, ~1 ms per step of pure latency.  Here the problem is turned around: a CTA
+// owns EIGHT OUTPUT CHANNELS of one image and the whole K extent -- no split-K, no reduction, one launch.  Its 8 x K weight slab
+// (<= 148 KB) is fetched with cp.async BEFORE the grid dependency resolves (weights are step-invariant: under programmatic dependent
+// launch the HBM stream overlaps the previous kernel's tail), the activations stream through a 4-stage ring of 64-channel slices (halo
+// tile for 3x3), and the product runs on mma.sync.m16n8k16 whose N = 8 is exactly the CTA's channel slab: 8 warps = 4 pixel tiles x 2
+// halves of every slice's K, two independent accumulator chains per warp, one shared-memory add at the end.
+constexpr int SM_THREADS = 256, SM_STAGES = 4;
+
+template <int TAPS>
+__global__ void __launch_bounds__(SM_THREADS)
+conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, const float* __restrict__ bias, const __half* __restrict__ res,
+                  __half* __restrict__ out, int Cin, int64_t a_sn, int64_t a_sh, int64_t a_sw, int64_t ldb, int64_t o_sn, int64_t o_sh, int64_t o_sw,
+                  int64_t r_sn, int64_t r_sh, int64_t r_sw) {
+  constexpr int HALO = TAPS == 9 ? 10 : 8;           // stage tile edge in pixels
+  constexpr int PIXS = HALO * HALO;                   // 100 / 64 pixels per 64-channel slice
+  constexpr int STAGE = PIXS * 128;
+  extern __shared__ __align__(128) uint8_t sm_smem[];
+  const int K = TAPS * Cin, wld = K + 8;
+  uint8_t* stage_base = sm_smem;
+  __half* ws = reinterpret_cast<__half*>(sm_smem + SM_STAGES * STAGE);
+  __shared__ float red[4][32][4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * 8, img = blockIdx.y;
+  // weight slab of this CTA's 8 output channels: independent of the previous kernel
+  {
+    const uint32_t wbase = as_smem(ws);
+    const __half* wsrc = Wp + (int64_t)n0 * ldb;
+    for (int v = tid; v < 8 * (K / 8); v += SM_THREADS) {
+      const int r = v / (K / 8), c = (v - r * (K / 8)) * 8;
+      nr_cp16(wbase + (r * wld + c) * 2, wsrc + (int64_t)r * ldb + c, true);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  const __half* An = A + (int64_t)img * a_sn;
+  const int nslices = Cin / 64;
+  auto load_slice = [&](int s) {
+    const uint32_t base = as_smem(stage_base + (s % SM_STAGES) * STAGE);
+    for (int v = tid; v < PIXS * 8; v += SM_THREADS) {
+      const int pix = v >> 3, ch = v & 7;
+      const int hy = pix / HALO, hx = pix - hy * HALO;
+      const int y = TAPS == 9 ? hy - 1 : hy, x = TAPS == 9 ? hx - 1 : hx;
+      const bool ok = y >= 0 && y < 8 && x >= 0 && x < 8;
+      const __half* src = ok ? An + (int64_t)y * a_sh + (int64_t)x * a_sw + s * 64 + ch * 8 : A;
+      nr_cp16(base + pix * 128 + ((ch ^ (pix & 7)) << 4), src, ok);
+    }
+  };
+  for (int s = 0; s < SM_STAGES; ++s) {  // always SM_STAGES groups in flight (empty ones past the end keep the wait counts uniform)
+    if (s < nslices) load_slice(s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  float acc[2][4];
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+  const int mt = warp & 3, kh = warp >> 2;  // pixel tile (image rows 2 mt, 2 mt + 1), half of each slice's k16 steps
+  const int mi = lane >> 3;
+  const int wrow = lane >> 2, wcol = (lane & 3) * 2;
+  const int p = (lane & 7) + (mi & 1) * 8;        // pixel of this lane's ldmatrix row inside the 16-pixel tile
+  const int py = 2 * mt + (p >> 3), px = p & 7;   // its image coordinates
+  for (int s = 0; s < nslices; ++s) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(SM_STAGES - 1) : "memory");  // the weight slab and slice s have landed
+    __syncthreads();
+    const uint32_t base = as_smem(stage_base + (s % SM_STAGES) * STAGE);
+#pragma unroll
+    for (int tap = 0; tap < TAPS; ++tap) {
+      const int dy = TAPS == 9 ? tap / 3 - 1 : 0, dx = TAPS == 9 ? tap % 3 - 1 : 0;
+      const int pix = TAPS == 9 ? (py + 1 + dy) * HALO + px + 1 + dx : py * HALO + px;
+      const __half* wk = ws + wrow * wld + tap * Cin + s * 64 + wcol;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int ks = kh * 2 + j;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wk + ks * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wk + ks * 16 + 8);
+        const int ch = ks * 2 + (mi >> 1);
+        uint32_t a[4];
+        ldsm_x4(base + pix * 128 + ((ch ^ (pix & 7)) << 4), a);
+        mma16816(acc[j], a, b0, b1);
+      }
+    }
+    __syncthreads();  // every warp is done with this stage before it is refilled
+    if (s + SM_STAGES < nslices) load_slice(s + SM_STAGES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  float c[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) c[e] = acc[0][e] + acc[1][e];
+  if (kh == 1) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[mt][lane][e] = c[e];
+  }
+  __syncthreads();
+  if (kh == 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e] += red[mt][lane][e];
+    const int ch = n0 + wcol;
+    const float b0 = bias ? bias[ch] : 0.f, b1 = bias ? bias[ch + 1] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // accumulator rows lane / 4 and lane / 4 + 8 of the 16-pixel tile
+      const int q = wrow + h * 8, y = 2 * mt + (q >> 3), x = q & 7;
+      float v0 = c[2 * h] + b0, v1 = c[2 * h + 1] + b1;
+      if (res) {
+        const float2 r = __half22float2(*reinterpret_cast<const __half2*>(res + (int64_t)img * r_sn + (int64_t)y * r_sh + (int64_t)x * r_sw + ch));
+        v0 += r.x;
+        v1 += r.y;
+      }
+      *reinterpret_cast<__half2*>(out + (int64_t)img * o_sn + (int64_t)y * o_sh + (int64_t)x * o_sw + ch) = __floats2half2_rn(v0, v1);
+    }
+  }
+}
+
+static inline int conv_small_smem(int taps, int Cin) { return SM_STAGES * (taps == 9 ? 100 : 64) * 128 + 8 * (taps * Cin + 8) * 2; }
+
+bool conv_small_eligible(const ConvTcLaunch& L) {
+  const ConvTcParams& p = L.p;
+  return (p.taps == 9 || p.taps == 1) && p.H == 8 && p.W == 8 && p.Cin % 64 == 0 && p.Cout % 8 == 0 && !p.out_f32 && p.out_sc == 1 && !p.b_batched &&
+         p.res_mode == 0 && p.epi_stats == nullptr && (L.impl == 0 || L.impl == 3) && L.ldb % 8 == 0 && p.out_sw % 2 == 0 &&
+         (p.res == nullptr || p.res_sw % 2 == 0) && conv_small_smem(p.taps, p.Cin) <= 200 * 1024;
+}
+
+int conv_small_launch(const ConvTcLaunch& L, cudaStream_t st) {
+  const ConvTcParams& p = L.p;
+  const int smem = conv_small_smem(p.taps, p.Cin);
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
+    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set.mark();
+  }
+  const dim3 grid((unsigned)(p.Cout / 8), (unsigned)p.NB);
+  if (p.taps == 9)
+    CGD_CUDA(launch_pdl(conv_small_kernel<9>, grid, dim3(SM_THREADS), (size_t)smem, st, L.A, L.Wp, p.bias, p.res, (__half*)p.out, p.Cin, L.a_sn, L.a_sh, L.a_sw,
+                        L.ldb, p.out_sn, p.out_sh, p.out_sw, p.res_sn, p.res_sh, p.res_sw));
+  else
+    CGD_CUDA(launch_pdl(conv_small_kernel<1>, grid, dim3(SM_THREADS), (size_t)smem, st, L.A, L.Wp, p.bias, p.res, (__half*)p.out, p.Cin, L.a_sn, L.a_sh, L.a_sw,
+                        L.ldb, p.out_sn, p.out_sh, p.out_sw, p.res_sn, p.res_sh, p.res_sw));
+  return 0;
+}
+
 }  // namespace cgd

@@ -547,6 +547,16 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
     }
     L.narrow = (narrow_on && conv_narrow_eligible(L)) ? 1 : 0;
   }
+  // 8 x 8 images (deepest UNet level): one launch, a CTA per 8 output channels streaming its whole weight slab (conv_narrow.cu,
+  // conv_small_kernel) instead of split-K tiles + a reduce launch; CGD_CONV_SMALL=0 keeps the tcgen05 path for A/B runs
+  {
+    static int small_on = -1;
+    if (small_on < 0) {
+      const char* e = getenv("CGD_CONV_SMALL");
+      small_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    L.small = (small_on && !L.narrow && conv_small_eligible(L)) ? 1 : 0;
+  }
   return 0;
 }
 
@@ -577,6 +587,7 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
     return 0;
   }
   if (L.narrow) return conv_narrow_launch(L, st);
+  if (L.small) return conv_small_launch(L, st);
   if (L.cluster_split) return conv_tc3_launch(L, st);
   int rc = 0;
   if (conv_use_pair_kernel(L)) rc = conv_tc2_launch(L, st);
@@ -600,6 +611,8 @@ int conv_tc_launch(const ConvTcLaunch& L, cudaStream_t st) {
   return 0;
 }
 
-int conv_tc_num_launches(const ConvTcLaunch& L) { return (L.impl != 1 && L.p.splits > 1 && !L.p.fuse_reduce && !L.cluster_split) ? 2 : 1; }
+int conv_tc_num_launches(const ConvTcLaunch& L) {
+  return (L.impl != 1 && !L.small && !L.narrow && L.p.splits > 1 && !L.p.fuse_reduce && !L.cluster_split) ? 2 : 1;
+}
 
 }  // namespace cgd

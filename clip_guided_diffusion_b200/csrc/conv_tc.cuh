@@ -45,6 +45,7 @@ struct ConvTcLaunch {
   int tail_units;                    // > 0: launch the TAIL instantiation over this many schedule units
   ConvTcParams p;
   int BN, impl, m_tiles, n_tiles;
+  int small;                         // 8 x 8 images: the weight-streaming mma.sync kernel of conv_narrow.cu (8 output channels per CTA, no split-K)
   int narrow;                        // <= 8 output channels, fp32 out, 3x3: the halo-tile mma.sync kernel of conv_narrow.cu instead of a tcgen05 tile
   int co_resident;                   // pair kernel: launch the 2-CTAs-per-SM instantiation with a short operand ring (latency-bound layers)
   int cluster_split;                 // split-K inside a 2*splits-CTA cluster, reduced through DSMEM (conv_tc3.cu): no workspace, one launch
@@ -62,6 +63,8 @@ bool conv_use_pair_kernel(const ConvTcLaunch& L);
 int conv_tc3_launch(const ConvTcLaunch& L, cudaStream_t st);  // conv_tc3.cu
 bool conv_narrow_eligible(const ConvTcLaunch& L);              // conv_narrow.cu
 int conv_narrow_launch(const ConvTcLaunch& L, cudaStream_t st);
+bool conv_small_eligible(const ConvTcLaunch& L);
+int conv_small_launch(const ConvTcLaunch& L, cudaStream_t st);
 bool conv_cluster_split_ok(const ConvTcLaunch& L);
 int conv_tc3_max_clusters(int BN, int S);
 

@@ -35,6 +35,13 @@ CASES = [
     ("conv3x3_256x256_c256_dominant_res", 1, 256, 256, 256, 256, 9, True, True),
     ("conv3x3_256x256_c512_to_256", 1, 256, 256, 512, 256, 9, True, False),      # output blocks at 256x256: K = 4608
     ("conv3x3_128x128_c256", 1, 128, 128, 256, 256, 9, True, True),
+    # 8 x 8 images: the weight-streaming kernel (csrc/conv_narrow.cu, conv_small_kernel: 8 output channels per CTA, no split-K) -- the
+    # deepest UNet level's 3x3 convs and attention 1x1s, forward and dgrad, with / without residual, two images
+    ("conv3x3_8x8_c1024_res", 1, 8, 8, 1024, 1024, 9, True, True),
+    ("conv1x1_8x8_qkv", 1, 8, 8, 1024, 3072, 1, True, False),
+    ("conv1x1_8x8_proj_res_b2", 2, 8, 8, 1024, 1024, 1, True, True),
+    ("conv1x1_8x8_k3072", 1, 8, 8, 3072, 1024, 1, True, False),
+    ("conv3x3_8x8_c2048_to_1024", 1, 8, 8, 2048, 1024, 9, True, False),   # K too large for the slab: stays on the tcgen05 split-K path
 ]
 
 
