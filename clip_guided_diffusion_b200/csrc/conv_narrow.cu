@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "pdl.cuh"
+#include "tc_ptx.cuh"
 
 namespace cgd {
 
@@ -141,51 +142,61 @@ int conv_narrow_launch(const ConvTcLaunch& L, cudaStream_t st) {
 // tile for 3x3), and the product runs on mma.sync.m16n8k16 whose N = 8 is exactly the CTA's channel slab: 8 warps = 4 pixel tiles x 2
 // halves of every slice's K, two independent accumulator chains per warp, one shared-memory add at the end.
 constexpr int SM_THREADS = 256, SM_STAGES = 4;
+constexpr int SM_PITCH = 144;  // bytes per pixel slot of a stage: 64 channels (128 B) + 16 B, so that 8 consecutive pixels hit 8 bank groups
 
+// Data movement: cp.async.bulk (TMA 1-D) with mbarrier completion -- 8 copies for the weight slab (one row of K halfs per output channel),
+// 64 per slice for the activations (one pixel's 128 bytes each).  A first version issued every 16-byte piece as its own cp.async
+// (~22 k requests per CTA) and was request-bound: 20 us for the 1024 -> 1024 3x3, no faster than the split-K tiles it replaced.
 template <int TAPS>
 __global__ void __launch_bounds__(SM_THREADS)
 conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, const float* __restrict__ bias, const __half* __restrict__ res,
                   __half* __restrict__ out, int Cin, int64_t a_sn, int64_t a_sh, int64_t a_sw, int64_t ldb, int64_t o_sn, int64_t o_sh, int64_t o_sw,
                   int64_t r_sn, int64_t r_sh, int64_t r_sw) {
-  constexpr int HALO = TAPS == 9 ? 10 : 8;           // stage tile edge in pixels
-  constexpr int PIXS = HALO * HALO;                   // 100 / 64 pixels per 64-channel slice
-  constexpr int STAGE = PIXS * 128;
+  constexpr int HALO = TAPS == 9 ? 10 : 8;           // stage tile edge in pixel slots (3x3: a zero border around the 8 x 8 image)
+  constexpr int PIXS = HALO * HALO;
+  constexpr int STAGE = PIXS * SM_PITCH;
   extern __shared__ __align__(128) uint8_t sm_smem[];
   const int K = TAPS * Cin, wld = K + 8;
   uint8_t* stage_base = sm_smem;
   __half* ws = reinterpret_cast<__half*>(sm_smem + SM_STAGES * STAGE);
   __shared__ float red[4][32][4];
+  __shared__ __align__(8) uint64_t wbar, full_bar[SM_STAGES];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * 8, img = blockIdx.y;
-  // weight slab of this CTA's 8 output channels: independent of the previous kernel
-  {
-    const uint32_t wbase = as_smem(ws);
-    const __half* wsrc = Wp + (int64_t)n0 * ldb;
-    for (int v = tid; v < 8 * (K / 8); v += SM_THREADS) {
-      const int r = v / (K / 8), c = (v - r * (K / 8)) * 8;
-      nr_cp16(wbase + (r * wld + c) * 2, wsrc + (int64_t)r * ldb + c, true);
+  if (tid == 0) {
+    mbar_init(&wbar, 1);
+    for (int s = 0; s < SM_STAGES; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (TAPS == 9)  // the border slots are never written again: zero once (generic proxy; the bulk copies only touch interior slots)
+    for (int v = tid; v < SM_STAGES * PIXS * (SM_PITCH / 16); v += SM_THREADS) {
+      const int pix = (v / (SM_PITCH / 16)) % PIXS, hy = pix / HALO, hx = pix - hy * HALO;
+      if (hy == 0 || hy == HALO - 1 || hx == 0 || hx == HALO - 1) *reinterpret_cast<uint4*>(stage_base + (size_t)v * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  __syncthreads();
+  // weight slab of this CTA's 8 output channels: independent of the previous kernel -> issued before the grid dependency resolves
+  if (warp == 0) {
+    if (lane == 0) mbar_expect_tx(&wbar, (uint32_t)(8 * K * 2));
+    __syncwarp();
+    if (lane < 8) bulk_load_1d(ws + lane * wld, Wp + (int64_t)(n0 + lane) * ldb, (uint32_t)(K * 2), &wbar);
   }
   pdl_wait();
   pdl_launch_dependents();
   const __half* An = A + (int64_t)img * a_sn;
   const int nslices = Cin / 64;
-  auto load_slice = [&](int s) {
-    const uint32_t base = as_smem(stage_base + (s % SM_STAGES) * STAGE);
-    for (int v = tid; v < PIXS * 8; v += SM_THREADS) {
-      const int pix = v >> 3, ch = v & 7;
-      const int hy = pix / HALO, hx = pix - hy * HALO;
-      const int y = TAPS == 9 ? hy - 1 : hy, x = TAPS == 9 ? hx - 1 : hx;
-      const bool ok = y >= 0 && y < 8 && x >= 0 && x < 8;
-      const __half* src = ok ? An + (int64_t)y * a_sh + (int64_t)x * a_sw + s * 64 + ch * 8 : A;
-      nr_cp16(base + pix * 128 + ((ch ^ (pix & 7)) << 4), src, ok);
+  auto load_slice = [&](int s) {  // warp 0: one pixel's 64-channel slice (128 contiguous bytes) per copy, two per lane
+    const int st = s % SM_STAGES;
+    if (lane == 0) mbar_expect_tx(&full_bar[st], 64 * 128);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h, y = q >> 3, x = q & 7;
+      const int slot = TAPS == 9 ? (y + 1) * HALO + x + 1 : q;
+      bulk_load_1d(stage_base + st * STAGE + slot * SM_PITCH, An + (int64_t)y * a_sh + (int64_t)x * a_sw + s * 64, 128, &full_bar[st]);
     }
   };
-  for (int s = 0; s < SM_STAGES; ++s) {  // always SM_STAGES groups in flight (empty ones past the end keep the wait counts uniform)
-    if (s < nslices) load_slice(s);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
+  if (warp == 0)
+    for (int s = 0; s < SM_STAGES && s < nslices; ++s) load_slice(s);
   float acc[2][4];
 #pragma unroll
   for (int t = 0; t < 2; ++t)
@@ -196,10 +207,11 @@ conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, c
   const int wrow = lane >> 2, wcol = (lane & 3) * 2;
   const int p = (lane & 7) + (mi & 1) * 8;        // pixel of this lane's ldmatrix row inside the 16-pixel tile
   const int py = 2 * mt + (p >> 3), px = p & 7;   // its image coordinates
+  mbar_wait(&wbar, 0);
   for (int s = 0; s < nslices; ++s) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(SM_STAGES - 1) : "memory");  // the weight slab and slice s have landed
-    __syncthreads();
-    const uint32_t base = as_smem(stage_base + (s % SM_STAGES) * STAGE);
+    const int st = s % SM_STAGES;
+    mbar_wait(&full_bar[st], (uint32_t)((s / SM_STAGES) & 1));
+    const uint32_t base = as_smem(stage_base + st * STAGE);
 #pragma unroll
     for (int tap = 0; tap < TAPS; ++tap) {
       const int dy = TAPS == 9 ? tap / 3 - 1 : 0, dx = TAPS == 9 ? tap % 3 - 1 : 0;
@@ -210,15 +222,13 @@ conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, c
         const int ks = kh * 2 + j;
         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wk + ks * 16);
         const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wk + ks * 16 + 8);
-        const int ch = ks * 2 + (mi >> 1);
         uint32_t a[4];
-        ldsm_x4(base + pix * 128 + ((ch ^ (pix & 7)) << 4), a);
+        ldsm_x4(base + pix * SM_PITCH + (ks * 2 + (mi >> 1)) * 16, a);
         mma16816(acc[j], a, b0, b1);
       }
     }
     __syncthreads();  // every warp is done with this stage before it is refilled
-    if (s + SM_STAGES < nslices) load_slice(s + SM_STAGES);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (warp == 0 && s + SM_STAGES < nslices) load_slice(s + SM_STAGES);
   }
   float c[4];
 #pragma unroll
@@ -247,13 +257,14 @@ conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, c
   }
 }
 
-static inline int conv_small_smem(int taps, int Cin) { return SM_STAGES * (taps == 9 ? 100 : 64) * 128 + 8 * (taps * Cin + 8) * 2; }
+static inline int conv_small_smem(int taps, int Cin) { return SM_STAGES * (taps == 9 ? 100 : 64) * SM_PITCH + 8 * (taps * Cin + 8) * 2; }
 
 bool conv_small_eligible(const ConvTcLaunch& L) {
   const ConvTcParams& p = L.p;
   return (p.taps == 9 || p.taps == 1) && p.H == 8 && p.W == 8 && p.Cin % 64 == 0 && p.Cout % 8 == 0 && !p.out_f32 && p.out_sc == 1 && !p.b_batched &&
          p.res_mode == 0 && p.epi_stats == nullptr && (L.impl == 0 || L.impl == 3) && L.ldb % 8 == 0 && p.out_sw % 2 == 0 &&
-         (p.res == nullptr || p.res_sw % 2 == 0) && conv_small_smem(p.taps, p.Cin) <= 200 * 1024;
+         (p.res == nullptr || p.res_sw % 2 == 0) && L.a_sn % 8 == 0 && L.a_sh % 8 == 0 && L.a_sw % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(L.A) % 16) == 0 && (reinterpret_cast<uintptr_t>(L.Wp) % 16) == 0 && conv_small_smem(p.taps, p.Cin) <= 210 * 1024;
 }
 
 int conv_small_launch(const ConvTcLaunch& L, cudaStream_t st) {
@@ -261,8 +272,8 @@ int conv_small_launch(const ConvTcLaunch& L, cudaStream_t st) {
   const int smem = conv_small_smem(p.taps, p.Cin);
   static DeviceOnce attr_set;
   if (attr_set.needed()) {
-    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set.mark();
   }
   const dim3 grid((unsigned)(p.Cout / 8), (unsigned)p.NB);
