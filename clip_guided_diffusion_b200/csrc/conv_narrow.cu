@@ -142,20 +142,22 @@ int conv_narrow_launch(const ConvTcLaunch& L, cudaStream_t st) {
 // tile for 3x3), and the product runs on mma.sync.m16n8k16 whose N = 8 is exactly the CTA's channel slab: 8 warps = 4 pixel tiles x 2
 // halves of every slice's K, two independent accumulator chains per warp, one shared-memory add at the end.
 constexpr int SM_THREADS = 256, SM_STAGES = 4;
-constexpr int SM_PITCH = 144;  // bytes per pixel slot of a stage: 64 channels (128 B) + 16 B, so that 8 consecutive pixels hit 8 bank groups
 
-// Data movement: cp.async.bulk (TMA 1-D) with mbarrier completion -- 8 copies for the weight slab (one row of K halfs per output channel),
-// 64 per slice for the activations (one pixel's 128 bytes each).  A first version issued every 16-byte piece as its own cp.async
-// (~22 k requests per CTA) and was request-bound: 20 us for the 1024 -> 1024 3x3, no faster than the split-K tiles it replaced.
+// Data movement: per 64-channel slice ONE TMA tensor load of the box [64 ch x 10 x 10 x 1] anchored at (-1, -1) -- the 8 x 8 image with
+// its zero border, out-of-image coordinates zero-filled by the TMA unit, 128-byte swizzle (slot = pixel, 16-byte chunk ^= slot & 7) --
+// and eight cp.async.bulk copies for the weight slab (one row of K halfs per output channel).  Measured on the way here
+// (profiles/r02_call_s_small_v*.log): every 16-byte piece as its own cp.async (~22 k requests per CTA): 20 us, request-bound; one 128-byte
+// cp.async.bulk per pixel (1024 per CTA): 43 us -- small bulk copies cost ~40 ns each in the TMA unit.
 template <int TAPS>
 __global__ void __launch_bounds__(SM_THREADS)
-conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, const float* __restrict__ bias, const __half* __restrict__ res,
-                  __half* __restrict__ out, int Cin, int64_t a_sn, int64_t a_sh, int64_t a_sw, int64_t ldb, int64_t o_sn, int64_t o_sh, int64_t o_sw,
-                  int64_t r_sn, int64_t r_sh, int64_t r_sw) {
+conv_small_kernel(const __grid_constant__ CUtensorMap tmA, const __half* __restrict__ Wp, const float* __restrict__ bias,
+                  const __half* __restrict__ res, __half* __restrict__ out, int Cin, int64_t ldb, int64_t o_sn, int64_t o_sh, int64_t o_sw, int64_t r_sn,
+                  int64_t r_sh, int64_t r_sw) {
   constexpr int HALO = TAPS == 9 ? 10 : 8;           // stage tile edge in pixel slots (3x3: a zero border around the 8 x 8 image)
   constexpr int PIXS = HALO * HALO;
-  constexpr int STAGE = PIXS * SM_PITCH;
-  extern __shared__ __align__(128) uint8_t sm_smem[];
+  constexpr int STAGE = ((PIXS * 128 + 1023) / 1024) * 1024;  // 1024-byte aligned stages: the swizzle pattern is address-based
+  extern __shared__ uint8_t sm_smem_raw[];
+  uint8_t* sm_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_smem_raw) + 1023) & ~uintptr_t(1023));
   const int K = TAPS * Cin, wld = K + 8;
   uint8_t* stage_base = sm_smem;
   __half* ws = reinterpret_cast<__half*>(sm_smem + SM_STAGES * STAGE);
@@ -164,15 +166,11 @@ conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * 8, img = blockIdx.y;
   if (tid == 0) {
+    tma_prefetch_desc(&tmA);
     mbar_init(&wbar, 1);
     for (int s = 0; s < SM_STAGES; ++s) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (TAPS == 9)  // the border slots are never written again: zero once (generic proxy; the bulk copies only touch interior slots)
-    for (int v = tid; v < SM_STAGES * PIXS * (SM_PITCH / 16); v += SM_THREADS) {
-      const int pix = (v / (SM_PITCH / 16)) % PIXS, hy = pix / HALO, hx = pix - hy * HALO;
-      if (hy == 0 || hy == HALO - 1 || hx == 0 || hx == HALO - 1) *reinterpret_cast<uint4*>(stage_base + (size_t)v * 16) = make_uint4(0u, 0u, 0u, 0u);
-    }
   __syncthreads();
   // weight slab of this CTA's 8 output channels: independent of the previous kernel -> issued before the grid dependency resolves
   if (warp == 0) {
@@ -182,20 +180,13 @@ conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, c
   }
   pdl_wait();
   pdl_launch_dependents();
-  const __half* An = A + (int64_t)img * a_sn;
   const int nslices = Cin / 64;
-  auto load_slice = [&](int s) {  // warp 0: one pixel's 64-channel slice (128 contiguous bytes) per copy, two per lane
+  auto load_slice = [&](int s) {  // one thread: the whole (bordered) image slice as one tensor box
     const int st = s % SM_STAGES;
-    if (lane == 0) mbar_expect_tx(&full_bar[st], 64 * 128);
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int q = lane + 32 * h, y = q >> 3, x = q & 7;
-      const int slot = TAPS == 9 ? (y + 1) * HALO + x + 1 : q;
-      bulk_load_1d(stage_base + st * STAGE + slot * SM_PITCH, An + (int64_t)y * a_sh + (int64_t)x * a_sw + s * 64, 128, &full_bar[st]);
-    }
+    mbar_expect_tx(&full_bar[st], PIXS * 128);
+    tma_load_4d(stage_base + st * STAGE, &tmA, &full_bar[st], s * 64, TAPS == 9 ? -1 : 0, TAPS == 9 ? -1 : 0, img);
   };
-  if (warp == 0)
+  if (tid == 0)
     for (int s = 0; s < SM_STAGES && s < nslices; ++s) load_slice(s);
   float acc[2][4];
 #pragma unroll
@@ -222,13 +213,14 @@ conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, c
         const int ks = kh * 2 + j;
         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wk + ks * 16);
         const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wk + ks * 16 + 8);
+        const int ch = ks * 2 + (mi >> 1);
         uint32_t a[4];
-        ldsm_x4(base + pix * SM_PITCH + (ks * 2 + (mi >> 1)) * 16, a);
+        ldsm_x4(base + pix * 128 + ((ch ^ (pix & 7)) << 4), a);
         mma16816(acc[j], a, b0, b1);
       }
     }
     __syncthreads();  // every warp is done with this stage before it is refilled
-    if (warp == 0 && s + SM_STAGES < nslices) load_slice(s + SM_STAGES);
+    if (tid == 0 && s + SM_STAGES < nslices) load_slice(s + SM_STAGES);
   }
   float c[4];
 #pragma unroll
@@ -257,14 +249,16 @@ conv_small_kernel(const __half* __restrict__ A, const __half* __restrict__ Wp, c
   }
 }
 
-static inline int conv_small_smem(int taps, int Cin) { return SM_STAGES * (taps == 9 ? 100 : 64) * SM_PITCH + 8 * (taps * Cin + 8) * 2; }
+static inline int conv_small_smem(int taps, int Cin) {  // 1024-byte aligned stages (+ alignment slack) + the weight slab
+  return 1024 + SM_STAGES * (((taps == 9 ? 100 : 64) * 128 + 1023) / 1024) * 1024 + 8 * (taps * Cin + 8) * 2;
+}
 
 bool conv_small_eligible(const ConvTcLaunch& L) {
   const ConvTcParams& p = L.p;
   return (p.taps == 9 || p.taps == 1) && p.H == 8 && p.W == 8 && p.Cin % 64 == 0 && p.Cout % 8 == 0 && !p.out_f32 && p.out_sc == 1 && !p.b_batched &&
          p.res_mode == 0 && p.epi_stats == nullptr && (L.impl == 0 || L.impl == 3) && L.ldb % 8 == 0 && p.out_sw % 2 == 0 &&
          (p.res == nullptr || p.res_sw % 2 == 0) && L.a_sn % 8 == 0 && L.a_sh % 8 == 0 && L.a_sw % 8 == 0 &&
-         (reinterpret_cast<uintptr_t>(L.A) % 16) == 0 && (reinterpret_cast<uintptr_t>(L.Wp) % 16) == 0 && conv_small_smem(p.taps, p.Cin) <= 210 * 1024;
+         (reinterpret_cast<uintptr_t>(L.A) % 16) == 0 && (reinterpret_cast<uintptr_t>(L.Wp) % 16) == 0 && conv_small_smem(p.taps, p.Cin) <= 212 * 1024;
 }
 
 int conv_small_launch(const ConvTcLaunch& L, cudaStream_t st) {
@@ -272,17 +266,17 @@ int conv_small_launch(const ConvTcLaunch& L, cudaStream_t st) {
   const int smem = conv_small_smem(p.taps, p.Cin);
   static DeviceOnce attr_set;
   if (attr_set.needed()) {
-    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
+    CGD_CUDA(cudaFuncSetAttribute(conv_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
     attr_set.mark();
   }
   const dim3 grid((unsigned)(p.Cout / 8), (unsigned)p.NB);
   if (p.taps == 9)
-    CGD_CUDA(launch_pdl(conv_small_kernel<9>, grid, dim3(SM_THREADS), (size_t)smem, st, L.A, L.Wp, p.bias, p.res, (__half*)p.out, p.Cin, L.a_sn, L.a_sh, L.a_sw,
-                        L.ldb, p.out_sn, p.out_sh, p.out_sw, p.res_sn, p.res_sh, p.res_sw));
+    CGD_CUDA(launch_pdl(conv_small_kernel<9>, grid, dim3(SM_THREADS), (size_t)smem, st, L.tmS, L.Wp, p.bias, p.res, (__half*)p.out, p.Cin, L.ldb, p.out_sn,
+                        p.out_sh, p.out_sw, p.res_sn, p.res_sh, p.res_sw));
   else
-    CGD_CUDA(launch_pdl(conv_small_kernel<1>, grid, dim3(SM_THREADS), (size_t)smem, st, L.A, L.Wp, p.bias, p.res, (__half*)p.out, p.Cin, L.a_sn, L.a_sh, L.a_sw,
-                        L.ldb, p.out_sn, p.out_sh, p.out_sw, p.res_sn, p.res_sh, p.res_sw));
+    CGD_CUDA(launch_pdl(conv_small_kernel<1>, grid, dim3(SM_THREADS), (size_t)smem, st, L.tmS, L.Wp, p.bias, p.res, (__half*)p.out, p.Cin, L.ldb, p.out_sn,
+                        p.out_sh, p.out_sw, p.res_sn, p.res_sh, p.res_sw));
   return 0;
 }
 

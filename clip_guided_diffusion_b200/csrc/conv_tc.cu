@@ -556,6 +556,17 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
       small_on = (e && e[0] == '0') ? 0 : 1;
     }
     L.small = (small_on && !L.narrow && conv_small_eligible(L)) ? 1 : 0;
+    L.tmS = L.tmA;
+    if (L.small) {  // one TMA box per 64-channel slice: the 8 x 8 image with its zero border (out-of-image coordinates are zero-filled)
+      const cuuint32_t e = taps == 9 ? 10 : 8;
+      cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+      cuuint64_t strides[3] = {(cuuint64_t)op.i[9] * 2, (cuuint64_t)op.i[8] * 2, (cuuint64_t)op.i[7] * 2};
+      cuuint32_t box[4] = {64, e, e, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&L.tmS, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, op.p[0], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CGD_CHECK_ARG(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(8x8 image box) failed with %d", (int)r);
+    }
   }
   return 0;
 }

@@ -41,6 +41,7 @@ struct ConvTcLaunch {
   CUtensorMap tmA, tmB;              // A: 4-D pixel box; B: [BN x 64] weight slice (single-CTA kernel)
   CUtensorMap tmB2;                  // B: [BN/2 x 64] half slice per CTA of a pair (cta_group::2 kernel)
   CUtensorMap tmOut, tmRes;          // pair kernel epilogue: [64 ch x TW x TH x TN] boxes of the output / residual
+  CUtensorMap tmS;                   // 8 x 8 images (conv_small_kernel): the whole image + zero border as one [64 ch x 10 x 10 x 1] box (3x3) / [64 x 8 x 8 x 1] (1x1)
   CUtensorMap tmB4;                  // B: [BN/4 x 64] quarter slice per CTA (half tiles of the split last wave)
   int tail_units;                    // > 0: launch the TAIL instantiation over this many schedule units
   ConvTcParams p;
