@@ -548,12 +548,13 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
     L.narrow = (narrow_on && conv_narrow_eligible(L)) ? 1 : 0;
   }
   // 8 x 8 images (deepest UNet level): one launch, a CTA per 8 output channels streaming its whole weight slab (conv_narrow.cu,
-  // conv_small_kernel) instead of split-K tiles + a reduce launch; CGD_CONV_SMALL=0 keeps the tcgen05 path for A/B runs
+  // conv_small_kernel) instead of split-K tiles + a reduce launch.  Opt-in (CGD_CONV_SMALL=1): device-validated, but measured
+  // break-even per launch (17.7 vs 18.6 us for the 1024 -> 1024 3x3) and -0.5 % in the step (profiles/r02_call_s_small_v3.log).
   {
     static int small_on = -1;
     if (small_on < 0) {
       const char* e = getenv("CGD_CONV_SMALL");
-      small_on = (e && e[0] == '0') ? 0 : 1;
+      small_on = (e && e[0] == '1') ? 1 : 0;
     }
     L.small = (small_on && !L.narrow && conv_small_eligible(L)) ? 1 : 0;
     L.tmS = L.tmA;

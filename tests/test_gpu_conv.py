@@ -199,3 +199,15 @@ def test_narrow_conv_halo_kernel(shape):
     got = plan.view(out, (NB, Cout, H, W))
     err = float((got - ref).abs().max() / ref.abs().max())
     assert th.isfinite(got).all() and err < 2e-3, err
+
+
+def test_small_image_weight_streaming_kernel():
+    """CGD_CONV_SMALL=1: 8 x 8 images take conv_small_kernel (csrc/conv_narrow.cu: a CTA per 8 output channels streaming its whole
+    weight slab, TMA box per activation slice, mma.sync) instead of split-K tcgen05 tiles.  Opt-in (measured break-even); the switch
+    is read once per process, so the 8 x 8 cases are re-run in a child process with it on."""
+    import os, subprocess, sys
+    env = dict(os.environ, CGD_CONV_SMALL="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_conv.py", "-q", "-x", "-m", "gpu", "-k", "8x8 and (auto or tc2pair) and not small_image",
+                        "-p", "no:cacheprovider"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
