@@ -141,7 +141,7 @@ def build_engine(device, rank, world):
     if CFG["lpips"]:
         eng.set_init_image((th.rand(1, 3, CFG["image_size"], CFG["image_size"], generator=th.Generator().manual_seed(5)) * 2 - 1).to(device))
     del usd, vsd
-    diff = gd.create_gaussian_diffusion(1000, "linear", CFG["respacing"])
+    diff = gd.create_gaussian_diffusion(1000, "linear", CFG["respacing"], rescale_timesteps=ucfg.rescale_timesteps)
     th.manual_seed(0)
     tgt = th.nn.functional.normalize(th.randn(1, vcfg.output_dim), dim=-1)
     eng.set_targets(tgt, th.ones(1))
@@ -375,9 +375,16 @@ def oracle_cpu_setup():
     clip = seeded_init_(CLIPVisualOnly(VIT_CONFIGS[CFG["clip"]]), seed=1235).eval()
     for p in list(unet.parameters()) + list(clip.parameters()):
         p.requires_grad_(False)
-    diff = od.create_gaussian_diffusion(1000, "linear", CFG["respacing"])
-    tgt = th.nn.functional.normalize(th.randn(1, 512), dim=-1)
-    cond = og.OracleCondFn(diff, clip, tgt, th.ones(1), cut_size=224, num_cutouts=CFG["cutn"])
+    from clip_guided_diffusion_b200 import unet as pu
+    diff = od.create_gaussian_diffusion(1000, "linear", CFG["respacing"], rescale_timesteps=pu.config_for(CFG["image_size"], True).rescale_timesteps)
+    tgt = th.nn.functional.normalize(th.randn(1, VIT_CONFIGS[CFG["clip"]].output_dim), dim=-1)
+    extra = {}
+    if CFG["lpips"]:  # cfg5: init image + LPIPS-VGG init loss (cgd/cgd.py:220-224), same synthetic weights / image as our arm
+        from clip_guided_diffusion_b200 import weights as pw
+        from oracle import lpips as ol
+        init = th.rand(1, 3, CFG["image_size"], CFG["image_size"], generator=th.Generator().manual_seed(5)) * 2 - 1
+        extra = dict(lpips_model=ol.LPIPSVgg(pw.seeded_lpips_state_dict()), init_tensor=init, init_scale=1000.0)
+    cond = og.OracleCondFn(diff, clip, tgt, th.ones(1), cut_size=224, num_cutouts=CFG["cutn"], **extra)
     return unet, diff, cond
 
 
@@ -418,7 +425,12 @@ def torch_cuda_baseline(device, n_steps, dist=None, world=1):
     for m in clip.modules():  # clip.model.convert_weights leaves LayerNorm in fp32
         if isinstance(m, th.nn.LayerNorm):
             m.float()
-    cond = og.OracleCondFn(diff, clip, cond.target_embeds.to(device), cond.weights.to(device), cut_size=224, num_cutouts=CFG["cutn"])
+    extra = {}
+    if cond.kw.get("lpips_model") is not None:
+        lp = cond.kw["lpips_model"].to(device)
+        lp.sd = {k: v.to(device) for k, v in lp.sd.items()}
+        extra = dict(lpips_model=lp, init_tensor=cond.kw["init_tensor"].to(device), init_scale=cond.kw["init_scale"])
+    cond = og.OracleCondFn(diff, clip, cond.target_embeds.to(device), cond.weights.to(device), cut_size=224, num_cutouts=CFG["cutn"], **extra)
     B = CFG["per_gpu_batch"]
     i = diff.num_timesteps - 1
     fn = diff.ddim_sample_with_grad if CFG["respacing"].startswith("ddim") else diff.p_sample_with_grad
