@@ -24,17 +24,17 @@ dist.broadcast_object_list(box, src=0)
 out = box[0]
 os.makedirs(os.path.join(out, f"cwd{rank}"), exist_ok=True)
 os.chdir(os.path.join(out, f"cwd{rank}"))
-kw = dict(image_size=64, num_cutouts=4, prompts=["multi gpu"], timestep_respacing="ddim25", skip_timesteps=20, save_frequency=100, progress=False, seed=3,
+kw = dict(image_size=64, num_cutouts=4, prompts=["multi gpu"], timestep_respacing="ddim25", skip_timesteps=0, save_frequency=100, progress=False, seed=3,
           device=f"cuda:{local}", unet_state_dict=usd, clip_state_dict=vsd, target_embeds=tgt)
 got = list(cgd.clip_guided_diffusion(batch_size=world, prefix_path=os.path.join(out, "sharded"), rank=rank, world_size=world, **kw))
 dist.barrier()
 if rank == 0:
     from PIL import Image
     import numpy as np
-    # frames: step 0 of the own image (save_frequency 100 -> only step 0) + the gathered final step for EVERY image
+    # frames: step 0 of the own image (save_frequency 100) + the gathered final step (current_timestep == -1) for EVERY image
     assert sorted(b for b, _ in got) == [0] + list(range(world)), got
     ref = list(cgd.clip_guided_diffusion(batch_size=world, prefix_path=os.path.join(out, "single"), **kw))
-    finals = sorted(p for _, p in ref if p.endswith("0004.png"))
+    finals = sorted(p for _, p in ref if p.endswith("0024.png"))
     assert len(finals) == world
     worst = 0
     for p in finals:
@@ -42,7 +42,9 @@ if rank == 0:
         b = np.asarray(Image.open(p.replace("single", "sharded"))).astype(int)
         worst = max(worst, int(np.abs(a - b).max()))
     print(f"multi-GPU entry check: world {world}, rank 0 saved {world} gathered final frames; max |sharded - single| = {worst} of 255")
-    assert worst <= 8, worst  # fp16 kernels pick different tilings for batch 1 and batch N; five steps of seeded-random weights amplify that
+    # fp16 kernels pick different tilings for batch 1 and batch N and 25 free-running steps of seeded-random weights amplify the
+    # rounding differences (the exact shard == full-batch statement is tests/test_multirank_cpu.py, one step): loose bound only
+    assert worst <= 48, worst
 else:
     assert [b for b, _ in got] == [rank], got
 dist.barrier()
