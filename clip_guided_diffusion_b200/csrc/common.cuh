@@ -62,6 +62,16 @@ struct DeviceOnce {
   }
   int get() const { return value[cur()]; }
 };
+// SM count of the current device (148 on a full B200; grids of the persistent kernels are sized from it, not from the constant)
+static inline int device_sm_count() {
+  static DeviceOnce once;
+  if (once.needed()) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    once.mark(sms);
+  }
+  return once.get();
+}
 
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ float warp_sum(float v) {

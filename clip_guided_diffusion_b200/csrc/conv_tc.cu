@@ -464,7 +464,7 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
       tail_on = (e && e[0] == '1') ? 1 : 0;
     }
     const int total = ((L.m_tiles + 1) / 2) * L.n_tiles;
-    if (tail_on && p.epi_tma && !L.cluster_split && !p.b_batched && (BN == 128 || BN == 256) && sched_tail_pays(total, 74)) {
+    if (tail_on && device_sm_count() == 148 && p.epi_tma && !L.cluster_split && !p.b_batched && (BN == 128 || BN == 256) && sched_tail_pays(total, 74)) {
       const cuuint64_t K = (cuuint64_t)(taps * Cin);
       const cuuint64_t row_bytes = (cuuint64_t)ldb * 2 * (cuuint64_t)Npad;
       cuuint64_t dims4[4] = {K, (cuuint64_t)Npad, 1, 1};

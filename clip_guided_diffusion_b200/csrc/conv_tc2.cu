@@ -500,7 +500,7 @@ static int launch_tc2(const ConvTcLaunch& L, cudaStream_t st) {
   prm.dbg = dbg;
   prm.nstages = (L.p.nstages >= 2 && L.p.nstages <= Cfg::kStages) ? L.p.nstages : Cfg::kStages;
   const int smem = kSmemMax - (Cfg::kStages - prm.nstages) * Cfg::kStageBytes;
-  const int clusters = std::min(total, 74);  // 148 SMs = 74 TPC pairs
+  const int clusters = std::min(total, TAIL ? 74 : device_sm_count() / 2);  // one CTA pair per TPC (74 on B200; the TAIL schedule is built for 74)
   CGD_CUDA(launch_pdl(conv_tc2_kernel<BN, STATS, TAIL, CO>, dim3(2 * clusters), dim3(kThreads2), smem, st, L.tmA, L.tmB2, L.tmOut, L.tmRes, L.tmB4, prm,
                       L.n_tiles, pair_tiles, total));
   return 0;
