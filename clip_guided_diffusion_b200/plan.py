@@ -249,6 +249,8 @@ class Plan:
         self.tc_attention = os.environ.get("CGD_TC_ATTENTION", "0") == "1"
         # split-K reduced inside a thread-block cluster through DSMEM (csrc/conv_tc3.cu) instead of partials + a reduce launch
         self.cluster_splitk = os.environ.get("CGD_CONV_CLUSTER", "1") == "1"
+        # ... also for one-wave layers that did not need split-K to fill the machine but have long K loops (opt-in until measured)
+        self.cluster_wide = os.environ.get("CGD_CLUSTER_WIDE", "0") == "1"
         # GroupNorm forward from statistics reduced in the producing conv's epilogue (CONV flags 2 + GN_APPLY_EPI): one streaming trip
         # instead of two.  Interpreter-verified, NOT yet run on the device: opt-in until it is (DESIGN.md "Next")
         self.gn_epi_stats = os.environ.get("CGD_GN_EPI_STATS", "0") == "1"
@@ -341,6 +343,16 @@ class Plan:
         if splits > 1 and self.cluster_splitk and self.conv_impl in (0, 3) and b_ptr is None and not out_f32 and out_sc == 1:
             pick = pick_cluster_split(m_tiles, npad, kblocks, Cout)
             if pick is not None and pick[2] + 1.0 < workspace_split_estimate(bn, splits, kblocks, NB * H * W, npad):
+                bn, splits = pick[:2]
+                cluster = 1
+        elif (splits == 1 and self.cluster_wide and self.cluster_splitk and self.conv_impl in (0, 3) and b_ptr is None and not out_f32 and out_sc == 1
+              and m_tiles >= 2 and kblocks >= 32 and not (want_stats and self.gn_epi_stats)):
+            # one wave of narrow tiles with a long K loop (the 64 x 64 level: 64 BN-128 tiles x 72 K-blocks = 33 us at 0.46 us per K-block):
+            # wider tiles split along K inside a cluster can be shorter even though no split-K was "needed" to fill the machine
+            pick = pick_cluster_split(m_tiles, npad, kblocks, Cout)
+            rounds = -(-(((m_tiles + 1) // 2) * (npad // bn)) // 74)
+            plain = 5.0 + rounds * kblocks * (_T_KB[bn] + 0.10)  # + 0.10: measured 0.46 us per K-block at BN 128 in one-wave layers
+            if pick is not None and pick[2] + 2.0 < plain:
                 bn, splits = pick[:2]
                 cluster = 1
         ws = skbar = None
