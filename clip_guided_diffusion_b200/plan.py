@@ -249,8 +249,10 @@ class Plan:
         self.tc_attention = os.environ.get("CGD_TC_ATTENTION", "0") == "1"
         # split-K reduced inside a thread-block cluster through DSMEM (csrc/conv_tc3.cu) instead of partials + a reduce launch
         self.cluster_splitk = os.environ.get("CGD_CONV_CLUSTER", "1") == "1"
-        # ... also for one-wave layers that did not need split-K to fill the machine but have long K loops (opt-in until measured)
-        self.cluster_wide = os.environ.get("CGD_CLUSTER_WIDE", "0") == "1"
+        # ... also for one-wave layers that did not need split-K to fill the machine but have long K loops: the 64 x 64 level's
+        # 512 -> 512 3x3 runs 27.0 instead of 36.3 us, 1024 -> 512 43.5 instead of 66.0 us; +1.4 % per step, same box
+        # (profiles/r02_call_w_cluster_wide_v1.log).  CGD_CLUSTER_WIDE=0 switches it off for A/B runs.
+        self.cluster_wide = os.environ.get("CGD_CLUSTER_WIDE", "1") == "1"
         # GroupNorm forward from statistics reduced in the producing conv's epilogue (CONV flags 2 + GN_APPLY_EPI): one streaming trip
         # instead of two.  Interpreter-verified, NOT yet run on the device: opt-in until it is (DESIGN.md "Next")
         self.gn_epi_stats = os.environ.get("CGD_GN_EPI_STATS", "0") == "1"
