@@ -114,11 +114,12 @@ def _lpips_sd(given):
 
 
 def _tower_config(clip_sd: dict):
-    """ViT-B/32, ViT-B/16, ViT-L/14 (vit.py) or a ModifiedResNet tower -- RN50, RN101 (rn.py) -- recognised from the state_dict keys"""
+    """ViT-B/32, ViT-B/16, ViT-L/14 (vit.py) or a ModifiedResNet tower -- RN50, RN101, RN50x4, RN50x16 (rn.py; any width that is a
+    multiple of 16) -- recognised from the state_dict keys"""
     if "visual.layer1.0.conv1.weight" in clip_sd:
         cfg = rn_config_from_state_dict(clip_sd)
-        if cfg.width % 64:
-            raise NotImplementedError(f"ModifiedResNet width {cfg.width} (RN50x4 / x16 / x64) is not a multiple of the 64-channel K-slice")
+        if cfg.width % 16:
+            raise NotImplementedError(f"ModifiedResNet width {cfg.width}: the attention pool needs 64-wide heads (width a multiple of 16)")
         return cfg
     return vit_config_from_state_dict(clip_sd)
 
@@ -157,8 +158,7 @@ def clip_guided_diffusion(
     clip_sd = clip_state_dict if clip_state_dict is not None else _load_clip_sd(clip_model_name, checkpoints_dir)
     towers = {**VIT_CONFIGS, **RN_CONFIGS}
     if clip_state_dict is None and clip_model_name not in towers:
-        raise NotImplementedError(f"CLIP tower {clip_model_name!r} is not supported (supported: {sorted(towers)}; RN50x4 / x16 / x64 have "
-                                  "widths that are not multiples of the 64-channel K-slice)")
+        raise NotImplementedError(f"CLIP tower {clip_model_name!r} is not supported (supported: {sorted(towers)})")
     vit_cfg = _tower_config(clip_sd) if clip_state_dict is not None else towers[clip_model_name]
     if target_embeds is None:
         target_embeds, weights = _encode_text(prompts, clip_model_name, device)

@@ -1,4 +1,4 @@
-"""CLIP ``ModifiedResNet`` towers (RN50, RN101: the other `clip_model_name`s of cgd/clip_util.py:17) as an op list on the same kernels
+"""CLIP ``ModifiedResNet`` towers (RN50, RN101, RN50x4, RN50x16: the other `clip_model_name`s of cgd/clip_util.py:17) as an op list on the same kernels
 as the ViT tower: every layer is the tcgen05 conv (BatchNorm folded into weights and bias at build time -- the reference runs the
 tower in eval mode, cgd/clip_util.py:64), ReLU, 2x2 average pooling, the small-T attention kernel for AttentionPool2d.
 
@@ -7,8 +7,9 @@ Two layout tricks keep it on the existing kernels:
   cutouts in "patch order" ``[n, g*g, (c, ky, kx)]`` (that is how the ViT's patch conv became a GEMM); with patch size 2 that IS the
   2x2 space-to-depth tensor ``[n, 112, 112, 12 -> 64]``, and the stride-2 taps (a - 1 in {-1, 0, +1} of pixel row 2i) land on block
   offsets {-1, 0} with in-block rows {1, 0, 1} -- a 3x3 kernel over blocks whose +1 taps are zero (`stem_s2d_weight`).
-* widths below 64 (the stem's 32 channels) are zero-padded to 64 on the host, so activations stay multiples of the 64-channel
-  TMA K-slice; the padded outputs are relu(0) = 0.
+* widths that are not multiples of 64 (the stem's 32 channels; the 40 / 80 / 160-wide layers of RN50x4, the 48 / 96-wide layers of
+  RN50x16) are zero-padded to the next multiple on the host (`_conv_bn`: weight rows / columns and the folded bias), so activations stay
+  multiples of the 64-channel TMA K-slice; the padded outputs are relu(0 * x + 0) = 0 and their gradients meet zero weight columns.
 
 [3P] clip/model.py (clip-anytorch 2.6.0) is not in /root/reference: restated from the published architecture (oracle/clip_rn.py,
 parity unpinned, RN50 = 38,316,896 visual parameters).
@@ -48,7 +49,12 @@ class RNConfig:
         return (self.input_resolution // 32) ** 2 + 1
 
 
-RN_CONFIGS = {"RN50": RNConfig((3, 4, 6, 3), 1024, 224, 64), "RN101": RNConfig((3, 4, 23, 3), 512, 224, 64)}
+RN_CONFIGS = {"RN50": RNConfig((3, 4, 6, 3), 1024, 224, 64), "RN101": RNConfig((3, 4, 23, 3), 512, 224, 64),
+              "RN50x4": RNConfig((4, 6, 10, 6), 640, 288, 80), "RN50x16": RNConfig((6, 8, 18, 8), 768, 384, 96)}
+
+
+def ceil64(c: int) -> int:
+    return -(-c // 64) * 64
 
 
 def rn_config_from_state_dict(sd: dict) -> RNConfig:
@@ -110,14 +116,14 @@ class RNB200:
     def _bn(self, prefix):
         return {k: self._w(f"{prefix}.{k}") for k in ("weight", "bias", "running_mean", "running_var")}
 
-    def _conv_bn(self, conv, bn, name, cout_pad=None, cin_pad=None, s2d=False):
-        """packed (conv + folded BatchNorm), cached per tower family"""
+    def _conv_bn(self, conv, bn, name, s2d=False):
+        """packed (conv + folded BatchNorm), both channel counts zero-padded to multiples of 64; cached per tower family"""
         if name not in self._wcache:
             w, b = fold_bn(self._w(conv + ".weight"), self._bn(bn))
             if s2d:
                 w = stem_s2d_weight(w)
-            if cout_pad or cin_pad:
-                w, b = _pad_channels(w, b, cout_pad or w.shape[0], cin_pad or w.shape[1])
+            if w.shape[0] % 64 or w.shape[1] % 64:
+                w, b = _pad_channels(w, b, ceil64(w.shape[0]), ceil64(w.shape[1]))
             self._wcache[name] = pack_conv(self.plan, w, b, need_bwd=True, name=name)
         return self._wcache[name]
 
@@ -149,7 +155,7 @@ class RNB200:
     def _build(self, build_backward):
         p, cfg, n = self.plan, self.cfg, self.n
         g, kp, D, C = cfg.grid, cfg.kpad, cfg.output_dim, cfg.embed_dim
-        assert cfg.width % 64 == 0 and cfg.input_resolution % 32 == 0 and (cfg.input_resolution // 32) ** 2 + 1 <= 64
+        assert cfg.width % 16 == 0 and cfg.input_resolution % 32 == 0 and kp == 64
         self.patches = p.new(n * g * g * kp, "h", "patches")
         self.embeds = p.new(n * D, "f", "embeds")
         self.d_embeds = p.new(n * D, "f", "d_embeds")
@@ -157,9 +163,9 @@ class RNB200:
         p.mark("vit_fwd" + self.suffix)
         x0 = Act(self.patches, 0, n, g, g, kp, kp)
         w = cfg.width
-        h = p.relu(p.conv(x0, self._conv_bn("conv1", "bn1", "stem.conv1", cout_pad=64, cin_pad=kp, s2d=True), name="stem.conv1"), name="stem.relu1")
-        h = p.relu(p.conv(h, self._conv_bn("conv2", "bn2", "stem.conv2", cout_pad=64, cin_pad=64), name="stem.conv2"), name="stem.relu2")
-        h = p.relu(p.conv(h, self._conv_bn("conv3", "bn3", "stem.conv3", cin_pad=64), name="stem.conv3"), name="stem.relu3")
+        h = p.relu(p.conv(x0, self._conv_bn("conv1", "bn1", "stem.conv1", s2d=True), name="stem.conv1"), name="stem.relu1")
+        h = p.relu(p.conv(h, self._conv_bn("conv2", "bn2", "stem.conv2"), name="stem.conv2"), name="stem.relu2")
+        h = p.relu(p.conv(h, self._conv_bn("conv3", "bn3", "stem.conv3"), name="stem.conv3"), name="stem.relu3")
         h = p.pool2(h, name="stem.avgpool")
         inplanes = w
         for li, (blocks, planes, stride) in enumerate(zip(cfg.layers, (w, 2 * w, 4 * w, 8 * w), (1, 2, 2, 2)), start=1):

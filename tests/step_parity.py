@@ -31,7 +31,7 @@ def prod_unet_cfg(ocfg):
 
 
 def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0, respacing="25", conv_impl=0, use_graph=False, P=1,
-               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None, hw=None, rank=0, world_size=1, tower="vit", use_augs=False):
+               new_order=False, vit_streams=1, cutn_variants=(), run_cutn=None, init_scale=0.0, cutout_resize="pool", scales=None, hw=None, rank=0, world_size=1, tower="vit", use_augs=False, rn_width=64):
     ocfg = tiny_config(image_size=image, model_channels=64, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(image // 2,),
                        class_cond=True, use_new_attention_order=new_order)
     ounet = seeded_init_(UNetModel(ocfg)).eval()
@@ -39,9 +39,9 @@ def build_tiny(device, B=2, cutn=3, image=64, use_magnitude=False, sat_scale=0.0
         from clip_guided_diffusion_b200 import rn as prn
         from clip_guided_diffusion_b200 import weights as pw
         from oracle import clip_rn as orn
-        pvit_cfg = prn.RNConfig(layers=(1, 1, 1, 1), output_dim=64, input_resolution=32, width=64)
+        pvit_cfg = prn.RNConfig(layers=(1, 1, 1, 1), output_dim=64, input_resolution=32, width=rn_width)
         rn_sd = pw.seeded_rn_state_dict(pvit_cfg, seed=5)
-        oclip = orn.CLIPVisualRN(orn.RNConfig(layers=(1, 1, 1, 1), output_dim=64, input_resolution=32, width=64)).eval()
+        oclip = orn.CLIPVisualRN(orn.RNConfig(layers=(1, 1, 1, 1), output_dim=64, input_resolution=32, width=rn_width)).eval()
         oclip.visual.load_state_dict({k[len("visual."):]: v for k, v in rn_sd.items()}, strict=False)
     else:
         pvit_cfg = pv.ViTConfig(32, 16, 128, 2, 64)

@@ -33,7 +33,7 @@ def test_rn_tower_matches_oracle_on_device():
     assert cos > 0.99, cos
 
 
-@pytest.mark.parametrize("name", ["RN50", "RN101"])
+@pytest.mark.parametrize("name", ["RN50", "RN101", "RN50x4", "RN50x16"])
 def test_published_rn_towers_vs_oracle_on_device(name):
     """the towers the reference lists (cgd/clip_util.py:17) and its own test uses (RN50, test.py:139-143) at their published depth /
     width / embedding size: forward and input gradient of the whole tower vs the fp32 oracle (oracle/clip_rn.py)"""
@@ -41,7 +41,7 @@ def test_published_rn_towers_vs_oracle_on_device(name):
     from clip_guided_diffusion_b200 import weights as pw
     from oracle import clip_rn as orn
     from tests.plan_interp import Interp
-    n = 2
+    n = 2 if name in ("RN50", "RN101") else 1  # the wide towers (288 / 384 px, zero-padded 80 / 96-wide layers): one image bounds the CPU oracle
     cfg = prn.RN_CONFIGS[name]
     sd = pw.seeded_rn_state_dict(cfg, seed=3)
     oracle = orn.ModifiedResNet(orn.RNConfig(layers=tuple(cfg.layers), output_dim=cfg.output_dim, input_resolution=cfg.input_resolution,
@@ -63,10 +63,11 @@ def test_published_rn_towers_vs_oracle_on_device(name):
     assert cos > 0.99, cos
 
 
-def test_step_with_rn_tower_vs_oracle_and_ops():
+@pytest.mark.parametrize("rn_width", [64, 80])  # 80: RN50x4's width, zero-padded to the 64-channel K slice layer by layer
+def test_step_with_rn_tower_vs_oracle_and_ops(rn_width):
     from tests.gpu_harness import compare_ops
     from tests.step_parity import build_tiny, compare, engine_step, make_inputs, oracle_step
-    ctx = build_tiny("cuda", image=64, use_graph=True, B=2, cutn=3, tower="rn")
+    ctx = build_tiny("cuda", image=64, use_graph=True, B=2, cutn=3, tower="rn", rn_width=rn_width)
     x, y, noise, nseed, coords = make_inputs(ctx)
     o = oracle_step(ctx, "ddim", x, 14, y, nseed, coords, fac_index=14)
     e = engine_step(ctx, "ddim", x, 14, y, noise, coords, fac_index=14, fused=True)

@@ -32,10 +32,23 @@ def test_stem_space_to_depth_weight():
     assert th.allclose(got, ref, atol=1e-5)
 
 
-@pytest.mark.parametrize("n", [2])
-def test_rn_tower_matches_oracle(n):
-    cfg = prn.RNConfig(layers=(1, 2, 1, 1), output_dim=128, input_resolution=64, width=64)
-    ocfg = orn.RNConfig(layers=(1, 2, 1, 1), output_dim=128, input_resolution=64, width=64)
+def test_published_wide_towers_structure():
+    """RN50x4 / RN50x16 (cgd/clip_util.py:17): published depth, width, resolution and embedding size; widths 80 / 96 are not multiples
+    of the 64-channel K slice (rn._conv_bn zero-pads them)"""
+    for name, (n_params, tokens, embed) in {"RN50x4": (None, 82, 2560), "RN50x16": (None, 145, 3072)}.items():
+        cfg = prn.RN_CONFIGS[name]
+        sh = pw.rn_param_shapes(cfg)
+        m = orn.ModifiedResNet(orn.RNConfig(tuple(cfg.layers), cfg.output_dim, cfg.input_resolution, cfg.width))
+        ref = {"visual." + k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+        assert sh == ref
+        assert cfg.tokens == tokens and cfg.embed_dim == embed and cfg.embed_dim // cfg.heads == 64
+        assert prn.rn_config_from_state_dict({k: th.empty(s) for k, s in sh.items()}) == cfg
+
+
+@pytest.mark.parametrize("n,width", [(2, 64), (2, 80), (1, 48)])
+def test_rn_tower_matches_oracle(n, width):
+    cfg = prn.RNConfig(layers=(1, 2, 1, 1), output_dim=128, input_resolution=64, width=width)
+    ocfg = orn.RNConfig(layers=(1, 2, 1, 1), output_dim=128, input_resolution=64, width=width)
     sd = pw.seeded_rn_state_dict(cfg, seed=3)
     oracle = orn.ModifiedResNet(ocfg).eval()
     missing = oracle.load_state_dict({k[len("visual."):]: v for k, v in sd.items()}, strict=False)

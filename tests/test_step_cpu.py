@@ -20,6 +20,7 @@ def _interp_runner(eng):
                                      # swapped sides are clipped at the border (quirk B3) and still pooled to a square
                                      ("ddim", dict(B=1, cutn=6, image=32, hw=(32, 64))),
                                      ("ddim", dict(B=2, cutn=3, tower="rn")),  # CLIP ModifiedResNet tower instead of the ViT
+                                     ("ddim", dict(B=1, cutn=2, tower="rn", rn_width=80)),  # RN50x4-style width: zero-padded 40 / 80 / 160-wide layers
                                      # use_augs (cgd/modules.py:12-24): flip / affine / perspective / grayscale / noise inside the cutout ops
                                      ("ddim", dict(B=2, cutn=4, image=64, use_augs=True)),
                                      ("ancestral", dict(B=1, cutn=6, image=32, hw=(32, 48), use_augs=True)),
