@@ -38,6 +38,10 @@ WORKLOADS = {
     "cfg5": dict(image_size=512, respacing="1000", per_gpu_batch=1, cutn=64, clip="ViT-L/14", lpips=True, tflop=29.1,
                  name="BASELINE configs[4] shard: image_size=512, respace=1000 (ancestral), batch=1 per GPU, cutn=64, ViT-L/14, "
                       "init image + LPIPS init_scale=1000 (LPIPS FLOPs not counted)"),
+    # not a BASELINE configuration: the reference's default arguments (cgd/cgd.py:20-33) -- the 128x128 checkpoint (4 heads of 128 / 192 /
+    # 256 channels: csrc/attention_wide.cu); tflop = the executed contractions of the op list (Plan.conv_flops)
+    "default128": dict(image_size=128, respacing="1000", per_gpu_batch=1, cutn=16, clip="ViT-B/32", lpips=False, tflop=1.492,
+                       name="reference defaults: image_size=128, respace=1000 (ancestral), batch=1 per GPU, cutn=16, ViT-B/32"),
 }
 CFG = WORKLOADS["cfg2"]
 FLOP_PER_IMAGE_STEP = 4.775e12  # UNet 2.240+2.252, CLIP 0.141+0.143 TFLOP (fwd + dgrad)

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcgd_b200.so")
-SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_narrow.cu", "norm.cu", "norm_fused.cu", "norm_grid.cu", "norm_grid2.cu", "norm_stream.cu", "elementwise.cu", "attention.cu", "attention_small.cu", "attention_mma.cu", "guidance.cu", "augs.cu", "lpips.cu", "linear_small.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_narrow.cu", "norm.cu", "norm_fused.cu", "norm_grid.cu", "norm_grid2.cu", "norm_stream.cu", "elementwise.cu", "attention.cu", "attention_small.cu", "attention_mma.cu", "attention_wide.cu", "guidance.cu", "augs.cu", "lpips.cu", "linear_small.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]
 

@@ -305,9 +305,13 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const AttnArgs a) {
   }
 }
 
+int attn_wide_supported(int64_t d);                          // attention_wide.cu: head dims 128 / 192 / 256 (the 128x128 checkpoint's 4 heads)
+int launch_attn_wide_fwd(const CgdOp& op, cudaStream_t st);
+int launch_attn_wide_bwd(const CgdOp& op, cudaStream_t st);
+
 static int attn_args(const CgdOp& op, AttnArgs& a, bool bwd) {
   a.B = (int)op.i[0]; a.heads = (int)op.i[1]; a.T = (int)op.i[2];
-  CGD_CHECK_ARG(op.i[3] == 64, "attention: head dim %lld unsupported (only 64)", (long long)op.i[3]);
+  CGD_CHECK_ARG(op.i[3] == 64 || attn_wide_supported(op.i[3]), "attention: head dim %lld unsupported (64, 128, 192, 256)", (long long)op.i[3]);
   CGD_CHECK_ARG(a.B > 0 && a.heads > 0 && a.T > 0, "attention: bad dims");
   a.qbs = op.i[4]; a.qrs = op.i[5]; a.qhs = op.i[6]; a.obs = op.i[7]; a.ors = op.i[8]; a.ohs = op.i[9];
   CGD_CHECK_ARG(a.qrs % 8 == 0 && a.qhs % 8 == 0 && a.qbs % 8 == 0 && a.ors % 8 == 0 && a.ohs % 8 == 0 && a.obs % 8 == 0,
@@ -348,11 +352,15 @@ static bool attn_use_mma() {
   }
   return !off;
 }
-int attn_bwd_num_launches(const CgdOp& op) { return attn_use_small(op.i[2]) ? 1 : (attn_use_mma() ? 2 : 3); }
+int attn_bwd_num_launches(const CgdOp& op) {
+  if (op.i[3] != 64) return 2;
+  return attn_use_small(op.i[2]) ? 1 : (attn_use_mma() ? 2 : 3);
+}
 
 int launch_attn_fwd(const CgdOp& op, cudaStream_t st) {
   AttnArgs a{};
   if (int rc = attn_args(op, a, false)) return rc;
+  if (op.i[3] != 64) return launch_attn_wide_fwd(op, st);
   if (attn_use_small(a.T)) return launch_attn_small_fwd(op, st);
   if (attn_use_mma()) return launch_attn_mma_fwd(op, st);
   const int smem = 4 * AT * ALD * (int)sizeof(float);
@@ -369,6 +377,7 @@ int launch_attn_fwd(const CgdOp& op, cudaStream_t st) {
 int launch_attn_bwd(const CgdOp& op, cudaStream_t st) {
   AttnArgs a{};
   if (int rc = attn_args(op, a, true)) return rc;
+  if (op.i[3] != 64) return launch_attn_wide_bwd(op, st);
   if (attn_use_small(a.T)) return launch_attn_small_bwd(op, st);
   if (attn_use_mma()) return launch_attn_mma_bwd(op, st);
   const int smem_kv = 8 * AT * ALD * (int)sizeof(float), smem_q = 6 * AT * ALD * (int)sizeof(float);

@@ -613,14 +613,14 @@ class Plan:
         self._tape.append(bwd)
         return y
 
-    # ------------------------------------------------------------------ attention (head dim 64)
+    # ------------------------------------------------------------------ attention (head dim 64; 128 / 192 / 256 for the 128^2 checkpoint)
     def attention(self, qkv: Act, heads: int, T: int, nbatch: int, legacy_order: bool, name="attn") -> Act:
         """qkv: [nbatch*T rows, 3C].  legacy_order: per-head [q|k|v] interleave (UNet QKVAttentionLegacy);
         otherwise [q heads | k heads | v heads] (QKVAttention, nn.MultiheadAttention)."""
         C = qkv.C // 3
         d = C // heads
-        assert d == 64, "attention kernels support head dim 64"
-        if T % 256 == 0 and self.tc_attention and self.conv_impl in (0, 1, 3):
+        assert d in (64, 128, 192, 256), f"attention kernels support head dims 64 / 128 / 192 / 256, got {d}"
+        if d == 64 and T % 256 == 0 and self.tc_attention and self.conv_impl in (0, 1, 3):
             return self._attention_tc(qkv, heads, T, nbatch, legacy_order, name)
         out = Act(self.new(nbatch * T * C, "h", name), 0, qkv.N, qkv.H, qkv.W, C, C)
         lse = self.new(nbatch * heads * T, "f", name + "_lse")

@@ -1,5 +1,6 @@
-"""GPU: softmax attention (head dim 64) forward and input-gradient -- the single-tile tensor-core kernels (T <= 64:
-csrc/attention_small.cu), the flash kernels (csrc/attention.cu) and the batched-GEMM path (T % 256 == 0) -- against a plain PyTorch
+"""GPU: softmax attention (head dim 64; 128 / 192 / 256 for the 128x128 checkpoint's four heads: csrc/attention_wide.cu) forward and
+input-gradient -- the single-tile tensor-core kernels (T <= 64: csrc/attention_small.cu), the flash kernels (csrc/attention_mma.cu)
+and the batched-GEMM path (T % 256 == 0) -- against a plain PyTorch
 fp32 reference of [3P] QKVAttentionLegacy / QKVAttention / nn.MultiheadAttention's core."""
 import math
 
@@ -21,7 +22,18 @@ CASES = [  # nbatch, heads, T, legacy
     (1, 4, 256, True),     # UNet 16x16 level
     (1, 8, 1024, True),    # UNet 32x32 level
     (1, 2, 300, False),    # ragged last tile
+    # head dims of the 128x128 checkpoint (num_heads = 4): 32x32 level 512 / 4, 16x16 level 768 / 4, 8x8 level 1024 / 4
+    (1, 4, 1024, True, 128),
+    (1, 4, 256, True, 192),
+    (1, 4, 64, True, 256),
+    (2, 2, 100, True, 128),    # ragged last tile, two images
+    (2, 3, 37, False, 192),    # single ragged tile, [q.. | k.. | v..] order
+    (1, 2, 130, False, 256),   # three tiles, the last with 2 rows
 ]
+
+
+def _case_id(c):
+    return f"b{c[0]}_h{c[1]}_t{c[2]}_{'legacy' if c[3] else 'new'}" + (f"_d{c[4]}" if len(c) > 4 else "")
 
 
 def _split(qkv, heads, legacy):
@@ -44,12 +56,13 @@ def _ref(qkv, heads, legacy):
 
 
 @pytest.mark.parametrize("tc", [False, True], ids=["flash", "tcgen05_gemms"])
-@pytest.mark.parametrize("case", CASES, ids=[f"b{c[0]}_h{c[1]}_t{c[2]}_{'legacy' if c[3] else 'new'}" for c in CASES])
+@pytest.mark.parametrize("case", CASES, ids=[_case_id(c) for c in CASES])
 def test_attention_fwd_bwd(case, tc):
-    B, heads, T, legacy = case
-    if tc and T % 256 != 0:
-        pytest.skip("the batched-GEMM path needs T % 256 == 0")
-    C = heads * 64
+    B, heads, T, legacy = case[:4]
+    d = case[4] if len(case) > 4 else 64
+    if tc and (T % 256 != 0 or d != 64):
+        pytest.skip("the batched-GEMM path needs T % 256 == 0 and head dim 64")
+    C = heads * d
     th.manual_seed(0)
     plan = Plan()
     plan.tc_attention = tc  # False: flash kernels (attention_small.cu / attention_mma.cu); True: batched tcgen05 GEMMs

@@ -8,6 +8,7 @@ state_dict in upstream key layout), x_t, timestep, class label, noise and cutout
     cfg3  256x256, "1000" (ancestral), 1 image, 32 cutouts, ViT-B/32      (per-GPU shard of batch 8)
     cfg4  512x512, ddim250,            1 image, 16 cutouts, ViT-B/16      (per-GPU shard of batch 4)
     cfg5  512x512, "1000" (ancestral), 1 image, 64 cutouts, ViT-L/14, init image + LPIPS init_scale 1000 (shard of batch 8)
+    default128  128x128, "1000" (ancestral), 1 image, 16 cutouts, ViT-B/32: the reference's default arguments (cgd/cgd.py:20-33)
 
 Tolerances (SURVEY.md 8c protocol item 2, the same as tests/test_gpu_ops.py): cos(g) > 0.995, rel L2 of pred_xstart and of the
 sample < 2e-2 (fp16 storage with fp32 accumulation against fp32 everywhere), the loss terms within 2 %."""
@@ -28,6 +29,9 @@ CASES = {
     "cfg3": dict(size=256, respacing="1000", cutn=32, clip="ViT-B/32", lpips=False, t_index=700),
     "cfg4": dict(size=512, respacing="ddim250", cutn=16, clip="ViT-B/16", lpips=False, t_index=120),
     "cfg5": dict(size=512, respacing="1000", cutn=64, clip="ViT-L/14", lpips=True, t_index=400),
+    # not a BASELINE configuration: the reference's DEFAULT call (cgd/cgd.py:20-33: image_size 128, "1000", 16 cutouts, ViT-B/32) -- the
+    # 128x128 checkpoint, whose four heads attend with 128 / 192 / 256 channels each (csrc/attention_wide.cu)
+    "default128": dict(size=128, respacing="1000", cutn=16, clip="ViT-B/32", lpips=False, t_index=500),
 }
 
 

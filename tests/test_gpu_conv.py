@@ -42,6 +42,18 @@ CASES = [
     ("conv1x1_8x8_proj_res_b2", 2, 8, 8, 1024, 1024, 1, True, True),
     ("conv1x1_8x8_k3072", 1, 8, 8, 3072, 1024, 1, True, False),
     ("conv3x3_8x8_c2048_to_1024", 1, 8, 8, 2048, 1024, 9, True, False),   # K too large for the slab: stays on the tcgen05 split-K path
+    # widths of the 128x128 checkpoint (channel_mult 1, 1, 2, 3, 4: a 768-wide 16x16 level, 1280 / 1792-wide concatenations)
+    ("conv3x3_16x16_c768_res", 1, 16, 16, 768, 768, 9, True, True),
+    ("conv3x3_16x16_c1792_to_768", 1, 16, 16, 1792, 768, 9, True, False),
+    ("conv3x3_32x32_c1280_to_512", 1, 32, 32, 1280, 512, 9, True, False),
+    ("conv1x1_16x16_c768_qkv", 1, 16, 16, 768, 2304, 1, True, False),
+    ("conv3x3_8x8_c1792_to_1024", 1, 8, 8, 1792, 1024, 9, True, False),
+    # CLIP RN50x4 (288 px, width 80 zero-padded to 128; 320 / 640 / 2560-wide stages) and RN50x16 (384 px) shapes
+    ("conv1x1_72x72_c128_to_320_res", 1, 72, 72, 128, 320, 1, True, True),
+    ("conv3x3_144x144_c64_to_128", 1, 144, 144, 64, 128, 9, True, False),
+    ("conv3x3_36x36_c192", 2, 36, 36, 192, 192, 9, True, False),
+    ("conv1x1_9x9_c2560_to_640", 1, 9, 9, 2560, 640, 1, True, True),
+    ("linear_m82_k2560_qkv", 1, 1, 82, 2560, 7680, 1, True, False),
 ]
 
 

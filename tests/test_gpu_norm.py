@@ -29,6 +29,12 @@ CASES = [
     (1, 65536, 512, False, True),   # 33 M elements: the direct-load backward engine (norm_grid2.cu)
     (2, 4096, 192, True, True),     # C = 192: groups straddle the 8-channel vectors (64x64 checkpoint widths)
     (3, 1024, 64, False, True),
+    # widths of the 128x128 checkpoint: 24 / 40 / 56 channels per group = 3 / 5 / 7 16-byte vectors per pixel per CTA in the fused kernels
+    (1, 256, 768, True, True),
+    (1, 64, 768, False, False),
+    (1, 1024, 1280, True, True),
+    (1, 256, 1792, True, True),
+    (1, 64, 1792, False, True),
 ]
 
 

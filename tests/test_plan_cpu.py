@@ -54,6 +54,38 @@ def test_unet_plan_matches_oracle(new_order, cond):
     assert cos(g, gref) > 0.999 and rel(g, gref) < 4e-2, (cos(g, gref), rel(g, gref))
 
 
+@pytest.mark.parametrize("heads,mult", [(1, (1, 2)), (1, (1, 2, 3))])
+def test_unet_plan_with_num_heads_wide_head_dims(heads, mult):
+    """the 128x128 checkpoint's attention (data/diffusion_model_flags.py: num_heads = 4, num_head_channels unset -> head dim =
+    channels / num_heads = 128 / 192 / 256; csrc/attention_wide.cu): here 128 and 192 channels in one head, legacy qkv order"""
+    import dataclasses
+    th.manual_seed(0)
+    size = 16 * 2 ** (len(mult) - 1)
+    ocfg = tiny_config(image_size=size, model_channels=64, channel_mult=mult, num_res_blocks=1, attention_resolutions=(size // 2, size // 4))
+    ocfg = dataclasses.replace(ocfg, num_heads=heads, num_head_channels=-1)
+    oracle = seeded_init_(UNetModel(ocfg)).eval()
+    B = 1
+    net = pu.UNetB200(_prod_cfg(ocfg), oracle.state_dict(), batch=B, device="cpu", seed_scale=64.0)
+    from clip_guided_diffusion_b200._lib import OP
+    dims = sorted({op.i[3] for op in net.plan.ops if op.code == OP["ATTN_FWD"]})
+    assert dims == [64 * m for m in mult[1:]], dims
+    it = Interp(net.plan)
+    x = th.randn(B, 3, size, size)
+    t = th.tensor([431.0])
+    y = th.tensor([3])
+    net.set_inputs(x, t, y)
+    it.run_range("unet_emb", "unet_bwd")
+    xo = x.clone().requires_grad_()
+    ref = oracle(xo, t, y)
+    assert rel(net.out_view.clone(), ref.detach()) < 2e-2
+    d_out = th.randn(B, 6, size, size) * 0.1
+    (gref,) = th.autograd.grad((ref * d_out).sum(), xo)
+    net.seed_view[:, :, :6] = (d_out * net.seed_scale).reshape(B, 6, -1).permute(0, 2, 1).half()
+    it.run_range("unet_bwd", "unet_end")
+    g = net.dx_view / net.seed_scale
+    assert cos(g, gref) > 0.999 and rel(g, gref) < 4e-2, (cos(g, gref), rel(g, gref))
+
+
 def test_vit_plan_matches_oracle():
     th.manual_seed(0)
     ocfg = OViTConfig(64, 32, 128, 2, 64)
@@ -81,7 +113,7 @@ def test_param_inventories_match_oracle():
     from clip_guided_diffusion_b200 import weights as pw
     from oracle.unet import config_for as oconfig_for
     from oracle.clip_vit import VIT_CONFIGS as OV
-    for size, cond in [(64, True), (256, True), (256, False), (512, True)]:
+    for size, cond in [(64, True), (128, True), (256, True), (256, False), (512, True)]:
         with th.device("meta"):
             m = UNetModel(oconfig_for(size, cond))
         ref = {k: tuple(v.shape) for k, v in m.state_dict().items()}
@@ -98,10 +130,11 @@ def test_cluster_split_picks_are_eligible():
     one wave of clusters; every K split is non-empty."""
     from clip_guided_diffusion_b200 import plan as P
     seen = 0
-    for (NB, H, W) in [(1, 8, 8), (2, 8, 8), (1, 16, 16), (1, 32, 32), (1, 64, 64), (1, 1, 800), (1, 1, 3152), (4, 16, 16)]:
+    for (NB, H, W) in [(1, 8, 8), (2, 8, 8), (1, 16, 16), (1, 32, 32), (1, 64, 64), (1, 1, 800), (1, 1, 3152), (4, 16, 16),
+                       (1, 72, 72), (1, 36, 36), (2, 18, 18), (1, 9, 9), (1, 1, 82), (1, 12, 12), (1, 1, 145)]:
         m_tiles = P.conv_tile_count(NB, H, W)
-        for cin in (256, 512, 768, 1024, 1536, 2048, 2304, 3072):
-            for cout in (256, 512, 768, 1024, 1536, 2048, 3072):
+        for cin in (128, 192, 256, 320, 512, 640, 768, 1024, 1280, 1536, 1792, 2048, 2304, 2560, 3072):
+            for cout in (128, 192, 256, 320, 512, 640, 768, 1024, 1280, 1536, 1792, 2048, 2560, 3072, 7680):
                 for taps in (1, 9):
                     kb = taps * cin // 64
                     npad = P._npad(cout)
