@@ -1,5 +1,5 @@
-"""Pair every op of the cfg2 step plan (rebuilt on the CPU, shapes only) with its launch(es) in an ncu gpu__time_duration launch
-list of scripts/profile_step.py eager, and print time by op kind and shape.
+"""Pair every op of the cfg2 step plan (or of the bench workload named by CGD_PROFILE_WORKLOAD; rebuilt on the CPU, shapes only) with its
+launch(es) in an ncu gpu__time_duration launch list of scripts/profile_step.py eager, and print time by op kind and shape.
 
     python scripts/op_report.py profiles/r01_launches_cfg2_step_v5_warm.csv [kind-filter]
 """
@@ -53,10 +53,13 @@ STREAM = os.environ.get("CGD_GN_GRID_ENGINE", "direct")[0] == "s"
 def main():
     launches = load_launches(sys.argv[1])
     filt = sys.argv[2] if len(sys.argv) > 2 else None
+    if os.environ.get("CGD_PROFILE_WORKLOAD"):
+        bench.CFG = bench.WORKLOADS[os.environ["CGD_PROFILE_WORKLOAD"]]
+    ddim = bench.CFG["respacing"].startswith("ddim")
     eng, diff, cond = bench.build_engine(th.device("cpu"), 0, 1)
     plan, m = eng.plan, eng.plan.marks
     segs = [("unet_emb", "unet_bwd"), ("pmv", "cond"), ("cut_fwd", "sph"), ("vit_fwd", "vit_bwd"), ("sph", "cut_bwd"), ("vit_bwd", "vit_end"),
-            ("cut_bwd", "guide"), ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g"), ("upd_ddim_g", "upd_ddim")]
+            ("cut_bwd", "guide"), ("guide", "final"), ("unet_bwd", "unet_end"), ("final", "upd_anc_g"), ("upd_ddim_g", "upd_ddim") if ddim else ("upd_anc_g", "upd_anc")]
     ops = []
     for a, b in segs:
         ops += plan.ops[m[a]:m[b]]
@@ -70,7 +73,7 @@ def main():
         if kind == "CONV" and op.i[17] > 1 and not (len(op.i) > 23 and op.i[23]):
             n = 2
         elif kind == "ATTN_BWD":
-            n = 1 if op.i[2] <= 64 else 2
+            n = 1 if op.i[2] <= 64 and op.i[3] == 64 else 2
         elif kind == "FINAL_GRAD" and op.flags & 1:
             n = 2
         elif kind in ("GN_FWD_GRID", "GN_BWD_GRID") and STREAM and op.i[2] % 256 == 0:
