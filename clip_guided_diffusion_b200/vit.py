@@ -46,6 +46,7 @@ VIT_CONFIGS = {
     "ViT-B/32": ViTConfig(224, 32, 768, 12, 512),
     "ViT-B/16": ViTConfig(224, 16, 768, 12, 512),
     "ViT-L/14": ViTConfig(224, 14, 1024, 24, 768),
+    "ViT-L/14@336px": ViTConfig(336, 14, 1024, 24, 768),  # in CLIP_MODEL_URLS (cgd/clip_util.py:28): 24 x 24 patches + class token = 577 tokens
 }
 
 

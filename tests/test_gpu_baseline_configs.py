@@ -9,6 +9,7 @@ state_dict in upstream key layout), x_t, timestep, class label, noise and cutout
     cfg4  512x512, ddim250,            1 image, 16 cutouts, ViT-B/16      (per-GPU shard of batch 4)
     cfg5  512x512, "1000" (ancestral), 1 image, 64 cutouts, ViT-L/14, init image + LPIPS init_scale 1000 (shard of batch 8)
     default128  128x128, "1000" (ancestral), 1 image, 16 cutouts, ViT-B/32: the reference's default arguments (cgd/cgd.py:20-33)
+    vit_l14_336  256x256, ddim250, 1 image, 4 cutouts of 336 px, ViT-L/14@336px
 
 Tolerances (SURVEY.md 8c protocol item 2, the same as tests/test_gpu_ops.py): cos(g) > 0.995, rel L2 of pred_xstart and of the
 sample < 2e-2 (fp16 storage with fp32 accumulation against fp32 everywhere), the loss terms within 2 %."""
@@ -32,6 +33,8 @@ CASES = {
     # not a BASELINE configuration: the reference's DEFAULT call (cgd/cgd.py:20-33: image_size 128, "1000", 16 cutouts, ViT-B/32) -- the
     # 128x128 checkpoint, whose four heads attend with 128 / 192 / 256 channels each (csrc/attention_wide.cu)
     "default128": dict(size=128, respacing="1000", cutn=16, clip="ViT-B/32", lpips=False, t_index=500),
+    # the one CLIP_MODEL_URLS entry (cgd/clip_util.py:28) whose cutouts are not 224 px: 336 px, 24 x 24 patches of 14, 577 tokens
+    "vit_l14_336": dict(size=256, respacing="ddim250", cutn=4, clip="ViT-L/14@336px", lpips=False, t_index=180),
 }
 
 
@@ -51,7 +54,8 @@ def _oracle_on_gpu(c, usd, vsd, lsd, init, tgt, dev):
     ucfg = pu.config_for(c["size"], True)
     odiff = od.create_gaussian_diffusion(1000, "linear", c["respacing"], rescale_timesteps=ucfg.rescale_timesteps)
     olp = ol.LPIPSVgg({k: v.to(dev) for k, v in lsd.items()}).to(dev) if lsd is not None else None
-    cond = og.OracleCondFn(odiff, oclip, tgt.to(dev), th.ones(1, device=dev), cut_size=224, num_cutouts=c["cutn"], lpips_model=olp,
+    cond = og.OracleCondFn(odiff, oclip, tgt.to(dev), th.ones(1, device=dev), cut_size=VIT_CONFIGS[c["clip"]].input_resolution,
+                           num_cutouts=c["cutn"], lpips_model=olp,
                            init_tensor=init.to(dev) if init is not None else None, init_scale=1000.0 if lsd is not None else 0.0)
     return ounet, odiff, cond
 
@@ -76,7 +80,7 @@ def test_full_size_step_vs_fp32_oracle(name):
         noise = th.randn(1, 3, size, size, generator=g)
         y = th.tensor([417])
         th.manual_seed(23)
-        coords = pg.MakeCutouts(224, c["cutn"])._generate_coords(size, size, c["cutn"])
+        coords = pg.MakeCutouts(vcfg.input_resolution, c["cutn"])._generate_coords(size, size, c["cutn"])
         t_index = c["t_index"]
 
         # ---- engine: one CUDA-graph replay of the fused step

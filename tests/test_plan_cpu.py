@@ -118,7 +118,7 @@ def test_param_inventories_match_oracle():
             m = UNetModel(oconfig_for(size, cond))
         ref = {k: tuple(v.shape) for k, v in m.state_dict().items()}
         assert pw.unet_param_shapes(pu.config_for(size, cond)) == ref
-    for name in ("ViT-B/32", "ViT-B/16", "ViT-L/14"):
+    for name in ("ViT-B/32", "ViT-B/16", "ViT-L/14", "ViT-L/14@336px"):
         with th.device("meta"):
             m = CLIPVisualOnly(OV[name])
         ref = {k: tuple(v.shape) for k, v in m.state_dict().items()}
