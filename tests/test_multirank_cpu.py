@@ -103,7 +103,12 @@ def _entry_worker(rank, world, port, outdir, ret):
     from tests.test_entry_cpu import _InterpretedEngine
     cgd._require_cuda = lambda device: None
     cgd.GuidedStepB200 = _InterpretedEngine
-    ucfg, vcfg = pu.config_for(64, True), pv.ViTConfig(32, 16, 64, 1, 32)
+    # a two-level 64-channel UNet of the 64 x 64 family: the collective and the save / yield bookkeeping are under test here, the real
+    # 64 x 64 architecture goes through the same entry point in tests/test_entry_cpu.py
+    ucfg = pu.UNetConfig(image_size=64, model_channels=64, num_res_blocks=1, channel_mult=(1, 2), attention_resolutions=(32,),
+                         use_new_attention_order=True, noise_schedule="cosine")
+    cgd.config_for = lambda image_size, class_cond=True: ucfg
+    vcfg = pv.ViTConfig(32, 16, 64, 1, 32)
     usd = pw.seeded_state_dict(pw.unet_param_shapes(ucfg), 1234)
     vsd = pw.seeded_state_dict(pw.vit_param_shapes(vcfg), 1235)
     tgt = th.randn(1, 32, generator=th.Generator().manual_seed(0))
