@@ -116,3 +116,45 @@ def test_oracle_lpips_trunk_matches_torchvision_vgg16():
     assert d.shape == (2, 1, 1, 1) and float((d - want).abs().max() / want.abs().max()) < 1e-5
     assert tuple(model.shift.flatten().tolist()) == pytest.approx((-0.030, -0.088, -0.188))
     assert tuple(model.scale.flatten().tolist()) == pytest.approx((0.458, 0.448, 0.450))
+
+
+def test_oracle_rn_bottleneck_stages_match_torchvision():
+    """`oracle/clip_rn.py` Bottleneck vs torchvision's: CLIP's ModifiedResNet differs from the torchvision ResNet only in the stem, the
+    anti-aliasing average pools (stride > 1) and the attention pool.  Its stride-1 stage is torchvision's `resnet50().layer1` key for
+    key (the "-1" pool of `downsample` holds no parameters), so the same state_dict must give the same output and input gradient; a
+    strided bottleneck equals a stride-1 torchvision block evaluated in two halves with the pool in between."""
+    import torchvision
+    from oracle.clip_rn import Bottleneck, ModifiedResNet, RNConfig
+    g = th.Generator().manual_seed(11)
+    o = ModifiedResNet(RNConfig(layers=(3, 1, 1, 1), output_dim=64, input_resolution=32, width=64)).eval()
+    sd = {}
+    for k, v in o.layer1.state_dict().items():  # random weights AND random BatchNorm running statistics
+        sd[k] = v if "num_batches" in k else (th.rand(v.shape, generator=g) + 0.5 if "running_var" in k else th.randn(v.shape, generator=g) * 0.2)
+    o.layer1.load_state_dict(sd)
+    tv = torchvision.models.resnet50(weights=None).layer1.eval()
+    tv.load_state_dict(sd)  # identical keys
+    x = th.randn(2, 64, 8, 8, generator=g)
+    seed = th.randn(2, 256, 8, 8, generator=g)
+    a, ga = _fwd_and_grad(o.layer1, x, seed)
+    b, gb = _fwd_and_grad(tv, x, seed)
+    assert float((a - b).abs().max() / b.abs().max()) < 1e-5 and float((ga - gb).abs().max() / gb.abs().max()) < 1e-5
+
+    blk = Bottleneck(256, 128, stride=2).eval()  # first block of layer2
+    bsd = {}
+    for k, v in blk.state_dict().items():
+        bsd[k] = v if "num_batches" in k else (th.rand(v.shape, generator=g) + 0.5 if "running_var" in k else th.randn(v.shape, generator=g) * 0.2)
+    blk.load_state_dict(bsd)
+    tvb = torchvision.models.resnet.Bottleneck(256, 128, stride=1, downsample=th.nn.Sequential(
+        th.nn.Conv2d(256, 512, 1, bias=False), th.nn.BatchNorm2d(512))).eval()
+    tvb.load_state_dict(bsd)
+    pool = th.nn.AvgPool2d(2)
+
+    def tv_strided(z):  # torchvision's layers, CLIP's pool placement: after the 3x3's ReLU on the main branch, before the 1x1 on the skip
+        h = tvb.relu(tvb.bn2(tvb.conv2(tvb.relu(tvb.bn1(tvb.conv1(z))))))
+        return tvb.relu(tvb.bn3(tvb.conv3(pool(h))) + tvb.downsample(pool(z)))
+
+    x = th.randn(2, 256, 8, 8, generator=g)
+    seed = th.randn(2, 512, 4, 4, generator=g)
+    a, ga = _fwd_and_grad(blk, x, seed)
+    b, gb = _fwd_and_grad(tv_strided, x, seed)
+    assert float((a - b).abs().max() / b.abs().max()) < 1e-5 and float((ga - gb).abs().max() / gb.abs().max()) < 1e-5
