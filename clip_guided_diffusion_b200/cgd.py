@@ -200,7 +200,7 @@ def clip_guided_diffusion(
         from PIL import Image
         import numpy as np
         pil = Image.open(init_image).convert("RGB").resize((image_size, image_size))
-        init_tensor = th.from_numpy(np.asarray(pil)).float().div(255).permute(2, 0, 1).unsqueeze(0).mul(2).sub(1).to(device)
+        init_tensor = th.from_numpy(np.array(pil)).float().div(255).permute(2, 0, 1).unsqueeze(0).mul(2).sub(1).to(device)
         if engine.lpips is not None:  # cgd/cgd.py:147-148, 220-224
             engine.set_init_image(init_tensor)
 
