@@ -78,7 +78,8 @@ def _load_unet_sd(image_size, class_cond, checkpoints_dir):
 
 
 def _load_clip_sd(clip_model_name, checkpoints_dir):
-    path = os.path.join(checkpoints_dir, "clip", clip_model_name.replace("/", "-") + ".pt")
+    # file names of CLIP_MODEL_URLS (cgd/clip_util.py:20-29): ViT-B-32.pt, RN50x4.pt, ViT-L-14-336px.pt
+    path = os.path.join(checkpoints_dir, "clip", clip_model_name.replace("/", "-").replace("@", "-") + ".pt")
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} not found: pass clip_state_dict=...")
     try:
