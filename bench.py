@@ -50,10 +50,15 @@ DOMINANT = dict(M=65536, N=256, K=2304)  # 256^2 x 256ch conv3x3: 31 % of the UN
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    fb = dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")  # B200_PROFILING.md's stated fallback
     if os.path.exists(p):
-        d = json.load(open(p))
-        return dict(burst=float(d["bf16_tflops"]), sustained=float(d["bf16_tflops_sustained"]), hbm=float(d["hbm_gbs"]), src="measured")
-    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+        try:
+            d = json.load(open(p))
+            burst = float(d["bf16_tflops"])
+            return dict(burst=burst, sustained=float(d.get("bf16_tflops_sustained", burst)), hbm=float(d.get("hbm_gbs", fb["hbm"])), src="measured")
+        except (OSError, ValueError, KeyError, TypeError):  # unreadable / other schema: say "fallback" rather than abort the bench line
+            pass
+    return fb
 
 
 class ClockSampler:
