@@ -22,6 +22,7 @@ CASES = [  # nbatch, heads, T, legacy
     (1, 4, 256, True),     # UNet 16x16 level
     (1, 8, 1024, True),    # UNet 32x32 level
     (1, 2, 300, False),    # ragged last tile
+    (2, 16, 577, False),   # ViT-L/14@336px token count (24 x 24 patches + class token): nine full tiles and one row
     # head dims of the 128x128 checkpoint (num_heads = 4): 32x32 level 512 / 4, 16x16 level 768 / 4, 8x8 level 1024 / 4
     (1, 4, 1024, True, 128),
     (1, 4, 256, True, 192),

@@ -60,17 +60,8 @@ def _oracle_on_gpu(c, usd, vsd, lsd, init, tgt, dev):
     return ounet, odiff, cond
 
 
-# cases whose first device run is still pending are collected by tests/test_gpu_zz_first_run.py, the last file pytest visits, so that under
-# `-x` a surprise there cannot hide the result of any test that has already run on a B200
-FIRST_RUN_PENDING = ("vit_l14_336",)
-
-
-@pytest.mark.parametrize("name", [n for n in CASES if n not in FIRST_RUN_PENDING])
+@pytest.mark.parametrize("name", list(CASES))
 def test_full_size_step_vs_fp32_oracle(name):
-    run_case(name)
-
-
-def run_case(name):
     c = CASES[name]
     dev = th.device("cuda:0")
     tf32 = (th.backends.cuda.matmul.allow_tf32, th.backends.cudnn.allow_tf32)
