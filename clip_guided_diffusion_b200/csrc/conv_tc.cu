@@ -353,6 +353,12 @@ int conv_tc_prepare(const CgdOp& op, ConvTcLaunch& L) {
   const int64_t NB = op.i[0], H = op.i[1], W = op.i[2], Cin = op.i[3], Cout = op.i[4], Npad = op.i[5], taps = op.i[6];
   const int64_t BN = op.i[16], splits = op.i[17] > 0 ? op.i[17] : 1;
   CGD_CHECK_ARG(NB > 0 && H > 0 && W > 0, "conv: bad image dims %lld %lld %lld", (long long)NB, (long long)H, (long long)W);
+  // tile counts, pixel indices and the TMA box arithmetic below are 32-bit: reject sizes whose pixel count does not fit instead of
+  // overflowing (a 2^31-row "image" used to spin in pick_tile's power-of-two search)
+  CGD_CHECK_ARG(NB <= (1 << 24) && H <= (1 << 24) && W <= (1 << 24) && NB * H <= (int64_t)0x7fffffff && NB * H * W <= (int64_t)0x7fffffff && Cin <= (1 << 24) &&
+                    Cout <= (1 << 24) && Npad <= (1 << 24),
+                "conv: dims out of range (N %lld H %lld W %lld Cin %lld Cout %lld Npad %lld; N*H*W must fit 31 bits)", (long long)NB,
+                (long long)H, (long long)W, (long long)Cin, (long long)Cout, (long long)Npad);
   CGD_CHECK_ARG(Cin > 0 && Cin % 64 == 0, "conv: Cin=%lld must be a positive multiple of 64", (long long)Cin);
   CGD_CHECK_ARG(taps == 1 || taps == 9, "conv: taps must be 1 or 9");
   CGD_CHECK_ARG(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 192 || BN == 256, "conv: unsupported BN=%lld", (long long)BN);

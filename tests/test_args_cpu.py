@@ -64,3 +64,42 @@ def test_epilogue_statistics_ops_pass_c_side_checks():
         plan.backward()
         assert P.OP["GN_APPLY_EPI"] in [o.code for o in plan.ops] and plan.ops[0].flags & 2
         _check_plan(plan, f"epi stats {N}x{H}x{W}")
+
+
+FULL_SIZE = {  # every configuration that runs on the device at full size (tests/test_gpu_baseline_configs.py, test_gpu_fullsize.py, test_gpu_rn.py)
+    "cfg1": dict(size=64, cutn=4, clip="ViT-B/32", mag=True),
+    "cfg2": dict(size=256, cutn=16, clip="ViT-B/32"),
+    "cfg3": dict(size=256, cutn=32, clip="ViT-B/32"),
+    "cfg4": dict(size=512, cutn=16, clip="ViT-B/16"),
+    "cfg5": dict(size=512, cutn=64, clip="ViT-L/14", lpips=True),
+    "default128": dict(size=128, cutn=16, clip="ViT-B/32"),
+    "vit_l14_336": dict(size=256, cutn=4, clip="ViT-L/14@336px"),
+    "rn50x16": dict(size=256, cutn=4, clip="RN50x16"),
+    "rn101": dict(size=256, cutn=8, clip="RN101"),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_size_step_plans_pass_c_side_checks(name, monkeypatch):
+    """the op lists of the published architectures, built shapes-only (no weight data is packed: `Plan.const` only reserves the bytes),
+    against the library's argument checks -- a check tightened in csrc/ must not reject a layer of a real checkpoint"""
+    from clip_guided_diffusion_b200 import guidance as pg
+    from clip_guided_diffusion_b200 import rn as prn
+    from clip_guided_diffusion_b200 import unet as pu
+    from clip_guided_diffusion_b200 import vit as pv
+    from clip_guided_diffusion_b200 import weights as pw
+    monkeypatch.setattr(P.Plan, "const", lambda self, t, dt, name="": self.new(t.numel(), dt, name))
+    monkeypatch.setattr(P.Plan, "finalize", lambda self, device: self)
+    c = FULL_SIZE[name]
+    empty = lambda shapes: {k: th.empty(v) for k, v in shapes.items()}  # noqa: E731
+    ucfg = pu.config_for(c["size"], True)
+    if c["clip"].startswith("RN"):
+        vcfg = prn.RN_CONFIGS[c["clip"]]
+        vsd = {k: (th.ones(v) if k.endswith("running_var") else th.zeros(v)) for k, v in pw.rn_param_shapes(vcfg).items()}  # BatchNorm is folded on the host
+    else:
+        vcfg = pv.VIT_CONFIGS[c["clip"]]
+        vsd = empty(pw.vit_param_shapes(vcfg))
+    extra = dict(lpips_sd=empty(pw.lpips_param_shapes()), init_scale=1000.0) if c.get("lpips") else {}
+    eng = pg.GuidedStepB200(ucfg, empty(pw.unet_param_shapes(ucfg)), vcfg, vsd, batch=1, num_cutouts=c["cutn"], device="cpu",
+                            use_magnitude=c.get("mag", False), **extra)
+    assert _check_plan(eng.plan, name) > 600
