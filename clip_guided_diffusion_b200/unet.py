@@ -101,6 +101,13 @@ class UNetB200:
         self.B = batch
         self.H = height or cfg.image_size
         self.W = width or cfg.image_size
+        # every level but the last halves the image and the output path doubles it back onto the skip connection: sizes that are not a
+        # multiple of 2^(levels - 1) (image_size + height_offset / width_offset, cgd/cgd.py:244) make the reference fail in th.cat of
+        # the first mismatching skip; said here, before anything is packed
+        step = 2 ** (len(cfg.channel_mult) - 1)
+        if self.H % step or self.W % step or self.H <= 0 or self.W <= 0:
+            raise ValueError(f"image {self.H}x{self.W}: height and width must be positive multiples of {step} for this {len(cfg.channel_mult)}-level UNet "
+                             "(image_size + height_offset / width_offset)")
         self.num_classes = cfg.num_classes if cfg.class_cond else None
         self.dtype = th.float16
         self.seed_scale = float(seed_scale)

@@ -79,3 +79,12 @@ def test_wide_image_fails_like_the_reference(tmp_path, monkeypatch):
 def test_init_scale_without_lpips_weights_is_a_clear_error(tmp_path, monkeypatch):
     with pytest.raises(RuntimeError, match="LPIPS"):
         _call(tmp_path, monkeypatch, dict(init_image="init.png", skip_timesteps=20, init_scale=1000))
+
+
+def test_offsets_that_break_the_skip_connections_are_a_clear_error(tmp_path, monkeypatch):
+    """image_size + offset must stay a multiple of 2^(levels - 1) (the reference dies in th.cat of the first skip connection)"""
+    with pytest.raises(ValueError, match="multiples of 2"):
+        _call(tmp_path, monkeypatch, dict(height_offset=1))
+    from clip_guided_diffusion_b200 import guidance as pg
+    with pytest.raises(ValueError, match="multiples of 32 for this 6-level UNet"):
+        pg.GuidedStepB200(pu.config_for(256, True), {}, None, None, batch=1, height=264, device="cpu")
