@@ -76,3 +76,29 @@ def test_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.split() == ["1", str(8 + 24 * 8 + 8 * 4 + 12 * 8)], out.stdout + out.stderr
+
+
+def test_product_path_never_imports_the_oracle():
+    """`oracle/` is test infrastructure: nothing under the package may import it, and bench.py only inside its CPU / PyTorch-CUDA
+    baseline legs (`oracle_cpu_setup`, `torch_cuda_baseline`) -- never in the engine construction or the timed loops of the own arm"""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def oracle_imports(path):
+        tree = ast.parse(open(path).read())
+        hits = []
+        for fn in ast.walk(tree):
+            if isinstance(fn, (ast.FunctionDef, ast.Module)):
+                for node in (fn.body if isinstance(fn, ast.FunctionDef) else [n for n in fn.body if not isinstance(n, (ast.FunctionDef, ast.ClassDef))]):
+                    for sub in ast.walk(node):
+                        mod = sub.module if isinstance(sub, ast.ImportFrom) else (sub.names[0].name if isinstance(sub, ast.Import) else None)
+                        if mod and (mod == "oracle" or mod.startswith("oracle.")):
+                            hits.append(getattr(fn, "name", "<module>"))
+        return set(hits)
+
+    pkg = os.path.join(root, "clip_guided_diffusion_b200")
+    for f in sorted(os.listdir(pkg)):
+        if f.endswith(".py"):
+            assert not oracle_imports(os.path.join(pkg, f)), f"{f} imports the oracle"
+    assert oracle_imports(os.path.join(root, "bench.py")) == {"oracle_cpu_setup", "torch_cuda_baseline"}  # also proves the detector sees imports
+    assert oracle_imports(os.path.join(root, "__graft_entry__.py")) == set()  # smoke() reaches it through tests/step_parity.py only
