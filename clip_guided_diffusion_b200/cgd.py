@@ -77,9 +77,13 @@ def _load_unet_sd(image_size, class_cond, checkpoints_dir):
     return th.load(path, map_location="cpu")
 
 
+def clip_checkpoint_filename(clip_model_name: str) -> str:
+    """file names of CLIP_MODEL_URLS (cgd/clip_util.py:20-29): ViT-B-32.pt, RN50x4.pt, ViT-L-14-336px.pt"""
+    return clip_model_name.replace("/", "-").replace("@", "-") + ".pt"
+
+
 def _load_clip_sd(clip_model_name, checkpoints_dir):
-    # file names of CLIP_MODEL_URLS (cgd/clip_util.py:20-29): ViT-B-32.pt, RN50x4.pt, ViT-L-14-336px.pt
-    path = os.path.join(checkpoints_dir, "clip", clip_model_name.replace("/", "-").replace("@", "-") + ".pt")
+    path = os.path.join(checkpoints_dir, "clip", clip_checkpoint_filename(clip_model_name))
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} not found: pass clip_state_dict=...")
     try:

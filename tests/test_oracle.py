@@ -246,3 +246,40 @@ def test_aug_ops_of_the_interpreter_match_the_reference_goldens():
     gx = plan.view(bg, (B, 3, H, W))
     gref = th.from_numpy(d[f"gx_{s}"]) * 0.5  # d/dx_in of ((x_in + 1) / 2); fp16 cotangent
     assert float((gx - gref).abs().max() / gref.abs().max()) < 2e-3
+
+
+def test_checkpoint_table_matches_the_reference_data_module():
+    """`config_for` (product and oracle), the checkpoint file names and the CLIP tower list against the reference's own tables
+    (data/diffusion_model_flags.py, cgd/clip_util.py:17-29; golden written by tests/golden/make_golden_flags.py), merged over
+    guided-diffusion's `model_and_diffusion_defaults()` the way cgd/script_util.py:305-315 does."""
+    import json
+    import os
+    from clip_guided_diffusion_b200 import cgd as pcgd
+    from clip_guided_diffusion_b200 import unet as pu
+    from clip_guided_diffusion_b200.rn import RN_CONFIGS
+    from clip_guided_diffusion_b200.vit import VIT_CONFIGS
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_flags_golden.json")))
+    defaults = dict(num_heads=4, num_head_channels=-1, use_new_attention_order=False, rescale_timesteps=False, noise_schedule="linear",
+                    class_cond=False)  # [3P] guided_diffusion/script_util.py model_and_diffusion_defaults (SURVEY Appendix A.1)
+    mult = {512: (0.5, 1, 1, 2, 2, 4, 4), 256: (1, 1, 2, 2, 4, 4), 128: (1, 1, 2, 3, 4), 64: (1, 2, 3, 4)}  # channel_mult "" -> by image size
+    assert len(gold["diffusion"]) == 6
+    for key, entry in gold["diffusion"].items():
+        cond, size = key.split("/")[0] == "cond", int(key.split("/")[1])
+        fl = {**defaults, **entry["model_flags"]}
+        assert fl["image_size"] == size and fl["class_cond"] == cond
+        # what every kernel of the path assumes about the published checkpoints
+        assert fl["learn_sigma"] and fl["resblock_updown"] and fl["use_scale_shift_norm"] and fl["use_fp16"] and fl["diffusion_steps"] == 1000
+        assert pcgd.DIFFUSION_FILENAMES[(cond, size)] == entry["filename"]
+        for cfg in (pu.config_for(size, cond), config_for(size, cond)):
+            assert cfg.image_size == size and cfg.class_cond == cond
+            assert cfg.model_channels == fl["num_channels"] and cfg.num_res_blocks == fl["num_res_blocks"]
+            assert tuple(cfg.attention_resolutions) == tuple(int(r) for r in fl["attention_resolutions"].split(","))
+            assert tuple(cfg.channel_mult) == mult[size]
+            assert cfg.num_head_channels == fl["num_head_channels"] and (fl["num_head_channels"] != -1 or cfg.num_heads == fl["num_heads"])
+            assert cfg.use_new_attention_order == fl["use_new_attention_order"]
+            assert cfg.rescale_timesteps == fl["rescale_timesteps"]
+        assert pu.config_for(size, cond).noise_schedule == fl["noise_schedule"]
+    towers = {**VIT_CONFIGS, **RN_CONFIGS}
+    assert set(gold["clip"]["names"]) <= set(towers), "every name of CLIP_MODEL_NAMES has a tower configuration"
+    for name, fname in gold["clip"]["files"].items():
+        assert pcgd.clip_checkpoint_filename(name) == fname
