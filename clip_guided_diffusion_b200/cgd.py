@@ -58,7 +58,9 @@ def log_image(image: th.Tensor, prefix_path, prompts, step: int, batch_idx: int)
     from PIL import Image
     dirname = Path(clean_and_combine_prompts(str(prefix_path), prompts, batch_idx))
     dirname.mkdir(parents=True, exist_ok=True)
-    arr = image.detach().float().add(1).div(2).clamp(0, 1).mul(255).round().byte().permute(1, 2, 0).cpu().numpy()
+    # tvf.to_pil_image(image.add(1).div(2).clamp(0, 1)) of the reference: torchvision converts a float tensor with `mul(255).byte()` --
+    # truncation, not rounding (pinned pixel for pixel on tests/golden/script_util_golden.json)
+    arr = image.detach().float().add(1).div(2).clamp(0, 1).mul(255).byte().permute(1, 2, 0).cpu().numpy()
     path = str(dirname / f"{step:04d}.png")
     pil = Image.fromarray(arr)
     pil.save(path)

@@ -66,3 +66,23 @@ def test_parse_prompt_and_log_image_known_answers(tmp_path, monkeypatch):
     assert cgd.clean_and_combine_prompts("o", ["a cat: 0.5/x!", "b"], 0) == os.path.join("o", "a_cat_05x_b", "00")
     assert len(os.path.basename(os.path.dirname(cgd.clean_and_combine_prompts("o", ["x" * 400], 0)))) == 255
     assert cgd.DIFFUSION_FILENAMES[(False, 512)] == "512x512_diffusion_uncond_finetune_008100.pt"
+
+
+def test_entry_helpers_match_the_reference_functions(tmp_path, monkeypatch):
+    """parse_prompt / clean_and_combine_prompts / log_image against answers produced by executing the reference's own function bodies
+    (tests/golden/make_golden_script_util.py): texts, weights, directory names, and the saved PNG pixel for pixel (torchvision's
+    to_pil_image truncates `x * 255`, it does not round)"""
+    import json
+    import numpy as np
+    from PIL import Image
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "script_util_golden.json")))
+    for prompt, text, weight in gold["parse_prompt"]:
+        assert cgd.parse_prompt(prompt) == (text, weight), prompt
+    for texts, batch_idx, path in gold["clean_and_combine_prompts"]:
+        assert cgd.clean_and_combine_prompts("o", texts, batch_idx) == path, texts
+    monkeypatch.chdir(tmp_path)
+    g = gold["log_image"]
+    path = cgd.log_image(th.tensor(g["image"], dtype=th.float32), "out", ["a b", "c!"], 12, 3)
+    assert path == g["path"] and os.path.exists("current.png") == g["current_png"]
+    assert np.array_equal(np.asarray(Image.open(path)), np.asarray(g["pixels"], dtype=np.uint8))
+    assert np.array_equal(np.asarray(Image.open("current.png")), np.asarray(g["pixels"], dtype=np.uint8))
