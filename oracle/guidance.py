@@ -3,7 +3,11 @@
 Follows, and is pinned by golden vectors generated from, the importable reference modules:
 ``cgd/losses.py:5-22``, ``cgd/modules.py:5-66``, ``cgd/clip_util.py:45`` and the ``cond_fn`` closure
 ``cgd/cgd.py:151-239`` (which cannot itself be imported: its module imports clip/lpips).
-Goldens: ``tests/golden/guidance_golden.npz`` made by ``tests/golden/make_golden.py``.
+Goldens: ``tests/golden/guidance_golden.npz`` made by ``tests/golden/make_golden.py``; the ``cond_fn`` restatement
+(``OracleCondFn`` / ``guidance_loss`` / ``magnitude_clamp``) is pinned on ``tests/golden/cond_fn_golden.npz``: what the reference's
+own closure returned when its unmodified source was cut out of ``cgd/cgd.py`` with ``ast`` and executed
+(``tests/golden/make_golden_cond_fn.py``, ``tests/test_cond_fn_reference.py``: 1e-5 incl. the whole-batch RMS clamp, the
+saturation term, several weighted prompts, a non-square image).
 """
 from __future__ import annotations
 
