@@ -88,3 +88,21 @@ def test_offsets_that_break_the_skip_connections_are_a_clear_error(tmp_path, mon
     from clip_guided_diffusion_b200 import guidance as pg
     with pytest.raises(ValueError, match="multiples of 32 for this 6-level UNet"):
         pg.GuidedStepB200(pu.config_for(256, True), {}, None, None, batch=1, height=264, device="cpu")
+
+
+def _driver_golden():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "driver_loop_golden.json")))
+
+
+@pytest.mark.parametrize("k", [i for i, g in enumerate(_driver_golden()) if g["respacing"] == "25" or g["skip"] >= 20])
+def test_saved_frames_follow_the_reference_driver_loop(k, tmp_path, monkeypatch):
+    """which (batch_idx, step) frames are yielded, against the reference's own loop statements executed on stand-ins
+    (tests/golden/make_golden_driver_loop.py: cgd/cgd.py:241-271 cut out with `ast`) -- including quirk B2: `current_timestep` starts at
+    num_timesteps - 1 whatever `skip_timesteps` is, so with skipped steps it never reaches -1 and the final frame is only saved when
+    its step index happens to be a multiple of `save_frequency`"""
+    g = _driver_golden()[k]
+    got = _call(tmp_path, monkeypatch, dict(timestep_respacing=g["respacing"], skip_timesteps=g["skip"], save_frequency=g["save_frequency"],
+                                            batch_size=g["batch"]))
+    steps = [[b, int(os.path.basename(p).split(".")[0])] for b, p in got]
+    assert steps == g["yields"], (g, steps)
