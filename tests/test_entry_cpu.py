@@ -86,3 +86,33 @@ def test_entry_helpers_match_the_reference_functions(tmp_path, monkeypatch):
     assert path == g["path"] and os.path.exists("current.png") == g["current_png"]
     assert np.array_equal(np.asarray(Image.open(path)), np.asarray(g["pixels"], dtype=np.uint8))
     assert np.array_equal(np.asarray(Image.open("current.png")), np.asarray(g["pixels"], dtype=np.uint8))
+
+
+def test_checkpoints_are_found_under_checkpoints_dir_by_the_reference_file_names(tmp_path):
+    """`checkpoints_dir/<DIFFUSION_LOOKUP filename>` and `checkpoints_dir/clip/<CLIP_MODEL_URLS basename>` (cgd/script_util.py:18,
+    cgd/clip_util.py:32-37): a plain state_dict file and a TorchScript archive (what OpenAI ships) both load; a missing file is a
+    FileNotFoundError that names the path and the keyword to pass instead"""
+    usd = {"a.weight": th.randn(3, 3)}
+    th.save(usd, tmp_path / "256x256_diffusion_uncond.pt")
+    got = cgd._load_unet_sd(256, False, str(tmp_path))
+    assert th.equal(got["a.weight"], usd["a.weight"])
+    with pytest.raises(FileNotFoundError, match="64x64_diffusion.pt"):
+        cgd._load_unet_sd(64, True, str(tmp_path))
+    with pytest.raises(ValueError, match="no published"):
+        cgd._load_unet_sd(64, False, str(tmp_path))
+    os.makedirs(tmp_path / "clip")
+    th.save({"visual.proj": th.randn(4, 2)}, tmp_path / "clip" / "ViT-B-16.pt")  # plain dict: th.jit.load refuses it, th.load takes it
+    assert tuple(cgd._load_clip_sd("ViT-B/16", str(tmp_path))["visual.proj"].shape) == (4, 2)
+
+    class M(th.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.visual = th.nn.Linear(2, 4)
+
+        def forward(self, x):
+            return self.visual(x)
+
+    th.jit.script(M()).save(str(tmp_path / "clip" / "ViT-L-14-336px.pt"))  # a TorchScript archive
+    assert set(cgd._load_clip_sd("ViT-L/14@336px", str(tmp_path))) == {"visual.weight", "visual.bias"}
+    with pytest.raises(FileNotFoundError, match="RN50.pt"):
+        cgd._load_clip_sd("RN50", str(tmp_path))
