@@ -85,7 +85,11 @@ def clip_checkpoint_filename(clip_model_name: str) -> str:
 
 
 def _load_clip_sd(clip_model_name, checkpoints_dir):
-    path = os.path.join(checkpoints_dir, "clip", clip_checkpoint_filename(clip_model_name))
+    # the reference keeps CLIP archives under CACHE_PATH/clip whatever checkpoints_dir is (cgd/clip_util.py:32-37); look there too
+    fname = clip_checkpoint_filename(clip_model_name)
+    path = os.path.join(checkpoints_dir, "clip", fname)
+    if not os.path.exists(path) and os.path.exists(os.path.join(CACHE_PATH, "clip", fname)):
+        path = os.path.join(CACHE_PATH, "clip", fname)
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} not found: pass clip_state_dict=...")
     try:
