@@ -180,6 +180,8 @@ def clip_guided_diffusion(
         raise RuntimeError("The weights must not sum to 0.")
     weights = weights / weights.sum().abs()  # cgd/cgd.py:102-105
 
+    if noise_schedule not in ("linear", "cosine"):  # cgd/script_util.py:302-303
+        raise ValueError("linear_or_cosine must be set")
     unet_cfg = config_for(image_size, class_cond)
     # CLI semantics (cgd/script_util.py:307-315): user noise_schedule overrides the checkpoint flag; rescale_timesteps from the flags
     unet_sd = unet_state_dict if unet_state_dict is not None else _load_unet_sd(image_size, class_cond, checkpoints_dir)

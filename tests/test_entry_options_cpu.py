@@ -106,3 +106,8 @@ def test_saved_frames_follow_the_reference_driver_loop(k, tmp_path, monkeypatch)
                                             batch_size=g["batch"]))
     steps = [[b, int(os.path.basename(p).split(".")[0])] for b, p in got]
     assert steps == g["yields"], (g, steps)
+
+
+def test_noise_schedule_is_validated_like_load_guided_diffusion(tmp_path, monkeypatch):
+    with pytest.raises(ValueError, match="linear_or_cosine"):  # cgd/script_util.py:302-303
+        _call(tmp_path, monkeypatch, dict(noise_schedule="sqrt"))
