@@ -114,3 +114,48 @@ def test_oracle_cutouts_and_losses_equal_the_reference_modules_on_random_inputs(
             assert th.equal(got, want)
             w = th.randn(want.shape, generator=g)
             assert th.equal(th.autograd.grad((got * w).sum(), x)[0], th.autograd.grad((want * w).sum(), x)[0])
+
+
+def test_oracle_cond_fn_equals_the_live_reference_closure_on_random_configurations():
+    """the committed cond_fn goldens widened: 40 random (batch, prompts, image size, cutouts, power, chain length, timestep, scales,
+    saturation, magnitude) configurations, reference closure (cgd/cgd.py:151-239, compiled from its source) vs `OracleCondFn`"""
+    import importlib.util
+    import types
+    from oracle import diffusion as od
+    from oracle import guidance as og
+    _ref_modules()
+    spec = importlib.util.spec_from_file_location("make_golden_cond_fn", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_cond_fn.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    while REF in sys.path[:1]:  # the script puts the reference first on sys.path for its own run: move it back behind this repository
+        sys.path.remove(REF)
+        sys.path.append(REF)
+    from cgd.modules import MakeCutouts as RefMakeCutouts
+    code = mg.reference_cond_fn_code()
+    rng = random.Random(3)
+    for trial in range(40):
+        B = rng.choice([1, 1, 2, 3])
+        P = 1 if B > 1 else rng.choice([1, 2, 4])  # quirk B1: the broadcast is only defined for B == 1 or P == 1
+        H = rng.choice([32, 40, 48, 64])
+        W = rng.choice([w for w in (32, 40, 48, 64) if w <= H])
+        cutn, power, T = rng.randint(1, 7), rng.choice([1.0, 0.5, 2.0]), rng.choice([25, 50, 100])
+        t, sat, mag = rng.randrange(T), rng.choice([0.0, 0.0, 12.5]), rng.random() < 0.5
+        scales = dict(clip_guidance_scale=rng.choice([1000, 250.0]), tv_scale=rng.choice([150, 0.0, 20.0]), range_scale=rng.choice([50, 5.0]))
+        g = th.Generator().manual_seed(1000 + trial)
+        x = th.randn(B, 3, H, W, generator=g) * rng.choice([0.5, 1.0, 1.6])
+        target = th.randn(P, 16, generator=g)
+        w = th.randn(P, generator=g).abs() + 0.1
+        w = w / w.sum().abs()
+        diff = od.create_gaussian_diffusion(1000, "linear", str(T))
+        ns = mg.make_closure(code, diffusion=types.SimpleNamespace(num_timesteps=T, sqrt_one_minus_alphas_cumprod=diff.sqrt_one_minus_alphas_cumprod),
+                             current_timestep=t, num_cutouts=cutn, make_cutouts=RefMakeCutouts(32, cutn, cutout_size_power=power), clip_model=mg.StubClip(32, 16),
+                             target_embeds=target, weights=w, sat_scale=sat, use_saturation=sat != 0, use_magnitude=mag, **scales)
+        th.manual_seed(trial)
+        xr = x.clone().requires_grad_()
+        want = ns["cond_fn"](xr, th.full((B,), t), {"pred_xstart": mg.stub_pred_xstart(xr)}).detach()
+        cond = og.OracleCondFn(diff, mg.StubClip(32, 16), target, w, cut_size=32, num_cutouts=cutn, cutout_power=power, sat_scale=sat, use_magnitude=mag, **scales)
+        cond.current_timestep = t
+        th.manual_seed(trial)
+        xr = x.clone().requires_grad_()
+        got = cond(xr, th.full((B,), t), {"pred_xstart": mg.stub_pred_xstart(xr)})
+        assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-12, (trial, B, P, H, W, cutn, T, t, sat, mag)
